@@ -1,0 +1,143 @@
+"""Literal problem data copied *as data* from the reference's own tests/examples
+(SURVEY.md section 8c, G1..G14).  Each builder returns ``(P, q, constraints)``
+in the reference's user-facing form (A x + b in K) using oracle cone classes;
+``expected`` holds the reference's known answers and tolerances.
+"""
+import numpy as np
+import scipy.sparse as sp
+
+from oracle import cosmo_oracle as O
+
+
+def g1_qp_nonneg():
+    """examples/qp.jl:13-27 — x*=[0.3,0.7], obj=1.88 (tol 1e-3)."""
+    q = np.array([1.0, 1.0])
+    P = np.array([[4.0, 1.0], [1.0, 2.0]])
+    A = np.array([[1.0, 1.0], [1.0, 0.0], [0.0, 1.0]])
+    l = np.array([1.0, 0.0, 0.0])
+    u = np.array([1.0, 0.7, 0.7])
+    Aa = np.vstack([-A, A])
+    ba = np.concatenate([u, -l])
+    return P, q, [O.Constraint(Aa, ba, O.Nonnegatives(6))]
+
+
+def g1_qp_box():
+    """examples/qp.jl:31-35."""
+    q = np.array([1.0, 1.0])
+    P = np.array([[4.0, 1.0], [1.0, 2.0]])
+    A = np.array([[1.0, 1.0], [1.0, 0.0], [0.0, 1.0]])
+    l = np.array([1.0, 0.0, 0.0])
+    u = np.array([1.0, 0.7, 0.7])
+    return P, q, [O.Constraint(A, np.zeros(3), O.Box(l, u))]
+
+
+G1_X = np.array([0.3, 0.7])
+G1_OBJ = 1.88
+
+
+def g2_box_feasible():
+    """test/UnitTests/qp-box.jl:15-32 — Solved, obj=-0.5 (atol 1e-5)."""
+    A = np.eye(2)
+    return np.eye(2), np.array([1.0, -1.0]), [O.Constraint(A, np.zeros(2), O.Box([0.0, 0.0], [1.0, 1.0]))]
+
+
+def g2_box_primal_infeasible_1():
+    """qp-box.jl:35-52 — Primal_infeasible."""
+    A = np.array([[1.0, 0.0], [1.0, 0.0]])
+    return np.eye(2), np.array([1.0, -1.0]), [O.Constraint(A, np.array([2.0, 0.0]), O.Box([0.0, 0.0], [1.0, 1.0]))]
+
+
+def g2_box_primal_infeasible_2():
+    """qp-box.jl:54-71 — Primal_infeasible."""
+    A = np.array([[1.0, 0.0], [1.0, 0.0]])
+    return np.eye(2), np.array([1.0, -1.0]), [O.Constraint(A, np.zeros(2), O.Box([0.0, 2.0], [1.0, 3.0]))]
+
+
+def g2_box_dual_infeasible():
+    """qp-box.jl:73-106 — Dual_infeasible (scaling=0/check_infeasibility=20 and scaling=10/40)."""
+    A = np.eye(2)
+    return np.zeros((2, 2)), np.array([1.0, 1.0]), [O.Constraint(A, np.ones(2), O.Box([0.0, -np.inf], [1.0, 3.0]))]
+
+
+def g12_lp():
+    """examples/lp.jl:17-46 — x*=[3,5,1,1], obj=20 (atol 1e-2); eps_abs=1e-4, eps_rel=1e-5."""
+    c = np.array([1.0, 2.0, 3.0, 4.0])
+    n = 4
+    I = np.eye(4)
+    c1 = O.Constraint(-I, 10.0 * np.ones(4), O.Nonnegatives(4))
+    c2 = O.Constraint(I, -np.ones(4), O.Nonnegatives(4))
+    A3 = np.zeros((1, n)); A3[0, 1] = 1.0          # Constraint(1, -5, Nonnegatives, n, 2:2)
+    c3 = O.Constraint(A3, np.array([-5.0]), O.Nonnegatives(1))
+    c4 = O.Constraint(np.array([[1.0, 0.0, 1.0, 0.0]]), np.array([-4.0]), O.Nonnegatives(1))
+    return np.zeros((4, 4)), c, [c1, c2, c3, c4]
+
+
+G12_X = np.array([3.0, 5.0, 1.0, 1.0])
+G12_OBJ = 20.0
+
+
+def svec_index(i, j):
+    """0-based position of (i,j), i<=j, in the column-major upper triangle (convexset.jl:432-442)."""
+    return j * (j + 1) // 2 + i
+
+
+def g13_lovasz_petersen():
+    """examples/lovasz_petersen.jl:22-60 — theta(Petersen) = 4.
+
+    JuMP form: max sum(X) s.t. tr X = 1, X_ij = 0 on edges, X PSD.  Restated in
+    COSMO's native svec form: variable x = svec(X) (off-diagonals * sqrt2),
+    min -<J, X> = -(sum_diag x + sqrt2 * sum_offdiag x).
+    """
+    n = 10
+    edges = [(1, 2), (1, 5), (1, 6), (2, 3), (2, 7), (3, 4), (3, 8), (4, 5), (4, 9), (5, 10),
+             (6, 8), (6, 9), (7, 9), (7, 10), (8, 10)]
+    d = n * (n + 1) // 2
+    q = np.zeros(d)
+    for j in range(n):
+        for i in range(j + 1):
+            q[svec_index(i, j)] = -1.0 if i == j else -np.sqrt(2.0)
+    rows = [np.zeros(d)]
+    for j in range(n):
+        rows[0][svec_index(j, j)] = 1.0
+    bz = [-1.0]
+    for (a, b) in edges:
+        r = np.zeros(d)
+        r[svec_index(a - 1, b - 1)] = 1.0
+        rows.append(r)
+        bz.append(0.0)
+    Az = np.vstack(rows)
+    cz = O.Constraint(Az, np.array(bz), O.ZeroSet(len(bz)))
+    cp = O.Constraint(sp.identity(d, format="csr"), np.zeros(d), O.PsdConeTriangle(d))
+    return np.zeros((d, d)), q, [cz, cp]
+
+
+G13_OBJ = -4.0
+
+
+def g3_hs21():
+    """test/UnitTests/moi_wrapper.jl:219-276 — HS21 (Maros-Meszaros) with redundant
+    constraints added in unsorted order to exercise set merging / sorting.
+    Known answers: obj = -99.96 (= 0.5 x'Px + r, r = -100), x = [-2, 0]; set order
+    Zero / Nonneg / Box / SOC.  Restated through the native Constraint form
+    (A x + b in K) instead of MOI."""
+    P = np.diag([0.02, 2.0])
+    q = np.zeros(2)
+    A = np.array([[-10.0, 1.0], [-1.0, 0.0], [0.0, -1.0]])
+    x_true = np.array([-2.0, 0.0])
+    nn1 = O.Constraint(A[0:1, :], np.array([-10.0]), O.Nonnegatives(1))            # A1 x >= 10
+    soc = O.Constraint(np.array([[-1.0, 0.0], [0.0, 1.0]]), np.zeros(2), O.SecondOrderCone(2))
+    box1 = O.Constraint(A[1:2, :], np.zeros(1), O.Box([2.0], [50.0]))
+    zero1 = O.Constraint(np.array([[1.0, 0.0]]), np.array([2.0]), O.ZeroSet(1))      # x1 == -2
+    nn2 = O.Constraint(-np.eye(2), 10.0 * np.ones(2), O.Nonnegatives(2))            # x - 10 <= 0
+    box2 = O.Constraint(A[2:3, :], np.zeros(1), O.Box([-50.0], [50.0]))
+    zeroset = O.Constraint(np.eye(2), -x_true, O.ZeroSet(2))
+    return P, q, [nn1, soc, box1, zero1, nn2, box2, zeroset]
+
+
+G3_X = np.array([-2.0, 0.0])
+G3_OBJ = -99.96 + 100.0  # the constant r = -100 is carried outside the solver
+
+
+def g14_update_qp():
+    """test/UnitTests/model_modifications.jl:33-47: G1 then update!(q=[2,3]) -> obj 3.5? (x=[0.5,0.5])."""
+    return g1_qp_nonneg()

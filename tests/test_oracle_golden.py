@@ -1,0 +1,174 @@
+"""Pin the CPU oracle against the reference's own literal known answers
+(G1, G2, G3, G8, G12, G13, G14) before it is trusted as the checker."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import cosmo_oracle as O
+from tests import golden_problems as G
+
+
+def _solve(builder, **kw):
+    P, q, cons = builder()
+    Pm, qm, A, b, cones = O.assemble(P, q, cons)
+    return O.solve(Pm, qm, A, b, cones, O.Settings(**kw)), cones
+
+
+@pytest.mark.parametrize("builder", [G.g1_qp_nonneg, G.g1_qp_box])
+@pytest.mark.parametrize("kkt", ["direct", "cg", "minres", "minres_reduced"])
+@pytest.mark.parametrize("scaling", [0, 10])
+def test_g1_simple_qp(builder, kkt, scaling):
+    # examples/qp.jl:41-44, test/UnitTests/simple.jl:21-47 (tol 1e-3)
+    res, _ = _solve(builder, kkt_solver=kkt, scaling=scaling)
+    if kkt in ("direct", "cg"):
+        assert res.status == "Solved"
+    else:
+        # MINRES: the reference passes abstol = tol_k / |initial residual|
+        # (kktsolver_indirect.jl:72-73,151-152), which *loosens* as the initial
+        # residual shrinks; the restated recurrence therefore plateaus near 3e-4
+        # and exits with Max_iter_reached.  The reference has no active test for
+        # this path (kktsolver.jl:7-8) -> parity unpinned; only accuracy is asserted.
+        assert res.status in ("Solved", "Max_iter_reached")
+    assert np.max(np.abs(res.x - G.G1_X)) < 1e-3
+    assert abs(res.obj_val - G.G1_OBJ) < 1e-3
+
+
+def test_g1_matches_survey_iteration_count():
+    # 375 iterations at eps 1e-5 with scaling=0, fixed rho, dense KKT
+    res, _ = _solve(G.g1_qp_nonneg, scaling=0, adaptive_rho=False)
+    assert res.status == "Solved" and res.iter == 375
+
+
+def test_g2_box():
+    res, _ = _solve(G.g2_box_feasible)
+    assert res.status == "Solved"
+    assert abs(res.obj_val - (-0.5)) < 1e-5  # qp-box.jl:31
+    res, _ = _solve(G.g2_box_primal_infeasible_1)
+    assert res.status == "Primal_infeasible"  # qp-box.jl:51
+    res, _ = _solve(G.g2_box_primal_infeasible_2)
+    assert res.status == "Primal_infeasible"  # qp-box.jl:70
+    res, _ = _solve(G.g2_box_dual_infeasible, check_infeasibility=20, scaling=0)
+    assert res.status == "Dual_infeasible"    # qp-box.jl:88
+    res, _ = _solve(G.g2_box_dual_infeasible, check_infeasibility=40, scaling=10)
+    assert res.status == "Dual_infeasible"    # qp-box.jl:105
+
+
+def test_g3_hs21_set_merging():
+    res, cones = _solve(G.g3_hs21)
+    # moi_wrapper.jl:266-271 (native assemble keeps the two Box sets separate)
+    kinds = [type(c).__name__ for c in cones]
+    assert kinds == ["ZeroSet", "Nonnegatives", "Box", "Box", "SecondOrderCone"]
+    assert cones[0].dim == 3 and cones[1].dim == 3
+    assert res.status == "Solved"
+    assert abs(res.obj_val - G.G3_OBJ) < 1e-3
+    assert np.max(np.abs(res.x - G.G3_X)) < 1e-3
+
+
+@pytest.mark.parametrize("kkt", ["direct", "cg"])
+def test_g12_lp(kkt):
+    res, _ = _solve(G.g12_lp, eps_abs=1e-4, eps_rel=1e-5, kkt_solver=kkt)
+    assert res.status == "Solved"
+    assert np.max(np.abs(res.x - G.G12_X)) < 1e-2  # lp.jl:44
+    assert abs(res.obj_val - G.G12_OBJ) < 1e-2     # lp.jl:46
+
+
+@pytest.mark.parametrize("scaling", [0, 10])
+def test_g13_lovasz_petersen(scaling):
+    res, _ = _solve(G.g13_lovasz_petersen, scaling=scaling, eps_abs=1e-6, eps_rel=1e-6)
+    assert res.status == "Solved"
+    assert abs(res.obj_val - G.G13_OBJ) < 1e-3
+
+
+def test_g14_model_updates():
+    # model_modifications.jl:20-31: second optimize! warm-starts from the first
+    P, q, cons = G.g1_qp_nonneg()
+    Pm, qm, A, b, cones = O.assemble(P, q, cons)
+    ws = O.Workspace(Pm, qm, A, b, cones, O.Settings(check_termination=1))
+    r1 = ws.optimize()
+    r2 = ws.optimize()
+    assert abs(r1.obj_val - r2.obj_val) <= 1e-3 and r2.iter <= r1.iter
+    # :33-43 update!(q=[2,3]) -> obj 3.5, x=[0.5,0.5]
+    ws = O.Workspace(Pm, qm, A, b, cones, O.Settings())
+    ws.optimize()
+    ws.update(q=np.array([2.0, 3.0]))
+    r = ws.optimize()
+    assert abs(r.obj_val - 3.5) < 1e-3 and np.linalg.norm(r.x - [0.5, 0.5]) < 1e-3
+    # :45-61 LP, update!(b=[0,1]) -> x=[0,-1]
+    Pm, qm, A, b, cones = O.assemble(np.zeros((2, 2)), np.array([1.0, 1.0]),
+                                     [O.Constraint(np.eye(2), np.array([-2.0, -3.0]), O.Nonnegatives(2))])
+    ws = O.Workspace(Pm, qm, A, b, cones, O.Settings(check_termination=20))
+    r = ws.optimize()
+    assert np.linalg.norm(r.x - [2.0, 3.0]) < 1e-3
+    ws.update(b=np.array([0.0, 1.0]))
+    r2 = ws.optimize()
+    assert np.linalg.norm(r2.x - [0.0, -1.0]) < 1e-4
+
+
+def test_g8_algebra_kats():
+    # test/UnitTests/algebra.jl:31-60
+    E = np.array([1.0, 2.0, 3.0])
+    v = np.array([-1.0, 5.0, 4.0])
+    assert O.scaled_norm(E, v, 1) == 23
+    assert O.scaled_norm(E, v, 2) == np.linalg.norm([-1.0, 10.0, 12.0])
+    assert O.scaled_norm(E, v, np.inf) == 12
+    with pytest.raises(ValueError):
+        O.scaled_norm(E, v, 3)
+    A = sp.csc_matrix(np.array([[1.0, 2, 3, 4], [2, -1, 30, 4.1]]))
+    B = sp.csc_matrix(np.array([[1.0, 3, -2, 4.2], [-100, -1, -2, -100]]))
+    vv = O.col_norms(A)
+    assert np.array_equal(vv, [2, 2, 30, 4.1])
+    O.col_norms(B, vv)
+    assert np.array_equal(vv, [100, 3, 30, 100])
+    vv = O.row_norms(A.T)
+    O.row_norms(B.T, vv)
+    assert np.array_equal(vv, [100, 3, 30, 100])
+    x = np.linspace(-5, 5, 50); x[9] = -8; x[19] = 8
+    xc = O.clip(x, -2, 2)
+    assert xc.max() <= 2 and xc.min() >= -2
+    xc2 = O.clip(x, -2, 2, -100, 100)
+    assert xc2[9] == -100 and xc2[19] == 100
+
+
+def test_g9_cone_membership_and_projection():
+    # test/UnitTests/sets.jl:27-112 — projections land in the cone (property tests)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(10)
+    O.project_cone(x, O.SecondOrderCone(10))
+    assert np.linalg.norm(x[1:]) <= x[0] + 1e-12
+    X = rng.standard_normal((4, 4)); X = X + X.T
+    xs = X.reshape(-1, order="F").copy()
+    O.project_cone(xs, O.PsdCone(16))
+    assert np.linalg.eigvalsh(xs.reshape(4, 4, order="F")).min() >= -1e-9
+    xt = O.extract_upper_triangle(X, np.sqrt(2.0))
+    O.project_cone(xt, O.PsdConeTriangle(10))
+    Xp = O.populate_upper_triangle(xt, 4, 1 / np.sqrt(2.0))
+    Xp = Xp + np.triu(Xp, 1).T
+    assert np.linalg.eigvalsh(Xp).min() >= -1e-9
+    # triangle and square projections agree
+    assert np.allclose(Xp, xs.reshape(4, 4, order="F"), atol=1e-12)
+    # exact eigen-clip reference
+    w, V = np.linalg.eigh(X)
+    assert np.allclose(Xp, (V * np.maximum(w, 0)) @ V.T, atol=1e-12)
+    one = np.array([-3.0]); O.project_cone(one, O.PsdConeTriangle(1)); assert one[0] == 0.0
+
+
+def test_kkt_indirect_matches_direct():
+    # the reference's (disabled) test kktsolver.jl:96-125: CG/MINRES vs dense K\b, before/after update_rho!
+    rng = np.random.default_rng(1)
+    n, m = 10, 15
+    A = sp.random(m, n, density=0.4, random_state=2, format="csc")
+    Pd = sp.random(n, n, density=0.4, random_state=3); P = sp.csc_matrix(Pd @ Pd.T)
+    rho = 0.1 * np.ones(m)
+    st = O.Settings()
+    rhs = rng.standard_normal(n + m)
+    for name in ["cg", "minres_reduced", "minres"]:
+        S = O.make_kkt_solver(name, P, A, 1e-6, rho.copy(), st)
+        S.iteration_counter = 10 ** 6  # tight tolerance
+        D = O.DirectKKT(P, A, 1e-6, rho)
+        assert np.allclose(S.solve(rhs), D.solve(rhs), atol=1e-5), name
+        rho2 = rng.uniform(0.05, 0.5, m)
+        S.update_rho(rho2); D.update_rho(rho2)
+        for _ in range(3):  # maxiter = size(A,2) per call; warm start carries over
+            S.iteration_counter = 10 ** 6
+            sol = S.solve(rhs)
+        assert np.allclose(sol, D.solve(rhs), atol=1e-5), name
