@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py -- ADMM iterations/sec of the B200 engine on BASELINE config C2.
+
+A "step" is one ADMM iteration (one pass of the hot loop, solver.jl:140-165) on
+the random sparse QP n=50k, m=100k, 1% density (nnz(A)=5e7), Nonneg+Box cones,
+CG reduced-KKT solver, scaling=0, fixed rho, EmptyAccelerator.
+
+  value     iterations/s, problem resident in HBM, loop timed with CUDA events on
+            the engine stream (max over ranks).
+  e2e       same metric through the public C-ABI calls with HOST buffers:
+            update_qb + warm_start (H2D) + solve (K iterations) + result D2H,
+            wall-clocked around the calls.  The one-time model upload is the
+            analogue of the reference's `setup!`, which its own metric
+            (times.iter_time / iter) excludes as well; it is reported as setup_s.
+  roofline  dominant kernel = the CSR SpMV t = rho.*(A u): algorithmic bytes
+            (12 B/nnz + vectors) / CUDA-event time per launch.
+  cpu_baseline  the oracle port (oracle/cosmo_oracle.py) on this box's host cores,
+            bounded sample of the same workload.
+
+`--impl reference` times the oracle port (the reference cannot run here: no Julia).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ADMM iterations/sec"
+UNIT = "iter/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=50_000)
+    ap.add_argument("--m", type=int, default=100_000)
+    ap.add_argument("--density", type=float, default=0.01)
+    ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--cpu-sample-iters", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a, extra=None):
+    cfg = {"workload": "C2 random sparse QP n=%d m=%d density=%g (nnz(A)=%d), Nonnegatives(m/2)+Box(m/2), "
+                       "CGIndirectKKTSolver, scaling=0, adaptive_rho=false, EmptyAccelerator, cold start"
+                       % (a.n, a.m, a.density, int(round(a.density * a.m)) * a.n),
+           "n": a.n, "m": a.m, "seed": a.seed, "l2": "inputs_larger_than_L2 (A + A' = 1.2 GB streamed per operator application)",
+           "sharding": "rows of A / cones split across ranks, n-vectors replicated, one allreduce(sum) per operator application"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def oracle_iterations(P, q, A, b, sets, iters, warm):
+    """Time `iters` ADMM iterations of the oracle port after `warm` untimed ones (same settings)."""
+    import cosmo_b200
+    from oracle import cosmo_oracle as O
+    cones = cosmo_b200.problems.to_oracle_cones(sets)
+    marks = {}
+
+    def cb(it, ws):
+        marks[it] = time.perf_counter()
+
+    st = O.Settings(kkt_solver="cg", scaling=0, adaptive_rho=False, max_iter=warm + iters, eps_abs=0.0, eps_rel=0.0,
+                    check_termination=25, check_infeasibility=40)
+    ws = O.Workspace(P, q, A, b, cones, st)
+    t0 = time.perf_counter()
+    res = ws.optimize(iter_callback=cb)
+    tstart = marks[warm] if warm >= 1 else t0
+    dt = marks[warm + iters] - tstart
+    inner = res.kkt.inner_iterations
+    return dt, iters, float(np.mean(inner)) if inner else 0.0
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(a, rank, world):
+    if rank != 0:
+        return
+    import cosmo_b200
+    P, q, A, b, sets = cosmo_b200.problems.random_sparse_qp(a.n, a.m, a.density, a.seed)
+    # bounded sample: SciPy's compiled single-threaded CSC mat-vec, like Julia's SparseArrays.mul!
+    scale = (a.n * a.m * a.density) / 5e7
+    cap = max(2, int(8 / max(scale, 1e-3))) if scale > 0.2 else 200
+    iters = max(1, min(a.steps, cap))
+    warm = max(0, min(a.warmup, 1 if scale > 0.2 else a.warmup))
+    dt, iters, cg = oracle_iterations(P, q, A, b, sets, iters, warm)
+    val = iters / dt
+    sample = "%d ADMM iterations after %d warm-up (of the requested %d/%d), oracle port: SciPy CSC mat-vec, 1 thread" % (
+        iters, warm, a.steps, a.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": iters,
+            "warmup": warm, "ms_per_step": 1e3 * dt / iters, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(a, {"cg_iters_per_admm_iter": cg}),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                             "host_cores_available": host_cores()},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    a = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+        return
+
+    import torch
+    import cosmo_b200
+    from cosmo_b200 import sharding
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the engine has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # ---- problem (identical on every rank: same seed) ---------------------------------
+    t0 = time.perf_counter()
+    P, q, A, b, sets = cosmo_b200.problems.random_sparse_qp(a.n, a.m, a.density, a.seed)
+    gen_s = time.perf_counter() - t0
+    n, m = a.n, a.m
+    settings = cosmo_b200.Settings(scaling=0, adaptive_rho=False, max_iter=a.steps, eps_abs=0.0, eps_rel=0.0)
+
+    t0 = time.perf_counter()
+    shard = sharding.make_shard(P, q, A, b, sets, rank, world)
+    eng = sharding.create_engine(shard, settings, device=local_rank, dist=dist)
+    setup_s = time.perf_counter() - t0
+    m_loc = shard.A.shape[0]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # pinned host buffers for the e2e leg
+    pin = lambda k: torch.empty(k, dtype=torch.float64).pin_memory().numpy()
+    hq, hb = pin(n), pin(m_loc)
+    hq[:] = shard.q; hb[:] = shard.b
+    hx0, hs0, hmu0 = pin(n), pin(m_loc), pin(m_loc)
+    hx0[:] = 0; hs0[:] = 0; hmu0[:] = 0
+    ox, os_, omu = pin(n), pin(m_loc), pin(m_loc)
+
+    def run(iters):
+        st = cosmo_b200.Settings(scaling=0, adaptive_rho=False, max_iter=iters, eps_abs=0.0, eps_rel=0.0).to_struct()
+        eng.update_settings(st)
+        eng.reset()
+        return eng.solve(ox, os_, omu)
+
+    # ---- warm-up --------------------------------------------------------------------------
+    barrier()
+    if a.warmup > 0:
+        run(max(a.warmup, 3))
+    # ---- timed: device-resident ---------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    out = run(a.steps)
+    barrier()
+    dev_s = out.times["iter_time_device"]
+    # ---- timed: end to end through the C ABI with host buffers ----------------------------------
+    st = cosmo_b200.Settings(scaling=0, adaptive_rho=False, max_iter=a.steps, eps_abs=0.0, eps_rel=0.0).to_struct()
+    eng.update_settings(st)
+    eng.reset()
+    barrier()
+    t0 = time.perf_counter()
+    eng.update_qb(hq, hb)
+    eng.warm_start(hx0, hs0, hmu0)
+    out2 = eng.solve(ox, os_, omu)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline of the dominant kernel (CUDA events on the engine stream) -------------------------
+    ms_A, bytes_A = eng.spmv_bench(0, 20)
+    ms_At, bytes_At = eng.spmv_bench(3, 20)
+
+    if dist is not None:
+        t = torch.tensor([dev_s, e2e_s, ms_A, ms_At], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_s, e2e_s, ms_A, ms_At = [float(v) for v in t.tolist()]
+        tb = torch.tensor([bytes_A, bytes_At], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tb, op=dist.ReduceOp.SUM)
+        bytes_A_all, bytes_At_all = [float(v) for v in tb.tolist()]
+    else:
+        bytes_A_all, bytes_At_all = bytes_A, bytes_At
+
+    if rank == 0:
+        peaks, peak_src = None, "fallback (B200_PROFILING.md: 6650 GB/s)"
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peak, peak_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+        except Exception:
+            peak = 6650.0
+        ach_A = bytes_A / (ms_A * 1e-3) / 1e9
+        ach_At = bytes_At / (ms_At * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "spmv_traffic.json"))).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        cg = out.kkt_inner_iterations / max(out.iter, 1)
+        line = {"metric": METRIC, "value": a.steps / dev_s, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": 1e3 * dev_s / a.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(a, {"cg_iters_per_admm_iter": cg, "setup_s": setup_s, "problem_gen_s": gen_s,
+                                              "kkt_multiplications": out.kkt_multiplications}),
+                "e2e": {"value": a.steps / e2e_s, "unit": UNIT,
+                        "h2d_bytes_per_step": 8.0 * (n + m_loc + n + 2 * m_loc) / a.steps,
+                        "d2h_bytes_per_step": 8.0 * (n + 2 * m_loc) / a.steps,
+                        "note": "update_qb + warm_start + solve(K iterations) + result download, host pinned buffers; "
+                                "model upload (setup!) excluded like in the reference's iter_time"},
+                "gpu_launches": int(out.kernel_launches),
+                "clocks": clocks,
+                "roofline": {"bound": "hbm", "kernel": "spmv_kernel<double,32,EpiScale> (t = rho.*(A u))",
+                             "achieved": ach_A, "peak": peak, "unit": "GB/s", "frac": ach_A / peak,
+                             "traffic": traffic, "peak_source": peak_src, "ms_per_launch": ms_A,
+                             "algorithmic_bytes_per_launch": bytes_A,
+                             "other": {"kernel": "spmv_kernel<double,32,EpiKktOp> (c = A't + P u + sigma u, dot)",
+                                       "achieved": ach_At, "frac": ach_At / peak, "ms_per_launch": ms_At,
+                                       "algorithmic_bytes_per_launch": bytes_At}}}
+        if not a.no_cpu_baseline and world == 1:
+            scale = (a.n * a.m * a.density) / 5e7
+            it_cpu = a.cpu_sample_iters if scale > 0.2 else 50
+            dt, iters, cgc = oracle_iterations(P, q, A, b, sets, it_cpu, 0)
+            line["cpu_baseline"] = {"value": iters / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": "first %d ADMM iterations of the same workload (cold start, %.1f CG its/iter), "
+                                              "oracle port: SciPy CSC mat-vec single thread like SparseArrays.mul!" % (iters, cgc),
+                                    "host_cores_available": host_cores()}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,10 @@
+"""cosmo_b200: B200-native ADMM iteration engine behind COSMO.jl's solver API.
+
+The directory is named ``cosmo.jl_b200`` (not importable as written); the
+top-level shim ``cosmo_b200.py`` registers it under the name ``cosmo_b200``.
+"""
+from .engine import Engine, EngineError, default_settings, load_library, nccl_unique_id  # noqa: F401
+from .model import (Box, Constraint, Model, Nonnegatives, PsdCone, PsdConeTriangle, Result, ResultInfo,  # noqa: F401
+                    SecondOrderCone, Settings, ZeroSet, assemble, optimize, ruiz_equilibrate)
+from . import problems  # noqa: F401
+from . import sharding  # noqa: F401,E402

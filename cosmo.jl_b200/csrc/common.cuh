@@ -1,0 +1,132 @@
+// common.cuh -- shared device helpers for the COSMO B200 engine (sm_100a).
+//
+// * streaming 128-bit loads for the CSR value / index streams (read once per
+//   SpMV: keep them out of L1 so the gathered vector stays resident),
+// * a deterministic multi-output block reduction with a "last block" second
+//   stage: every kernel that produces scalars (dots, norms, inf-norms) writes
+//   per-block partials, the last block to finish folds them in a fixed order
+//   and runs a tiny scalar epilogue (the `finalize` functor).  No floating-point
+//   atomics anywhere => bitwise reproducible runs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cosmo {
+
+constexpr int kBlock = 256;           // threads per block for every reducing kernel
+constexpr int kWarpsPerBlock = kBlock / 32;
+constexpr int kMaxGrid = 148 * 8;     // 148 SMs x 8 resident 256-thread blocks
+constexpr int kMaxRed = 8;            // max reduction slots per kernel
+
+template <typename T>
+struct CsrView {
+  const int* rowptr;  // nrows+1 (nullptr => matrix absent)
+  const int* col;
+  const T* val;
+};
+
+// per-stream scratch for the two-stage reductions
+template <typename T>
+struct RedBuf {
+  T* partials;        // kMaxGrid * kMaxRed
+  T* out;             // where the folded scalars go (NS sums then NM maxes)
+  unsigned* ticket;   // zero between kernels
+};
+
+// ---- streaming loads --------------------------------------------------------
+__device__ __forceinline__ void load4_stream(const double* p, double (&v)[4]) {
+  double2 a = __ldcs(reinterpret_cast<const double2*>(p));
+  double2 b = __ldcs(reinterpret_cast<const double2*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void load4_stream(const float* p, float (&v)[4]) {
+  float4 a = __ldcs(reinterpret_cast<const float4*>(p));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+__device__ __forceinline__ int4 load4_stream(const int* p) {
+  return __ldcs(reinterpret_cast<const int4*>(p));
+}
+
+// NaN-propagating max of non-negative magnitudes (Julia's norm(x, Inf) returns NaN
+// when an entry is NaN; fmax would silently drop it).
+template <typename T>
+__device__ __forceinline__ T nanmax(T a, T b) {
+  return (a > b || a != a) ? a : b;
+}
+
+template <typename T>
+__device__ __forceinline__ T tabs(T a) { return a < 0 ? -a : a; }
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_nanmax(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = nanmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Fold per-thread accumulators (NS sums, NM maxes) over the block, publish the
+// block partial, and let the last block fold all partials and call fin(out).
+// Must be called by all kBlock threads of every block of the grid.
+template <typename T, int NS, int NM, typename Fin>
+__device__ __forceinline__ void reduce_and_finalize(const T* accS, const T* accM, const RedBuf<T>& rb,
+                                                    const Fin& fin) {
+  constexpr int NR = NS + NM;
+  static_assert(NR >= 1 && NR <= kMaxRed, "reduction slots");
+  __shared__ T sm[kWarpsPerBlock][NR];
+  __shared__ int is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NS; ++k) {
+    T v = warp_sum(accS[k]);
+    if (lane == 0) sm[warp][k] = v;
+  }
+#pragma unroll
+  for (int k = 0; k < NM; ++k) {
+    T v = warp_nanmax(accM[k]);
+    if (lane == 0) sm[warp][NS + k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NR) {
+    const int k = threadIdx.x;
+    T v = sm[0][k];
+    for (int w = 1; w < kWarpsPerBlock; ++w) v = (k < NS) ? v + sm[w][k] : nanmax(v, sm[w][k]);
+    rb.partials[(size_t)blockIdx.x * NR + k] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = atomicAdd(rb.ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    for (int k = warp; k < NR; k += kWarpsPerBlock) {
+      T v = 0;
+      for (int b = lane; b < (int)gridDim.x; b += 32) {
+        T p = __ldcg(rb.partials + (size_t)b * NR + k);
+        v = (k < NS) ? v + p : nanmax(v, p);
+      }
+      v = (k < NS) ? warp_sum(v) : warp_nanmax(v);
+      if (lane == 0) rb.out[k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      fin(rb.out);
+      *rb.ticket = 0u;
+    }
+  }
+}
+
+struct NoFin {
+  template <typename T>
+  __device__ void operator()(T*) const {}
+};
+
+}  // namespace cosmo

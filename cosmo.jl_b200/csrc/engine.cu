@@ -1,0 +1,1197 @@
+// engine.cu -- the B200-native ADMM iteration engine behind include/cosmo_b200.h.
+//
+// Host-side driver of the hot loop of COSMO.optimize! (reference
+// src/solver.jl:125-167, restated in SURVEY.md Appendix A) plus the C ABI.
+// All arithmetic runs in the hand-written sm_100a kernels of spmv.cuh,
+// vector_kernels.cuh and psd.cuh; the host only sequences launches, reads
+// back a handful of scalars at the reference's own decision points
+// (termination / infeasibility / rho-adaptation checks, CG convergence) and
+// never touches vector data.  There is no CPU fallback: without a CUDA device
+// every entry point fails with COSMO_B200_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+#include <string>
+#include <vector>
+
+#include "../../include/cosmo_b200.h"
+#include "common.cuh"
+#include "psd.cuh"
+#include "spmv.cuh"
+#include "vector_kernels.cuh"
+
+namespace cosmo {
+
+static thread_local std::string g_create_error;
+
+struct EngineError {
+  int code;
+  std::string msg;
+};
+
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) {                                                                        \
+      char _b[512];                                                                                 \
+      snprintf(_b, sizeof(_b), "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__,        \
+               __LINE__, cudaGetErrorString(_e));                                                   \
+      throw EngineError{COSMO_B200_ERR_CUDA, _b};                                                   \
+    }                                                                                               \
+  } while (0)
+
+static inline double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ---- NCCL through dlopen (the single-GPU path has no NCCL dependency) --------
+struct NcclUniqueId { char internal[128]; };
+typedef void* NcclComm;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+  int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*CommDestroy)(NcclComm) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool load(std::string& err) {
+    if (lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+      lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) { err = std::string("cannot dlopen libnccl: ") + dlerror(); return false; }
+    GetUniqueId = (int (*)(NcclUniqueId*))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (int (*)(NcclComm*, int, NcclUniqueId, int))dlsym(lib, "ncclCommInitRank");
+    AllReduce = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    CommDestroy = (int (*)(NcclComm))dlsym(lib, "ncclCommDestroy");
+    GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { err = "libnccl lacks required symbols"; return false; }
+    return true;
+  }
+};
+static NcclApi g_nccl;
+constexpr int kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2;
+
+// ---- device buffer -----------------------------------------------------------
+template <typename U>
+struct DevBuf {
+  U* p = nullptr;
+  size_t n = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { if (p) cudaFree(p); }
+  void alloc(size_t count, bool zero = true) {
+    if (p) { cudaFree(p); p = nullptr; }
+    n = count;
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(U);
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) throw EngineError{COSMO_B200_ERR_ALLOC, std::string("cudaMalloc failed: ") + cudaGetErrorString(e)};
+    if (zero) CUDA_TRY(cudaMemset(p, 0, bytes));
+  }
+  void upload(const U* host, size_t count, cudaStream_t st) {
+    if (count) CUDA_TRY(cudaMemcpyAsync(p, host, count * sizeof(U), cudaMemcpyHostToDevice, st));
+  }
+  void upload(const std::vector<U>& h, cudaStream_t st) {
+    if (n < h.size()) alloc(h.size(), false);
+    upload(h.data(), h.size(), st);
+  }
+};
+
+template <typename T>
+struct DevCsr {
+  int nrows = 0, ncols = 0;
+  long long nnz = 0;
+  DevBuf<int> rowptr, col;
+  DevBuf<T> val;
+  int lanes = 32;
+  CsrView<T> view() const { return CsrView<T>{rowptr.p, col.p, val.p}; }
+  double spmv_bytes() const {  // 12 nnz + 4 (rows+1) + 8 cols + 8 rows   (fp64)
+    return (double)nnz * (sizeof(T) + 4) + 4.0 * (nrows + 1) + (double)sizeof(T) * ncols + (double)sizeof(T) * nrows;
+  }
+};
+
+static int pick_lanes(double mean_row) {
+  if (mean_row > 24.0) return 32;
+  if (mean_row > 3.0) return 8;
+  return 2;
+}
+
+struct HostCsr {
+  int nrows = 0, ncols = 0;
+  std::vector<int> rowptr, col;
+  std::vector<double> val;  // staged in double, narrowed on upload when T=float
+};
+
+class EngineBase {
+ public:
+  virtual ~EngineBase() {}
+  std::string err;
+  virtual void update_settings(const cosmo_b200_settings& st) = 0;
+  virtual void warm_start(const void* x, const void* s, const void* mu) = 0;
+  virtual void update_qb(const void* q, const void* b) = 0;
+  virtual void update_rho(const void* rho_vec, double rho) = 0;
+  virtual void reset() = 0;
+  virtual void solve(cosmo_b200_result* out) = 0;
+  virtual void project(const void* ws, void* s_out) = 0;
+  virtual void kkt_solve(const void* rhs, void* sol, int64_t* inner) = 0;
+  virtual void residuals(const void* x, const void* s, const void* mu, int ignore_scaling, double* out) = 0;
+  virtual void spmv(int which, const void* x, void* y) = 0;
+  virtual void spmv_bench(int which, int reps, double* ms, double* bytes) = 0;
+  virtual void get_rho_vec(void* out) = 0;
+  virtual void get_w(void* out) = 0;
+  virtual void comm_init(int nranks, int rank, const void* id128) = 0;
+};
+
+template <typename T>
+class Engine : public EngineBase {
+ public:
+  Engine(const cosmo_b200_problem& p, const cosmo_b200_settings& st);
+  ~Engine() override;
+  void update_settings(const cosmo_b200_settings& st) override { st_ = st; }
+  void warm_start(const void* x, const void* s, const void* mu) override;
+  void update_qb(const void* q, const void* b) override;
+  void update_rho(const void* rho_vec, double rho) override;
+  void reset() override;
+  void solve(cosmo_b200_result* out) override;
+  void project(const void* ws, void* s_out) override;
+  void kkt_solve(const void* rhs, void* sol, int64_t* inner) override;
+  void residuals(const void* x, const void* s, const void* mu, int ignore_scaling, double* out) override;
+  void spmv(int which, const void* x, void* y) override;
+  void spmv_bench(int which, int reps, double* ms, double* bytes) override;
+  void get_rho_vec(void* out) override;
+  void get_w(void* out) override;
+  void comm_init(int nranks, int rank, const void* id128) override;
+
+ private:
+  // ---- problem ----
+  int n_ = 0, m_ = 0, device_ = 0;
+  cosmo_b200_settings st_;
+  bool scaled_ = false;
+  double c_ = 1.0;
+  DevCsr<T> A_, At_, P_;
+  DevBuf<T> q_, b_, D_, Dinv_, E_, Einv_;
+  std::vector<double> hb_;                       // host copy of b (row classification)
+  std::vector<double> hl_, hu_;                  // host box bounds (m-length, +-inf elsewhere)
+  std::vector<cosmo_b200_set> sets_;             // type + dim only
+  std::vector<int> set_off_;
+  // cones
+  DevBuf<unsigned char> row_class_, rho_class_;
+  DevBuf<int> row_cone_;
+  DevBuf<T> box_l_, box_u_;
+  int n_soc_ = 0, n_soc_chunks_ = 0;
+  DevBuf<int> soc_off_, soc_dim_, soc_chunk_start_, soc_chunk_len_, soc_cone_chunk_ptr_;
+  DevBuf<T> soc_norm_, soc_chunk_sum_, soc_norm2_;
+  PsdBatch<T> psd_;
+  // ---- state ----
+  DevBuf<T> W_[2];           // operator variable, ping-pong (w / w_prev)
+  int cur_ = 0, prev_ = 1;
+  DevBuf<T> xs_, s_, mu_;    // warm-start / exit copies of x; s; mu
+  DevBuf<T> rho_vec_;
+  double rho_ = 0.1;
+  std::vector<double> rho_updates_;
+  bool is_optimized_ = false;
+  // KKT (reduced CG)
+  DevBuf<T> ls_, t0_, tm_, xsol_, rhsb_, cb_, r_, u_, nu_;
+  long long kkt_counter_ = 1;   // S.iteration_counter
+  int last_cg_iters_ = 1;
+  long long total_inner_ = 0, total_mults_ = 0;
+  // scratch
+  DevBuf<T> vec_m_, vec_n_, vec_n2_, dy_, dx_;
+  DevBuf<T> sc_;       // device scalars
+  DevBuf<int> isc_;
+  DevBuf<T> partials_;
+  DevBuf<unsigned> ticket_;
+  T* h_sc_ = nullptr;  // pinned mirrors
+  int* h_isc_ = nullptr;
+  cudaStream_t stream_ = nullptr;
+  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+  long long launches_ = 0;
+  // multi-GPU
+  int nranks_ = 1, rank_ = 0;
+  NcclComm comm_ = nullptr;
+
+  // ---- helpers ----
+  RedBuf<T> red(int out_slot) { return RedBuf<T>{partials_.p, sc_.p + out_slot, ticket_.p}; }
+  RedBuf<T> red_ptr(T* out) { return RedBuf<T>{partials_.p, out, ticket_.p}; }
+  static int vgrid(long long n) { return (int)std::min<long long>(std::max<long long>((n + kBlock - 1) / kBlock, 1), kMaxGrid); }
+  static int sgrid(long long rows, int lanes) {
+    long long per = kBlock / lanes;
+    return (int)std::min<long long>(std::max<long long>((rows + per - 1) / per, 1), kMaxGrid);
+  }
+  void check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw EngineError{COSMO_B200_ERR_CUDA, std::string("launch of ") + what + " failed: " + cudaGetErrorString(e)};
+    ++launches_;
+  }
+  void sync() { CUDA_TRY(cudaStreamSynchronize(stream_)); }
+  void upload_vec(DevBuf<T>& dst, const void* host, size_t count);
+  void download_vec(void* host, const T* src, size_t count);
+  void build_csr(DevCsr<T>& dst, const HostCsr& h);
+  void classify_and_set_rho(bool reset_rho);
+  void allreduce_sum(T* buf, size_t count);
+  void allreduce_max(T* buf, size_t count);
+
+  template <typename Epi>
+  void launch_spmv(const DevCsr<T>& M1, const T* x1, const DevCsr<T>* M2, const T* x2, int nrows, const Epi& epi,
+                   RedBuf<T> rb, const char* name);
+  void project_device(const T* w, bool with_rhs, const T* ws_rhs);
+  void soc_norms(const T* ws, T* norm_out);
+  void kkt_core(bool fused_tail, const T* w_src, T* w_dst);
+  void compute_residuals(const T* x, const T* s, const T* mu, bool ignore_scaling, double out[5]);
+  bool adapt_rho(const T* x);
+  bool primal_infeasible();
+  bool dual_infeasible();
+  void recover_mu(const T* w_prev) {
+    recover_mu_kernel<T><<<vgrid(m_), kBlock, 0, stream_>>>(m_, rho_vec_.p, w_prev + n_, s_.p, mu_.p);
+    check_launch("recover_mu");
+  }
+  void read_scalars(int first, int count) {
+    CUDA_TRY(cudaMemcpyAsync(h_sc_ + first, sc_.p + first, count * sizeof(T), cudaMemcpyDeviceToHost, stream_));
+    sync();
+  }
+};
+
+// ---------------------------------------------------------------------------
+template <typename T>
+void Engine<T>::upload_vec(DevBuf<T>& dst, const void* host, size_t count) {
+  if (count == 0) return;
+  CUDA_TRY(cudaMemcpyAsync(dst.p, host, count * sizeof(T), cudaMemcpyHostToDevice, stream_));
+}
+template <typename T>
+void Engine<T>::download_vec(void* host, const T* src, size_t count) {
+  if (count == 0) return;
+  CUDA_TRY(cudaMemcpyAsync(host, src, count * sizeof(T), cudaMemcpyDeviceToHost, stream_));
+}
+
+template <typename T>
+void Engine<T>::build_csr(DevCsr<T>& dst, const HostCsr& h) {
+  dst.nrows = h.nrows;
+  dst.ncols = h.ncols;
+  dst.nnz = (long long)h.col.size();
+  dst.lanes = pick_lanes(h.nrows ? (double)dst.nnz / h.nrows : 0.0);
+  dst.rowptr.alloc(h.nrows + 1, false);
+  dst.col.alloc(dst.nnz + 4, true);   // +4: the vector path never reads past nnz, padding keeps ASAN-style tools quiet
+  dst.val.alloc(dst.nnz + 4, true);
+  CUDA_TRY(cudaMemcpyAsync(dst.rowptr.p, h.rowptr.data(), (h.nrows + 1) * sizeof(int), cudaMemcpyHostToDevice, stream_));
+  if (dst.nnz) {
+    CUDA_TRY(cudaMemcpyAsync(dst.col.p, h.col.data(), dst.nnz * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    if (sizeof(T) == sizeof(double)) {
+      CUDA_TRY(cudaMemcpyAsync(dst.val.p, h.val.data(), dst.nnz * sizeof(double), cudaMemcpyHostToDevice, stream_));
+      sync();
+    } else {
+      std::vector<float> tmp(h.val.begin(), h.val.end());
+      CUDA_TRY(cudaMemcpyAsync(dst.val.p, tmp.data(), dst.nnz * sizeof(float), cudaMemcpyHostToDevice, stream_));
+      sync();
+    }
+  }
+  sync();
+}
+
+// Julia CSC -> (a) CSR of the transpose (zero conversion: same arrays, rebased)
+//              (b) CSR of the matrix itself (stable counting-sort transposition)
+template <typename T>
+static void csc_to_host_csrs(const cosmo_b200_csc& M, int base, HostCsr& csr, HostCsr& csr_t) {
+  const long long nr = M.nrows, nc = M.ncols;
+  if (nr < 0 || nc < 0 || nr >= (1LL << 31) - 8 || nc >= (1LL << 31) - 8)
+    throw EngineError{COSMO_B200_ERR_INVALID, "matrix dimensions out of int32 range"};
+  const long long nnz = nc ? (M.colptr[nc] - base) : 0;
+  if (nnz < 0 || nnz >= (1LL << 31) - 8) throw EngineError{COSMO_B200_ERR_INVALID, "nnz out of int32 range"};
+  const T* vals = static_cast<const T*>(M.nzval);
+  csr_t.nrows = (int)nc; csr_t.ncols = (int)nr;
+  csr_t.rowptr.resize(nc + 1);
+  csr_t.col.resize(nnz);
+  csr_t.val.resize(nnz);
+  for (long long j = 0; j <= nc; ++j) {
+    long long v = nc ? M.colptr[j] - base : 0;
+    if (v < 0 || v > nnz || (j > 0 && v < csr_t.rowptr[j - 1])) throw EngineError{COSMO_B200_ERR_INVALID, "colptr not monotone"};
+    csr_t.rowptr[j] = (int)v;
+  }
+  csr.nrows = (int)nr; csr.ncols = (int)nc;
+  csr.rowptr.assign(nr + 1, 0);
+  for (long long k = 0; k < nnz; ++k) {
+    long long r = M.rowval[k] - base;
+    if (r < 0 || r >= nr) throw EngineError{COSMO_B200_ERR_INVALID, "rowval out of range"};
+    csr_t.col[k] = (int)r;
+    csr_t.val[k] = (double)vals[k];
+    csr.rowptr[r + 1]++;
+  }
+  for (long long r = 0; r < nr; ++r) csr.rowptr[r + 1] += csr.rowptr[r];
+  csr.col.resize(nnz);
+  csr.val.resize(nnz);
+  std::vector<int> next(csr.rowptr.begin(), csr.rowptr.end() - 1);
+  for (long long j = 0; j < nc; ++j)
+    for (int k = csr_t.rowptr[j]; k < csr_t.rowptr[j + 1]; ++k) {
+      int r = csr_t.col[k];
+      int dstk = next[r]++;
+      csr.col[dstk] = (int)j;
+      csr.val[dstk] = csr_t.val[k];
+    }
+}
+
+template <typename T>
+Engine<T>::Engine(const cosmo_b200_problem& p, const cosmo_b200_settings& st) : st_(st) {
+  if (p.m < 0 || p.n < 0 || p.m >= (1LL << 31) - 8 || p.n >= (1LL << 31) - 8)
+    throw EngineError{COSMO_B200_ERR_INVALID, "model size out of range"};
+  n_ = (int)p.n; m_ = (int)p.m; device_ = p.device;
+  if (p.A.nrows != p.m || p.A.ncols != p.n) throw EngineError{COSMO_B200_ERR_INVALID, "A must be m x n"};
+  if (p.P.nrows != p.n || p.P.ncols != p.n) throw EngineError{COSMO_B200_ERR_INVALID, "P must be n x n"};
+  if (st.adaptive_rho && st.adaptive_rho_interval <= 0)
+    throw EngineError{COSMO_B200_ERR_UNSUPPORTED, "adaptive_rho_interval = 0 (wall-clock rule) is decided on the host; pass an interval > 0"};
+  int ndev = 0;
+  cudaError_t de = cudaGetDeviceCount(&ndev);
+  if (de != cudaSuccess || ndev == 0)
+    throw EngineError{COSMO_B200_ERR_CUDA, "no CUDA device available: the COSMO B200 engine has no CPU fallback"};
+  if (device_ < 0 || device_ >= ndev) throw EngineError{COSMO_B200_ERR_INVALID, "bad device ordinal"};
+  CUDA_TRY(cudaSetDevice(device_));
+  CUDA_TRY(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreate(&ev0_));
+  CUDA_TRY(cudaEventCreate(&ev1_));
+  CUDA_TRY(cudaMallocHost(&h_sc_, SC_COUNT * sizeof(T)));
+  CUDA_TRY(cudaMallocHost(&h_isc_, ISC_COUNT * sizeof(int)));
+
+  // ---- sets -> row tables -------------------------------------------------
+  long long off = 0;
+  std::vector<unsigned char> row_class(m_);
+  std::vector<int> row_cone(m_, 0);
+  hl_.assign(m_, -INFINITY);
+  hu_.assign(m_, INFINITY);
+  std::vector<int> soc_off, soc_dim;
+  std::vector<PsdConeDesc> psd_descs;
+  for (long long k = 0; k < p.n_sets; ++k) {
+    const cosmo_b200_set& sdesc = p.sets[k];
+    if (sdesc.dim < 0 || off + sdesc.dim > m_) throw EngineError{COSMO_B200_ERR_INVALID, "set dimensions exceed m"};
+    cosmo_b200_set keep = sdesc; keep.l = keep.u = nullptr;
+    sets_.push_back(keep);
+    set_off_.push_back((int)off);
+    unsigned char cls;
+    switch (sdesc.type) {
+      case COSMO_B200_ZERO: cls = ROW_ZERO; break;
+      case COSMO_B200_NONNEG: cls = ROW_NONNEG; break;
+      case COSMO_B200_BOX: {
+        cls = ROW_BOX;
+        if (!sdesc.l || !sdesc.u) throw EngineError{COSMO_B200_ERR_INVALID, "Box set without bounds"};
+        const T* l = static_cast<const T*>(sdesc.l);
+        const T* u = static_cast<const T*>(sdesc.u);
+        for (long long i = 0; i < sdesc.dim; ++i) {
+          if (l[i] > u[i]) throw EngineError{COSMO_B200_ERR_INVALID, "Box set: inconsistent lower/upper bounds"};
+          hl_[off + i] = l[i]; hu_[off + i] = u[i];
+        }
+        break;
+      }
+      case COSMO_B200_SOC:
+        cls = ROW_SOC;
+        for (long long i = 0; i < sdesc.dim; ++i) row_cone[off + i] = (int)soc_off.size();
+        if (sdesc.dim > 0) { soc_off.push_back((int)off); soc_dim.push_back((int)sdesc.dim); }
+        break;
+      case COSMO_B200_PSD_SQUARE:
+      case COSMO_B200_PSD_TRIANGLE: {
+        cls = ROW_PSD;
+        long long N;
+        if (sdesc.type == COSMO_B200_PSD_SQUARE) {
+          N = (long long)llround(sqrt((double)sdesc.dim));
+          if (N * N != sdesc.dim) throw EngineError{COSMO_B200_ERR_INVALID, "PsdCone: dimension must be a square"};
+        } else {
+          N = ((long long)floor(sqrt(1.0 + 8.0 * (double)sdesc.dim)) - 1) / 2;
+          while (N * (N + 1) / 2 < sdesc.dim) ++N;
+          if (N * (N + 1) / 2 != sdesc.dim) throw EngineError{COSMO_B200_ERR_INVALID, "PsdConeTriangle: dimension must be N(N+1)/2"};
+        }
+        for (long long i = 0; i < sdesc.dim; ++i) row_cone[off + i] = (int)psd_descs.size();
+        if (sdesc.dim > 0) psd_descs.push_back(PsdConeDesc{(int)off, (int)N, sdesc.type == COSMO_B200_PSD_TRIANGLE ? 1 : 0});
+        break;
+      }
+      default:
+        throw EngineError{COSMO_B200_ERR_UNSUPPORTED, "unsupported cone type (Exp/Pow/dual/complex PSD): fall back to the host loop"};
+    }
+    for (long long i = 0; i < sdesc.dim; ++i) row_class[off + i] = cls;
+    off += sdesc.dim;
+  }
+  if (off != m_) throw EngineError{COSMO_B200_ERR_INVALID, "sum of set dimensions != m"};
+
+  // ---- matrices -----------------------------------------------------------
+  {
+    HostCsr a, at, pp, ppt;
+    csc_to_host_csrs<T>(p.A, p.index_base, a, at);
+    build_csr(A_, a);
+    build_csr(At_, at);
+    csc_to_host_csrs<T>(p.P, p.index_base, pp, ppt);
+    build_csr(P_, pp);
+    // A' and P rows are traversed by the same lane group in the fused operator kernel
+    double mean = n_ ? (double)(At_.nnz + P_.nnz) / n_ : 0.0;
+    At_.lanes = pick_lanes(mean);
+  }
+  // ---- vectors ------------------------------------------------------------
+  auto up = [&](DevBuf<T>& d, const void* h, size_t cnt) { d.alloc(cnt); if (h) upload_vec(d, h, cnt); };
+  up(q_, p.q, n_);
+  up(b_, p.b, m_);
+  hb_.resize(m_);
+  for (int i = 0; i < m_; ++i) hb_[i] = (double)static_cast<const T*>(p.b)[i];
+  scaled_ = (p.D && p.Dinv && p.E && p.Einv);
+  c_ = p.c;
+  if (scaled_) { up(D_, p.D, n_); up(Dinv_, p.Dinv, n_); up(E_, p.E, m_); up(Einv_, p.Einv, m_); }
+  row_class_.alloc(m_); row_cone_.alloc(m_); rho_class_.alloc(m_);
+  if (m_) {
+    CUDA_TRY(cudaMemcpyAsync(row_class_.p, row_class.data(), m_, cudaMemcpyHostToDevice, stream_));
+    CUDA_TRY(cudaMemcpyAsync(row_cone_.p, row_cone.data(), m_ * sizeof(int), cudaMemcpyHostToDevice, stream_));
+  }
+  box_l_.alloc(m_); box_u_.alloc(m_);
+  {
+    std::vector<T> l(hl_.begin(), hl_.end()), u(hu_.begin(), hu_.end());
+    upload_vec(box_l_, l.data(), m_);
+    upload_vec(box_u_, u.data(), m_);
+    sync();
+  }
+  // SOC tables (chunks of <= 8192 tail rows)
+  n_soc_ = (int)soc_off.size();
+  if (n_soc_) {
+    const int CH = 8192;
+    std::vector<int> cs, cl, ptr(1, 0);
+    for (int k = 0; k < n_soc_; ++k) {
+      int start = soc_off[k] + 1, len = soc_dim[k] - 1;
+      for (int o = 0; o < len; o += CH) { cs.push_back(start + o); cl.push_back(std::min(CH, len - o)); }
+      ptr.push_back((int)cs.size());
+    }
+    n_soc_chunks_ = (int)cs.size();
+    soc_off_.upload(soc_off, stream_); soc_dim_.upload(soc_dim, stream_);
+    soc_chunk_start_.upload(cs, stream_); soc_chunk_len_.upload(cl, stream_); soc_cone_chunk_ptr_.upload(ptr, stream_);
+    soc_norm_.alloc(n_soc_); soc_norm2_.alloc(n_soc_); soc_chunk_sum_.alloc(std::max(n_soc_chunks_, 1));
+    sync();
+  }
+  psd_.init(psd_descs, stream_);
+
+  // ---- state / scratch ------------------------------------------------------
+  W_[0].alloc(n_ + m_); W_[1].alloc(n_ + m_);
+  xs_.alloc(n_); s_.alloc(m_); mu_.alloc(m_); rho_vec_.alloc(m_);
+  ls_.alloc(n_ + m_); t0_.alloc(m_); tm_.alloc(m_); xsol_.alloc(n_);
+  rhsb_.alloc(n_ + 8); cb_.alloc(n_ + 8); r_.alloc(n_); u_.alloc(n_); nu_.alloc(m_);
+  vec_m_.alloc(m_); vec_n_.alloc(n_ + 8); vec_n2_.alloc(n_); dy_.alloc(m_); dx_.alloc(n_);
+  sc_.alloc(SC_COUNT); isc_.alloc(ISC_COUNT);
+  partials_.alloc((size_t)kMaxGrid * kMaxRed); ticket_.alloc(1);
+  {
+    int h[ISC_COUNT] = {0};
+    h[ISC_MAXIT] = n_;   // IterativeSolvers default maxiter = size(A, 2)
+    CUDA_TRY(cudaMemcpyAsync(isc_.p, h, sizeof(h), cudaMemcpyHostToDevice, stream_));
+    sync();
+  }
+  rho_ = st_.rho;
+  classify_and_set_rho(true);
+  sync();
+}
+
+template <typename T>
+Engine<T>::~Engine() {
+  if (comm_ && g_nccl.CommDestroy) g_nccl.CommDestroy(comm_);
+  if (h_sc_) cudaFreeHost(h_sc_);
+  if (h_isc_) cudaFreeHost(h_isc_);
+  if (ev0_) cudaEventDestroy(ev0_);
+  if (ev1_) cudaEventDestroy(ev1_);
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+// classify_constraints! (setup.jl:75-85; convexset.jl:62-69, 831-842) and
+// set_rho_vec! / update_rho_vec! (parameters.jl:3-13, 75-81)
+template <typename T>
+void Engine<T>::classify_and_set_rho(bool reset_rho) {
+  std::vector<unsigned char> cls(m_, 0);
+  const double big = st_.COSMO_INFTY * st_.MIN_SCALING;
+  for (size_t k = 0; k < sets_.size(); ++k) {
+    const int off = set_off_[k];
+    const long long dim = sets_[k].dim;
+    if (sets_[k].type == COSMO_B200_ZERO) {
+      for (long long i = 0; i < dim; ++i) cls[off + i] = 1;
+    } else if (sets_[k].type == COSMO_B200_NONNEG) {
+      for (long long i = 0; i < dim; ++i) if (hb_[off + i] > big) cls[off + i] = 2;
+    } else if (sets_[k].type == COSMO_B200_BOX) {
+      for (long long i = 0; i < dim; ++i) {
+        const double l = hl_[off + i], u = hu_[off + i];
+        if (l < -big && u > big) cls[off + i] = 2;
+        else if ((u - l) < st_.RHO_TOL) cls[off + i] = 1;
+      }
+    }
+  }
+  if (m_) CUDA_TRY(cudaMemcpyAsync(rho_class_.p, cls.data(), m_, cudaMemcpyHostToDevice, stream_));
+  sync();
+  if (reset_rho) {
+    rho_ = st_.rho;
+    rho_updates_.clear();
+    rho_updates_.push_back(rho_);
+  }
+  rho_vec_kernel<T><<<vgrid(m_), kBlock, 0, stream_>>>(m_, rho_class_.p, (T)rho_, (T)st_.RHO_EQ_OVER_RHO_INEQ, (T)st_.RHO_MIN, rho_vec_.p);
+  check_launch("rho_vec");
+}
+
+template <typename T>
+void Engine<T>::warm_start(const void* x, const void* s, const void* mu) {
+  if (x) upload_vec(xs_, x, n_);
+  if (s) upload_vec(s_, s, m_);
+  if (mu) upload_vec(mu_, mu, m_);
+  sync();
+}
+
+template <typename T>
+void Engine<T>::update_qb(const void* q, const void* b) {
+  if (q) upload_vec(q_, q, n_);
+  if (b) {
+    upload_vec(b_, b, m_);
+    for (int i = 0; i < m_; ++i) hb_[i] = (double)static_cast<const T*>(b)[i];
+  }
+  sync();
+  if (b) classify_and_set_rho(false);
+  sync();
+}
+
+template <typename T>
+void Engine<T>::update_rho(const void* rho_vec, double rho) {
+  if (rho_vec) upload_vec(rho_vec_, rho_vec, m_);
+  rho_ = rho;
+  sync();
+}
+
+template <typename T>
+void Engine<T>::reset() {
+  CUDA_TRY(cudaMemsetAsync(xs_.p, 0, std::max(n_, 1) * sizeof(T), stream_));
+  CUDA_TRY(cudaMemsetAsync(s_.p, 0, std::max(m_, 1) * sizeof(T), stream_));
+  CUDA_TRY(cudaMemsetAsync(mu_.p, 0, std::max(m_, 1) * sizeof(T), stream_));
+  CUDA_TRY(cudaMemsetAsync(xsol_.p, 0, std::max(n_, 1) * sizeof(T), stream_));
+  CUDA_TRY(cudaMemsetAsync(W_[0].p, 0, std::max(n_ + m_, 1) * sizeof(T), stream_));
+  CUDA_TRY(cudaMemsetAsync(W_[1].p, 0, std::max(n_ + m_, 1) * sizeof(T), stream_));
+  kkt_counter_ = 1;
+  last_cg_iters_ = 1;
+  is_optimized_ = false;
+  psd_.reset_warm_start();
+  classify_and_set_rho(true);
+  sync();
+}
+
+template <typename T>
+void Engine<T>::allreduce_sum(T* buf, size_t count) {
+  if (nranks_ <= 1) return;
+  int rc = g_nccl.AllReduce(buf, buf, count, sizeof(T) == 8 ? kNcclFloat64 : kNcclFloat32, kNcclSum, comm_, stream_);
+  if (rc != 0) throw EngineError{COSMO_B200_ERR_NCCL, "ncclAllReduce(sum) failed"};
+}
+template <typename T>
+void Engine<T>::allreduce_max(T* buf, size_t count) {
+  if (nranks_ <= 1) return;
+  int rc = g_nccl.AllReduce(buf, buf, count, sizeof(T) == 8 ? kNcclFloat64 : kNcclFloat32, kNcclMax, comm_, stream_);
+  if (rc != 0) throw EngineError{COSMO_B200_ERR_NCCL, "ncclAllReduce(max) failed"};
+}
+
+template <typename T>
+void Engine<T>::comm_init(int nranks, int rank, const void* id128) {
+  if (nranks < 1 || rank < 0 || rank >= nranks) throw EngineError{COSMO_B200_ERR_INVALID, "bad rank / nranks"};
+  nranks_ = nranks; rank_ = rank;
+  if (nranks == 1) return;
+  std::string e;
+  if (!g_nccl.load(e)) throw EngineError{COSMO_B200_ERR_NCCL, e};
+  NcclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  CUDA_TRY(cudaSetDevice(device_));
+  int rc = g_nccl.CommInitRank(&comm_, nranks, id, rank);
+  if (rc != 0) throw EngineError{COSMO_B200_ERR_NCCL, std::string("ncclCommInitRank failed: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?")};
+}
+
+// ---------------------------------------------------------------------------
+template <typename T>
+template <typename Epi>
+void Engine<T>::launch_spmv(const DevCsr<T>& M1, const T* x1, const DevCsr<T>* M2, const T* x2, int nrows,
+                            const Epi& epi, RedBuf<T> rb, const char* name) {
+  const CsrView<T> v2 = M2 ? M2->view() : CsrView<T>{nullptr, nullptr, nullptr};
+  const int lanes = M1.lanes;
+  const int grid = sgrid(nrows, lanes);
+  if (lanes == 32) spmv_kernel<T, 32, Epi><<<grid, kBlock, 0, stream_>>>(M1.view(), x1, v2, x2, nrows, epi, rb);
+  else if (lanes == 8) spmv_kernel<T, 8, Epi><<<grid, kBlock, 0, stream_>>>(M1.view(), x1, v2, x2, nrows, epi, rb);
+  else spmv_kernel<T, 2, Epi><<<grid, kBlock, 0, stream_>>>(M1.view(), x1, v2, x2, nrows, epi, rb);
+  check_launch(name);
+}
+
+template <typename T>
+void Engine<T>::soc_norms(const T* ws, T* norm_out) {
+  if (!n_soc_) return;
+  if (n_soc_chunks_) {
+    soc_chunk_kernel<T><<<n_soc_chunks_, kBlock, 0, stream_>>>(ws, soc_chunk_start_.p, soc_chunk_len_.p, soc_chunk_sum_.p);
+    check_launch("soc_chunk");
+  }
+  soc_final_kernel<T><<<(n_soc_ + 127) / 128, 128, 0, stream_>>>(soc_chunk_sum_.p, soc_cone_chunk_ptr_.p, n_soc_, norm_out);
+  check_launch("soc_final");
+}
+
+// admm_z! (solver.jl:7-21) [+ rhs of admm_x!, solver.jl:50-51]
+template <typename T>
+void Engine<T>::project_device(const T* w, bool with_rhs, const T* ws_rhs) {
+  soc_norms(w + n_, soc_norm_.p);
+  psd_.project(w + n_, s_.p, stream_, st_.psd_max_sweeps, launches_);
+  ProjRhsArgs<T> a;
+  a.n = n_; a.m = m_; a.w = w; a.ws_rhs = ws_rhs ? ws_rhs : w + n_;
+  a.q = q_.p; a.b = b_.p; a.rho = rho_vec_.p; a.box_l = box_l_.p; a.box_u = box_u_.p;
+  a.row_class = row_class_.p; a.row_cone = row_cone_.p;
+  a.soc = SocTable<T>{soc_off_.p, soc_norm_.p};
+  a.s = s_.p; a.ls = ls_.p; a.t0 = t0_.p; a.sigma = (T)st_.sigma;
+  a.do_proj = 1; a.do_rhs = with_rhs ? 1 : 0;
+  proj_rhs_kernel<T><<<vgrid((long long)n_ + m_), kBlock, 0, stream_>>>(a);
+  check_launch("proj_rhs");
+}
+
+// solve!(S::IndirectReducedKKTSolver, y, x) with CG (kktsolver_indirect.jl:36-88).
+// Inputs: ls_ = [x1; x2], t0_ = rho .* x2.  Output: xsol_ = y1; then either
+//   fused_tail: w_dst = admm_w!(...) computed in the epilogue of the last SpMV, or
+//   plain:      nu_ = y2 = rho .* (A y1 - x2).
+template <typename T>
+void Engine<T>::kkt_core(bool fused_tail, const T* w_src, T* w_dst) {
+  if (st_.kkt_solver != COSMO_B200_KKT_CG)
+    throw EngineError{COSMO_B200_ERR_UNSUPPORTED, "only the CG reduced-KKT solver is implemented in this build"};
+  const int* done = isc_.p + ISC_DONE;
+  const bool lead = (rank_ == 0);
+  // rhs = x1 + A' (rho .* x2)
+  launch_spmv(At_, t0_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, n_,
+              EpiAddVec<T>{nullptr, rhsb_.p, lead ? ls_.p : nullptr}, red(SC_TMP0), "spmv_rhs");
+  allreduce_sum(rhsb_.p, n_);
+  // c = L x0 (warm start => one product for the initial residual)
+  launch_spmv(A_, xsol_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, m_, EpiScale<T>{nullptr, tm_.p, rho_vec_.p},
+              red(SC_TMP0), "spmv_A_scale");
+  launch_spmv(At_, tm_.p, lead ? &P_ : nullptr, xsol_.p, n_,
+              EpiKktOp<T>{nullptr, cb_.p, xsol_.p, lead ? (T)st_.sigma : (T)0}, red_ptr(cb_.p + n_), "spmv_kkt_op");
+  allreduce_sum(cb_.p, n_ + 1);
+  const double tol_num = st_.tol_constant / pow((double)kkt_counter_, st_.tol_exponent);
+  cg_init_kernel<T><<<vgrid(n_), kBlock, 0, stream_>>>(n_, rhsb_.p, cb_.p, r_.p, u_.p, red(SC_RES2),
+                                                      CgInitFin<T>{sc_.p, isc_.p, (T)tol_num});
+  check_launch("cg_init");
+  long long mults = 1;
+  int launched = 0;
+  int chunk = std::max(last_cg_iters_, 0);
+  for (;;) {
+    for (int i = 0; i < chunk; ++i) {
+      cg_update_u_kernel<T><<<vgrid(n_), kBlock, 0, stream_>>>(n_, r_.p, u_.p, sc_.p, isc_.p);
+      check_launch("cg_update_u");
+      launch_spmv(A_, u_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, m_, EpiScale<T>{done, tm_.p, rho_vec_.p},
+                  red(SC_TMP0), "spmv_A_scale");
+      launch_spmv(At_, tm_.p, lead ? &P_ : nullptr, u_.p, n_,
+                  EpiKktOp<T>{done, cb_.p, u_.p, lead ? (T)st_.sigma : (T)0}, red_ptr(cb_.p + n_), "spmv_kkt_op");
+      allreduce_sum(cb_.p, n_ + 1);
+      cg_update_xr_kernel<T><<<vgrid(n_), kBlock, 0, stream_>>>(n_, u_.p, cb_.p, cb_.p + n_, xsol_.p, r_.p, sc_.p, isc_.p,
+                                                             red(SC_RES2), CgStepFin<T>{sc_.p, isc_.p});
+      check_launch("cg_update_xr");
+      ++launched;
+    }
+    CUDA_TRY(cudaMemcpyAsync(h_isc_, isc_.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    sync();
+    if (h_isc_[ISC_DONE]) break;
+    chunk = 1;
+  }
+  const int iters = h_isc_[ISC_IT];
+  (void)launched;
+  last_cg_iters_ = iters;
+  total_inner_ += iters;
+  mults += iters;
+  total_mults_ += mults;
+  kkt_counter_ += 1;
+  if (fused_tail) {
+    launch_spmv(A_, xsol_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, m_,
+                EpiAdmmTail<T>{nullptr, ls_.p + n_, rho_vec_.p, s_.p, w_src + n_, w_dst + n_, (T)st_.alpha}, red(SC_TMP0),
+                "spmv_admm_tail");
+  } else {
+    launch_spmv(A_, xsol_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, m_,
+                EpiY2<T>{nullptr, nu_.p, ls_.p + n_, rho_vec_.p}, red(SC_TMP0), "spmv_y2");
+  }
+}
+
+// calculate_residuals! + max_res_component_norm + calculate_cost! (residuals.jl:30-96, 143-147)
+template <typename T>
+void Engine<T>::compute_residuals(const T* x, const T* s, const T* mu, bool ignore_scaling, double out[5]) {
+  const bool unscale = (st_.scaling != 0) && scaled_ && !ignore_scaling;
+  launch_spmv(A_, x, (const DevCsr<T>*)nullptr, (const T*)nullptr, m_,
+              EpiPrimalRes<T>{nullptr, s, b_.p, unscale ? Einv_.p : nullptr, nullptr}, red(SC_TMP0), "spmv_primal_res");
+  allreduce_max(sc_.p + SC_TMP0, 4);
+  launch_spmv(At_, mu, (const DevCsr<T>*)nullptr, (const T*)nullptr, n_, EpiStore<T>{nullptr, vec_n_.p}, red(SC_TMP4),
+              "spmv_At_mu");
+  allreduce_sum(vec_n_.p, n_);
+  // slots: [SC_TMP0..3] primal maxes are read first, the dual pass then reuses TMP0.. via a second read
+  read_scalars(SC_TMP0, 4);
+  const double rp = (double)h_sc_[SC_TMP0], m1 = (double)h_sc_[SC_TMP0 + 1], m2 = (double)h_sc_[SC_TMP0 + 2], m3 = (double)h_sc_[SC_TMP0 + 3];
+  // P lanes may differ from A' lanes: P_ has its own
+  launch_spmv(P_, x, (const DevCsr<T>*)nullptr, (const T*)nullptr, n_,
+              EpiDualRes<T>{nullptr, x, q_.p, vec_n_.p, unscale ? Dinv_.p : nullptr, unscale ? (T)(1.0 / c_) : (T)1},
+              red(SC_TMP0), "spmv_dual_res");
+  read_scalars(SC_TMP0, 6);
+  const double xPx = (double)h_sc_[SC_TMP0], qx = (double)h_sc_[SC_TMP0 + 1];
+  const double rd = (double)h_sc_[SC_TMP0 + 2], d1 = (double)h_sc_[SC_TMP0 + 3], d2 = (double)h_sc_[SC_TMP0 + 4], d3 = (double)h_sc_[SC_TMP0 + 5];
+  auto nmax = [](double a, double b) { return (a > b || a != a) ? a : b; };
+  out[0] = rp;
+  out[1] = rd;
+  out[2] = nmax(nmax(m1, m2), m3);
+  out[3] = nmax(nmax(d1, d2), d3);
+  out[4] = (1.0 / c_) * (0.5 * xPx + qx);
+}
+
+// adapt_rho_vec! / update_rho_vec! (parameters.jl:53-92)
+template <typename T>
+bool Engine<T>::adapt_rho(const T* x) {
+  double r[5];
+  compute_residuals(x, s_.p, mu_.p, true, r);
+  double rp = r[0] / (r[2] + 1e-10);
+  double rd = r[1] / (r[3] + 1e-10);
+  double new_rho = rho_ * sqrt(rp / (rd + 1e-10));
+  new_rho = std::min(std::max(new_rho, st_.RHO_MIN), st_.RHO_MAX);
+  if (new_rho > st_.adaptive_rho_tolerance * rho_ || new_rho < (1.0 / st_.adaptive_rho_tolerance) * rho_) {
+    rho_ = new_rho;
+    rho_vec_kernel<T><<<vgrid(m_), kBlock, 0, stream_>>>(m_, rho_class_.p, (T)rho_, (T)st_.RHO_EQ_OVER_RHO_INEQ, (T)st_.RHO_MIN, rho_vec_.p);
+    check_launch("rho_vec");
+    rho_updates_.push_back(new_rho);
+    return true;
+  }
+  return false;
+}
+
+// is_primal_infeasible! (infeasibility.jl:1-29); dy_ holds delta_y
+template <typename T>
+bool Engine<T>::primal_infeasible() {
+  const T eps = (T)st_.eps_prim_inf;
+  scaled_norminf_kernel<T><<<vgrid(m_), kBlock, 0, stream_>>>(m_, scaled_ ? E_.p : nullptr, dy_.p, red(SC_TMP0));
+  check_launch("norminf_dy");
+  allreduce_max(sc_.p + SC_TMP0, 1);
+  read_scalars(SC_TMP0, 1);
+  const double norm_dy = (double)h_sc_[SC_TMP0];
+  if (!(norm_dy > st_.eps_prim_inf)) return false;
+  launch_spmv(At_, dy_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, n_, EpiStore<T>{nullptr, vec_n_.p}, red(SC_TMP0), "spmv_At_dy");
+  allreduce_sum(vec_n_.p, n_);
+  scaled_norminf_kernel<T><<<vgrid(n_), kBlock, 0, stream_>>>(n_, scaled_ ? Dinv_.p : nullptr, vec_n_.p, red(SC_TMP0));
+  check_launch("norminf_Atdy");
+  read_scalars(SC_TMP0, 1);
+  if (!((double)h_sc_[SC_TMP0] <= st_.eps_prim_inf * norm_dy)) return false;
+  scal_kernel<T><<<vgrid(m_), kBlock, 0, stream_>>>(m_, (T)(-1.0 / norm_dy), dy_.p);
+  check_launch("scal_dy");
+  dot_kernel<T><<<vgrid(m_), kBlock, 0, stream_>>>(m_, dy_.p, b_.p, red(SC_TMP0));
+  check_launch("dot_dy_b");
+  cone_rows_certificate_kernel<T><<<vgrid(m_), kBlock, 0, stream_>>>(m_, 0, dy_.p, row_class_.p, box_l_.p, box_u_.p, eps, red(SC_TMP1));
+  check_launch("cone_cert_primal");
+  // SOC: -v in K*  <=>  |v[2:]| <= tol - v[1]  ;  PSD: -V + tol I positive definite
+  T flag = 0;
+  if (n_soc_) {
+    soc_norms(dy_.p, soc_norm2_.p);
+    soc_cert_kernel<T><<<1, kBlock, 0, stream_>>>(n_soc_, soc_off_.p, soc_norm2_.p, dy_.p, eps, sc_.p + SC_TMP3);
+    check_launch("soc_cert");
+  } else {
+    CUDA_TRY(cudaMemsetAsync(sc_.p + SC_TMP3, 0, sizeof(T), stream_));
+  }
+  const bool psd_ok = psd_.certificate(dy_.p, /*negate=*/true, (double)eps, stream_, st_.psd_max_sweeps, launches_);
+  (void)flag;
+  if (nranks_ > 1) {
+    allreduce_sum(sc_.p + SC_TMP0, 2);   // dy'b, box support sum
+    allreduce_max(sc_.p + SC_TMP2, 2);   // flags
+  }
+  read_scalars(SC_TMP0, 4);
+  const double dyt_b = (double)h_sc_[SC_TMP0];
+  const double box_sum = (double)h_sc_[SC_TMP1];
+  const bool cone_bad = (h_sc_[SC_TMP2] != 0) || (h_sc_[SC_TMP3] != 0) || !psd_ok;
+  const double sF = (cone_bad ? INFINITY : 0.0) + box_sum - dyt_b;
+  return sF <= st_.eps_prim_inf;
+}
+
+// is_dual_infeasible! (infeasibility.jl:32-68); dx_ holds delta_x
+template <typename T>
+bool Engine<T>::dual_infeasible() {
+  const T eps = (T)st_.eps_dual_inf;
+  scaled_norminf_kernel<T><<<vgrid(n_), kBlock, 0, stream_>>>(n_, scaled_ ? D_.p : nullptr, dx_.p, red(SC_TMP0));
+  check_launch("norminf_dx");
+  dot_kernel<T><<<vgrid(n_), kBlock, 0, stream_>>>(n_, q_.p, dx_.p, red(SC_TMP1));
+  check_launch("dot_q_dx");
+  read_scalars(SC_TMP0, 2);
+  const double norm_dx = (double)h_sc_[SC_TMP0];
+  if (!(norm_dx > st_.eps_dual_inf)) return false;
+  if (!((double)h_sc_[SC_TMP1] / (norm_dx * c_) < -st_.eps_dual_inf)) return false;
+  launch_spmv(P_, dx_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, n_,
+              EpiStoreScaledMax<T>{nullptr, nullptr, scaled_ ? Dinv_.p : nullptr}, red(SC_TMP0), "spmv_P_dx");
+  read_scalars(SC_TMP0, 1);
+  if (!((double)h_sc_[SC_TMP0] / (norm_dx * c_) <= st_.eps_dual_inf)) return false;
+  launch_spmv(A_, dx_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, m_, EpiStore<T>{nullptr, vec_m_.p}, red(SC_TMP0), "spmv_A_dx");
+  if (scaled_) {
+    scale_kernel<T><<<vgrid(m_), kBlock, 0, stream_>>>(m_, Einv_.p, vec_m_.p, vec_m_.p);
+    check_launch("scale_Adx");
+  }
+  scal_kernel<T><<<vgrid(m_), kBlock, 0, stream_>>>(m_, (T)(1.0 / norm_dx), vec_m_.p);
+  check_launch("scal_Adx");
+  cone_rows_certificate_kernel<T><<<vgrid(m_), kBlock, 0, stream_>>>(m_, 1, vec_m_.p, row_class_.p, box_l_.p, box_u_.p, eps, red(SC_TMP1));
+  check_launch("cone_cert_dual");
+  if (n_soc_) {
+    soc_norms(vec_m_.p, soc_norm2_.p);
+    soc_cert_kernel<T><<<1, kBlock, 0, stream_>>>(n_soc_, soc_off_.p, soc_norm2_.p, vec_m_.p, eps, sc_.p + SC_TMP3);
+    check_launch("soc_cert");
+  } else {
+    CUDA_TRY(cudaMemsetAsync(sc_.p + SC_TMP3, 0, sizeof(T), stream_));
+  }
+  const bool psd_ok = psd_.certificate(vec_m_.p, /*negate=*/true, (double)eps, stream_, st_.psd_max_sweeps, launches_);
+  if (nranks_ > 1) allreduce_max(sc_.p + SC_TMP2, 2);
+  read_scalars(SC_TMP2, 2);
+  return (h_sc_[SC_TMP2] == 0) && (h_sc_[SC_TMP3] == 0) && psd_ok;
+}
+
+// ---------------------------------------------------------------------------
+// The hot loop: COSMO.optimize!, src/solver.jl:125-167
+// ---------------------------------------------------------------------------
+template <typename T>
+void Engine<T>::solve(cosmo_b200_result* out) {
+  const double t_start = now_s();
+  CUDA_TRY(cudaSetDevice(device_));
+  const int n = n_, m = m_;
+  const long long launches0 = launches_;
+  total_inner_ = 0; total_mults_ = 0;
+  int status = COSMO_B200_UNDETERMINED;
+  double cost = INFINITY;
+  double info[5] = {INFINITY, INFINITY, 0.0, 0.0, INFINITY};
+  long long iter = 0;
+  bool rho_update_due = false, infeasibility_check_due = false;
+  double res_time = 0.0;
+
+  // warm starting the operator variable (solver.jl:128-129): w_x = x, w_s = mu ./ rho + s
+  cur_ = 0; prev_ = 1;
+  CUDA_TRY(cudaMemcpyAsync(W_[cur_].p, xs_.p, n * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+  ws_from_mu_kernel<T><<<vgrid(m), kBlock, 0, stream_>>>(m, rho_vec_.p, mu_.p, s_.p, W_[cur_].p + n);
+  check_launch("ws_from_mu");
+  is_optimized_ = true;
+  CUDA_TRY(cudaEventRecord(ev0_, stream_));
+  const double iter_start = now_s();
+
+  // x-step + w-step reading W[src], writing W[dst]
+  auto xw_step = [&](int src, int dst, bool do_proj, const T* ws_override) {
+    const T* w = W_[src].p;
+    const T* ws_rhs = ws_override ? ws_override : w + n;
+    if (do_proj) {
+      project_device(w, true, ws_rhs);
+    } else {
+      ProjRhsArgs<T> a;
+      a.n = n; a.m = m; a.w = w; a.ws_rhs = ws_rhs; a.q = q_.p; a.b = b_.p; a.rho = rho_vec_.p;
+      a.box_l = box_l_.p; a.box_u = box_u_.p; a.row_class = row_class_.p; a.row_cone = row_cone_.p;
+      a.soc = SocTable<T>{soc_off_.p, soc_norm_.p};
+      a.s = s_.p; a.ls = ls_.p; a.t0 = t0_.p; a.sigma = (T)st_.sigma; a.do_proj = 0; a.do_rhs = 1;
+      proj_rhs_kernel<T><<<vgrid((long long)n + m), kBlock, 0, stream_>>>(a);
+      check_launch("proj_rhs");
+    }
+    // the tail reads w_s from ws_rhs's buffer and writes W[dst] (elementwise, may alias)
+    T* wd = W_[dst].p;
+    kkt_core(true, ws_override ? (ws_override - n) : w, wd);
+    wx_update_kernel<T><<<vgrid(n), kBlock, 0, stream_>>>(n, w, xsol_.p, (T)st_.alpha, wd);
+    check_launch("wx_update");
+  };
+
+  // one initialisation step (solver.jl:137-138)
+  xw_step(cur_, 1 - cur_, false, nullptr);
+  cur_ = 1 - cur_; prev_ = 1 - cur_;
+
+  while (iter < st_.max_iter) {
+    ++iter;
+    // acceleration_pre!: EmptyAccelerator (accelerator_interface.jl:75)
+    if (infeasibility_check_due) {  // solver.jl:145-148
+      recover_mu(W_[prev_].p);
+      CUDA_TRY(cudaMemcpyAsync(dy_.p, mu_.p, m * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+    }
+    // w_prev = w (solver.jl:151): the current buffer becomes w_prev, the other one receives w_{k+1}
+    const int src = cur_, dst = 1 - cur_;
+    // rho adaptation rules (solver.jl:242-282)
+    if (st_.adaptive_rho && st_.adaptive_rho_interval > 0 && (iter % st_.adaptive_rho_interval) == 0 &&
+        (long long)(rho_updates_.size() - 1) < st_.adaptive_rho_max_adaptions)
+      rho_update_due = true;
+    if (rho_update_due) {
+      rho_update_due = false;
+      project_device(W_[src].p, false, nullptr);          // admm_z!
+      recover_mu(W_[src].p);                               // w_prev == w here
+      const double t0 = now_s();
+      const bool adapted = adapt_rho(W_[src].p);
+      res_time += now_s() - t0;
+      if (adapted) {
+        // w[n+1:end] = mu ./ rho + s (solver.jl:278), kept apart from w_prev
+        ws_from_mu_kernel<T><<<vgrid(m), kBlock, 0, stream_>>>(m, rho_vec_.p, mu_.p, s_.p, W_[dst].p + n);
+        check_launch("ws_from_mu");
+        xw_step(src, dst, false, W_[dst].p + n);
+      } else {
+        xw_step(src, dst, false, nullptr);
+      }
+    } else {
+      xw_step(src, dst, true, nullptr);
+    }
+    prev_ = src; cur_ = dst;
+    // acceleration_post!: EmptyAccelerator
+
+    // check_termination! (solver.jl:303-356)
+    if ((st_.check_termination > 0 && iter % st_.check_termination == 0) || iter == 1) {
+      const double t0 = now_s();
+      recover_mu(W_[prev_].p);
+      compute_residuals(W_[prev_].p, s_.p, mu_.p, false, info);
+      res_time += now_s() - t0;
+      cost = info[4];
+      if (fabs(cost) > 1e20) { status = COSMO_B200_UNSOLVED; break; }
+      if (st_.verbose) printf("%lld\t%.4e\t%.4e\t%.4e\t%.4e\n", iter, cost, info[0], info[1], rho_);
+      if (info[0] < st_.eps_abs + st_.eps_rel * info[2] && info[1] < st_.eps_abs + st_.eps_rel * info[3]) {
+        status = COSMO_B200_SOLVED;
+        break;
+      }
+    }
+    if (st_.check_infeasibility > 0 && iter % st_.check_infeasibility == 0) {
+      infeasibility_check_due = true;
+    } else if (infeasibility_check_due) {
+      infeasibility_check_due = false;
+      recover_mu(W_[prev_].p);
+      sub_kernel<T><<<vgrid(m), kBlock, 0, stream_>>>(m, dy_.p, mu_.p, dy_.p);          // dy -= mu
+      check_launch("sub_dy");
+      sub_kernel<T><<<vgrid(n), kBlock, 0, stream_>>>(n, W_[cur_].p, W_[prev_].p, dx_.p);  // dx = w_x - w_prev_x
+      check_launch("sub_dx");
+      if (primal_infeasible()) { status = COSMO_B200_PRIMAL_INFEASIBLE; cost = INFINITY; break; }
+      if (dual_infeasible()) { status = COSMO_B200_DUAL_INFEASIBLE; cost = -INFINITY; break; }
+    }
+    if (st_.time_limit != 0 && (now_s() - iter_start) > st_.time_limit) {
+      recover_mu(W_[prev_].p);
+      compute_residuals(W_[prev_].p, s_.p, mu_.p, false, info);
+      status = COSMO_B200_TIME_LIMIT_REACHED;
+      break;
+    }
+  }
+  recover_mu(W_[prev_].p);  // solver.jl:167
+  CUDA_TRY(cudaEventRecord(ev1_, stream_));
+  sync();
+  const double iter_time = now_s() - iter_start;
+  float dev_ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&dev_ms, ev0_, ev1_));
+  if (iter == st_.max_iter && status == COSMO_B200_UNDETERMINED) {  // solver.jl:173-176
+    compute_residuals(W_[prev_].p, s_.p, mu_.p, false, info);
+    status = COSMO_B200_MAX_ITER_REACHED;
+  }
+  // x = view(w_prev, 1:n): keep it for the next warm start and hand it out
+  CUDA_TRY(cudaMemcpyAsync(xs_.p, W_[prev_].p, n * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+  if (out) {
+    if (out->x) download_vec(out->x, W_[prev_].p, n);
+    if (out->s) download_vec(out->s, s_.p, m);
+    if (out->mu) download_vec(out->mu, mu_.p, m);
+    sync();
+    out->obj_val = cost;
+    out->iter = iter;
+    out->safeguarding_iter = 0;
+    out->status = status;
+    out->r_prim = info[0]; out->r_dual = info[1]; out->max_norm_prim = info[2]; out->max_norm_dual = info[3];
+    out->rho = rho_;
+    out->n_rho_updates = (int64_t)rho_updates_.size();
+    if (out->rho_updates)
+      for (int64_t i = 0; i < std::min<int64_t>(out->rho_updates_cap, out->n_rho_updates); ++i) out->rho_updates[i] = rho_updates_[i];
+    out->setup_time = 0.0;
+    out->iter_time = iter_time;
+    out->iter_time_device = dev_ms * 1e-3;
+    out->proj_time = 0.0;
+    out->kkt_time = 0.0;
+    out->res_time = res_time;
+    out->kkt_inner_iterations = total_inner_;
+    out->kkt_multiplications = total_mults_;
+    out->kernel_launches = launches_ - launches0;
+    out->solver_time = now_s() - t_start;
+  }
+  sync();
+}
+
+// ---- plugin-granularity entry points ---------------------------------------------
+template <typename T>
+void Engine<T>::project(const void* ws, void* s_out) {
+  CUDA_TRY(cudaSetDevice(device_));
+  // stage w_s in the s-part of a scratch operator variable
+  upload_vec(vec_m_, ws, m_);
+  CUDA_TRY(cudaMemcpyAsync(W_[1 - cur_].p + n_, vec_m_.p, m_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+  project_device(W_[1 - cur_].p, false, nullptr);
+  download_vec(s_out, s_.p, m_);
+  sync();
+}
+
+template <typename T>
+void Engine<T>::kkt_solve(const void* rhs, void* sol, int64_t* inner) {
+  CUDA_TRY(cudaSetDevice(device_));
+  upload_vec(ls_, rhs, (size_t)n_ + m_);
+  scale_kernel<T><<<vgrid(m_), kBlock, 0, stream_>>>(m_, rho_vec_.p, ls_.p + n_, t0_.p);
+  check_launch("scale_x2");
+  kkt_core(false, nullptr, nullptr);
+  download_vec(sol, xsol_.p, n_);
+  download_vec(static_cast<T*>(sol) + n_, nu_.p, m_);
+  sync();
+  if (inner) *inner = last_cg_iters_;
+}
+
+template <typename T>
+void Engine<T>::residuals(const void* x, const void* s, const void* mu, int ignore_scaling, double* out) {
+  CUDA_TRY(cudaSetDevice(device_));
+  upload_vec(dx_, x, n_);
+  upload_vec(vec_m_, s, m_);
+  upload_vec(dy_, mu, m_);
+  compute_residuals(dx_.p, vec_m_.p, dy_.p, ignore_scaling != 0, out);
+}
+
+template <typename T>
+void Engine<T>::spmv(int which, const void* x, void* y) {
+  CUDA_TRY(cudaSetDevice(device_));
+  if (which == 0) {
+    upload_vec(dx_, x, n_);
+    launch_spmv(A_, dx_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, m_, EpiStore<T>{nullptr, vec_m_.p}, red(SC_TMP0), "spmv_A");
+    download_vec(y, vec_m_.p, m_);
+  } else if (which == 1) {
+    upload_vec(dy_, x, m_);
+    launch_spmv(At_, dy_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, n_, EpiStore<T>{nullptr, vec_n_.p}, red(SC_TMP0), "spmv_At");
+    download_vec(y, vec_n_.p, n_);
+  } else if (which == 2) {
+    upload_vec(dx_, x, n_);
+    launch_spmv(P_, dx_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, n_, EpiStore<T>{nullptr, vec_n_.p}, red(SC_TMP0), "spmv_P");
+    download_vec(y, vec_n_.p, n_);
+  } else {
+    throw EngineError{COSMO_B200_ERR_INVALID, "spmv: which must be 0 (A), 1 (A') or 2 (P)"};
+  }
+  sync();
+}
+
+template <typename T>
+void Engine<T>::spmv_bench(int which, int reps, double* ms, double* bytes) {
+  CUDA_TRY(cudaSetDevice(device_));
+  if (reps < 1) reps = 1;
+  auto one = [&]() {
+    if (which == 0)
+      launch_spmv(A_, xsol_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, m_, EpiScale<T>{nullptr, tm_.p, rho_vec_.p}, red(SC_TMP0), "spmv_A_scale");
+    else if (which == 1)
+      launch_spmv(At_, tm_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, n_, EpiStore<T>{nullptr, vec_n_.p}, red(SC_TMP0), "spmv_At");
+    else if (which == 2)
+      launch_spmv(P_, xsol_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, n_, EpiStore<T>{nullptr, vec_n_.p}, red(SC_TMP0), "spmv_P");
+    else  // 3: the fused reduced-KKT operator stage 2 (A' and P rows + dot)
+      launch_spmv(At_, tm_.p, &P_, xsol_.p, n_, EpiKktOp<T>{nullptr, cb_.p, xsol_.p, (T)st_.sigma}, red_ptr(cb_.p + n_), "spmv_kkt_op");
+  };
+  for (int i = 0; i < 3; ++i) one();
+  CUDA_TRY(cudaEventRecord(ev0_, stream_));
+  for (int i = 0; i < reps; ++i) one();
+  CUDA_TRY(cudaEventRecord(ev1_, stream_));
+  sync();
+  float t = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&t, ev0_, ev1_));
+  *ms = (double)t / reps;
+  if (which == 0) *bytes = A_.spmv_bytes() + sizeof(T) * (double)m_;       // + rho
+  else if (which == 1) *bytes = At_.spmv_bytes();
+  else if (which == 2) *bytes = P_.spmv_bytes();
+  else *bytes = At_.spmv_bytes() + P_.spmv_bytes() - sizeof(T) * (double)n_;
+}
+
+template <typename T>
+void Engine<T>::get_rho_vec(void* out) { download_vec(out, rho_vec_.p, m_); sync(); }
+template <typename T>
+void Engine<T>::get_w(void* out) { download_vec(out, W_[cur_].p, (size_t)n_ + m_); sync(); }
+
+}  // namespace cosmo
+
+// ============================================================================
+// C ABI
+// ============================================================================
+struct cosmo_b200_handle {
+  cosmo::EngineBase* impl = nullptr;
+  std::string err;
+};
+
+#define ABI_GUARD(h, body)                                                   \
+  if (!(h) || !(h)->impl) return COSMO_B200_ERR_INVALID;                     \
+  try { body; return COSMO_B200_OK; }                                        \
+  catch (const cosmo::EngineError& e) { (h)->err = e.msg; return e.code; }   \
+  catch (const cosmo::PsdError& e) { (h)->err = e.msg; return COSMO_B200_ERR_NUMERICAL; } \
+  catch (const std::bad_alloc&) { (h)->err = "host allocation failed"; return COSMO_B200_ERR_ALLOC; } \
+  catch (...) { (h)->err = "unknown error"; return COSMO_B200_ERR_INVALID; }
+
+extern "C" {
+
+int cosmo_b200_abi_version(void) { return COSMO_B200_ABI_VERSION; }
+
+int cosmo_b200_default_settings(cosmo_b200_settings* s) {
+  if (!s) return COSMO_B200_ERR_INVALID;
+  memset(s, 0, sizeof(*s));
+  s->rho = 0.1; s->sigma = 1e-6; s->alpha = 1.6;
+  s->eps_abs = 1e-5; s->eps_rel = 1e-5; s->eps_prim_inf = 1e-4; s->eps_dual_inf = 1e-4;
+  s->max_iter = 5000; s->check_termination = 25; s->check_infeasibility = 40;
+  s->scaling = 10; s->adaptive_rho = 1; s->adaptive_rho_interval = 40; s->kkt_solver = COSMO_B200_KKT_CG;
+  s->adaptive_rho_tolerance = 5.0; s->adaptive_rho_max_adaptions = INT64_MAX;
+  s->RHO_MIN = 1e-6; s->RHO_MAX = 1e6; s->RHO_TOL = 1e-4; s->RHO_EQ_OVER_RHO_INEQ = 1e3;
+  s->COSMO_INFTY = 1e20; s->MIN_SCALING = 1e-4;
+  s->time_limit = 0.0; s->tol_constant = 1.0; s->tol_exponent = 1.5;
+  s->verbose = 0; s->psd_max_sweeps = 30;
+  return COSMO_B200_OK;
+}
+
+int cosmo_b200_create(cosmo_b200_handle** out, const cosmo_b200_problem* prob, const cosmo_b200_settings* settings) {
+  if (!out || !prob || !settings) { cosmo::g_create_error = "null argument"; return COSMO_B200_ERR_INVALID; }
+  *out = nullptr;
+  try {
+    cosmo::EngineBase* impl = nullptr;
+    if (prob->dtype == COSMO_B200_F64) impl = new cosmo::Engine<double>(*prob, *settings);
+    else if (prob->dtype == COSMO_B200_F32) impl = new cosmo::Engine<float>(*prob, *settings);
+    else throw cosmo::EngineError{COSMO_B200_ERR_UNSUPPORTED, "dtype must be Float64 or Float32 (BigFloat models fall back to the host loop)"};
+    cosmo_b200_handle* h = new cosmo_b200_handle();
+    h->impl = impl;
+    *out = h;
+    return COSMO_B200_OK;
+  } catch (const cosmo::EngineError& e) { cosmo::g_create_error = e.msg; return e.code; }
+  catch (const cosmo::PsdError& e) { cosmo::g_create_error = e.msg; return COSMO_B200_ERR_CUDA; }
+  catch (const std::bad_alloc&) { cosmo::g_create_error = "host allocation failed"; return COSMO_B200_ERR_ALLOC; }
+  catch (...) { cosmo::g_create_error = "unknown error"; return COSMO_B200_ERR_INVALID; }
+}
+
+void cosmo_b200_destroy(cosmo_b200_handle* h) {
+  if (!h) return;
+  delete h->impl;
+  delete h;
+}
+
+const char* cosmo_b200_last_error(const cosmo_b200_handle* h) {
+  return h ? h->err.c_str() : cosmo::g_create_error.c_str();
+}
+
+int cosmo_b200_update_settings(cosmo_b200_handle* h, const cosmo_b200_settings* s) {
+  if (!s) return COSMO_B200_ERR_INVALID;
+  ABI_GUARD(h, h->impl->update_settings(*s));
+}
+int cosmo_b200_warm_start(cosmo_b200_handle* h, const void* x, const void* s, const void* mu) { ABI_GUARD(h, h->impl->warm_start(x, s, mu)); }
+int cosmo_b200_update_qb(cosmo_b200_handle* h, const void* q, const void* b) { ABI_GUARD(h, h->impl->update_qb(q, b)); }
+int cosmo_b200_update_rho(cosmo_b200_handle* h, const void* rho_vec, double rho) { ABI_GUARD(h, h->impl->update_rho(rho_vec, rho)); }
+int cosmo_b200_reset(cosmo_b200_handle* h) { ABI_GUARD(h, h->impl->reset()); }
+int cosmo_b200_solve(cosmo_b200_handle* h, cosmo_b200_result* out) { ABI_GUARD(h, h->impl->solve(out)); }
+int cosmo_b200_project(cosmo_b200_handle* h, const void* w_s, void* s_out) {
+  if (!w_s || !s_out) return COSMO_B200_ERR_INVALID;
+  ABI_GUARD(h, h->impl->project(w_s, s_out));
+}
+int cosmo_b200_kkt_solve(cosmo_b200_handle* h, const void* rhs, void* sol, int64_t* inner) {
+  if (!rhs || !sol) return COSMO_B200_ERR_INVALID;
+  ABI_GUARD(h, h->impl->kkt_solve(rhs, sol, inner));
+}
+int cosmo_b200_residuals(cosmo_b200_handle* h, const void* x, const void* s, const void* mu, int32_t ignore_scaling, double out[5]) {
+  if (!x || !s || !mu || !out) return COSMO_B200_ERR_INVALID;
+  ABI_GUARD(h, h->impl->residuals(x, s, mu, ignore_scaling, out));
+}
+int cosmo_b200_spmv(cosmo_b200_handle* h, int32_t which, const void* x, void* y) {
+  if (!x || !y) return COSMO_B200_ERR_INVALID;
+  ABI_GUARD(h, h->impl->spmv(which, x, y));
+}
+int cosmo_b200_spmv_bench(cosmo_b200_handle* h, int32_t which, int32_t reps, double* ms, double* bytes) {
+  if (!ms || !bytes) return COSMO_B200_ERR_INVALID;
+  ABI_GUARD(h, h->impl->spmv_bench(which, reps, ms, bytes));
+}
+int cosmo_b200_get_rho_vec(cosmo_b200_handle* h, void* out) {
+  if (!out) return COSMO_B200_ERR_INVALID;
+  ABI_GUARD(h, h->impl->get_rho_vec(out));
+}
+int cosmo_b200_get_w(cosmo_b200_handle* h, void* out) {
+  if (!out) return COSMO_B200_ERR_INVALID;
+  ABI_GUARD(h, h->impl->get_w(out));
+}
+int cosmo_b200_comm_unique_id(void* id128) {
+  if (!id128) return COSMO_B200_ERR_INVALID;
+  std::string e;
+  if (!cosmo::g_nccl.load(e)) { cosmo::g_create_error = e; return COSMO_B200_ERR_NCCL; }
+  cosmo::NcclUniqueId id;
+  if (cosmo::g_nccl.GetUniqueId(&id) != 0) { cosmo::g_create_error = "ncclGetUniqueId failed"; return COSMO_B200_ERR_NCCL; }
+  memcpy(id128, &id, sizeof(id));
+  return COSMO_B200_OK;
+}
+int cosmo_b200_comm_init(cosmo_b200_handle* h, int32_t nranks, int32_t rank, const void* id128) {
+  if (nranks > 1 && !id128) return COSMO_B200_ERR_INVALID;
+  ABI_GUARD(h, h->impl->comm_init(nranks, rank, id128));
+}
+
+}  // extern "C"

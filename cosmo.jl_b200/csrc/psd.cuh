@@ -1,0 +1,546 @@
+// psd.cuh -- PSD-cone projection on the device (kernel K6 of SURVEY.md 2a).
+//
+// Replaces project!(x, ::PsdCone / ::PsdConeTriangle) (reference
+// src/convexset.jl:303-321, 402-412 -> _project! :219-241 -> LAPACK ?syevr
+// :163-189 -> rank_k_update! :243-263 -> svec pack/unpack :432-472).
+//
+// Round-1 eigensolver: cyclic two-sided Jacobi with the round-robin parallel
+// ordering, in the cone's own precision (fp64 for Model{Float64}).
+//   * small cones (N <= kPsdSmallMax; the clique batch produced by chordal
+//     decomposition): ONE CTA PER CONE, matrix and eigenvectors resident in
+//     shared memory, every cone of the batch in one launch.
+//   * large cones: matrix/eigenvectors in HBM (L2-resident for N <= ~2800),
+//     one (params, columns, rows) kernel triple per Jacobi round.
+// The projection keeps eigenpairs with lambda > 0 strictly (convexset.jl:250)
+// and rebuilds X+ = sum lambda_k v_k v_k' ; a cone of dim 1 is max(x, 0)
+// (convexset.jl:307-308, 404-405).
+//
+// fp64 note: tcgen05 has no fp64 kind, so this path runs on the
+// FP64 FMA pipe; the tensor-core (split-precision) variant is future work.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace cosmo {
+
+struct PsdConeDesc {
+  int off;       // first row of the cone in s
+  int N;         // matrix side
+  int triangle;  // 1: svec upper triangle (PsdConeTriangle), 0: column-major square (PsdCone)
+};
+
+constexpr int kPsdSmallMax = 96;   // 2 * (N+1)^2 * 8 B <= 227 KB shared memory
+
+template <typename T> struct PsdEps;
+template <> struct PsdEps<double> { static constexpr double v = 2.220446049250313e-16; };
+template <> struct PsdEps<float> { static constexpr double v = 1.1920929e-07; };
+
+// symmetric Schur rotation zeroing a_pq (Golub & Van Loan, Alg. 8.4.1)
+template <typename T>
+__device__ __forceinline__ void sym_schur(T app, T aqq, T apq, T& c, T& s) {
+  const T tau = (aqq - app) / (T(2) * apq);
+  const T t = (tau >= T(0)) ? T(1) / (tau + sqrt(T(1) + tau * tau)) : T(1) / (tau - sqrt(T(1) + tau * tau));
+  c = T(1) / sqrt(T(1) + t * t);
+  s = t * c;
+}
+
+// round-robin tournament pairing: round r in [0, Ne-1), slot k in [0, Ne/2)
+__device__ __forceinline__ void rr_pair(int Ne, int r, int k, int& p, int& q) {
+  const int M = Ne - 1;
+  if (k == 0) { p = r; q = M; }
+  else { p = (r + k) % M; q = (r - k + M) % M; }
+  if (p > q) { int t = p; p = q; q = t; }
+}
+
+// position of (i,j), i<=j, in the column-major upper triangle (convexset.jl:432-442)
+__device__ __forceinline__ long long svec_pos(int i, int j) { return (long long)j * (j + 1) / 2 + i; }
+
+// ---------------------------------------------------------------------------
+// Small cones: one CTA per cone, everything in shared memory.
+//   mode 0: s[cone] = Pi_PSD(ws[cone]);  mode 1: lam_max[cone] = max eigenvalue of mat(ws[cone])
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kBlock) psd_small_kernel(const PsdConeDesc* __restrict__ descs, const T* __restrict__ ws,
+                                                           T* __restrict__ s, int mode, T* __restrict__ lam_max,
+                                                           int max_sweeps, int* __restrict__ fail_flag) {
+  extern __shared__ unsigned char smem_raw[];
+  const PsdConeDesc d = descs[blockIdx.x];
+  const int N = d.N;
+  const T* x = ws + d.off;
+  if (N == 1) {
+    if (threadIdx.x == 0) {
+      const T v = x[0];
+      if (mode == 0) s[d.off] = (v > T(0)) ? v : ((v != v) ? v : T(0));
+      else lam_max[blockIdx.x] = v;
+    }
+    return;
+  }
+  const int ld = N | 1;  // odd leading dimension: conflict-free row sweeps
+  T* A = reinterpret_cast<T*>(smem_raw);
+  T* V = A + (size_t)ld * N;
+  T* cs = V + (size_t)ld * N;   // 2 * (N/2 + 1): rotation cosines / sines of the round
+  __shared__ T red[kWarpsPerBlock];
+  __shared__ int rotated;
+  __shared__ T thr_sh;
+  const T inv_sqrt2 = T(0.70710678118654752440);
+  const T sqrt2 = T(1.41421356237309504880);
+
+  // ---- load: X = mat(x) ----
+  T fro = 0;
+  for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+    const int i = e % N, j = e / N;
+    T v;
+    if (d.triangle) {
+      const int a = i < j ? i : j, b = i < j ? j : i;
+      v = x[svec_pos(a, b)];
+      if (a != b) v *= inv_sqrt2;
+    } else {
+      v = (x[(long long)j * N + i] + x[(long long)i * N + j]) / T(2);   // symmetrize_upper!, algebra.jl:201-208
+    }
+    A[i + j * ld] = v;
+    V[i + j * ld] = (i == j) ? T(1) : T(0);
+    fro += v * v;
+  }
+  fro = warp_sum(fro);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = fro;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    T f = 0;
+    for (int w = 0; w < kWarpsPerBlock; ++w) f += red[w];
+    thr_sh = (T)(PsdEps<T>::v) * sqrt(f);
+  }
+  __syncthreads();
+  const T thr = thr_sh;
+
+  // ---- cyclic Jacobi, round-robin ordering ----
+  const int Ne = (N + 1) & ~1;
+  const int npairs = Ne / 2;
+  int sweep = 0;
+  bool converged = false;
+  for (; sweep < max_sweeps; ++sweep) {
+    if (threadIdx.x == 0) rotated = 0;
+    __syncthreads();
+    for (int r = 0; r < Ne - 1; ++r) {
+      // rotation parameters of this round
+      for (int k = threadIdx.x; k < npairs; k += blockDim.x) {
+        int p, q;
+        rr_pair(Ne, r, k, p, q);
+        T c = T(1), sn = T(0);
+        if (q < N) {
+          const T apq = A[p + q * ld];
+          if (tabs(apq) > thr) {
+            sym_schur(A[p + p * ld], A[q + q * ld], apq, c, sn);
+            rotated = 1;
+          }
+        }
+        cs[2 * k] = c;
+        cs[2 * k + 1] = sn;
+      }
+      __syncthreads();
+      // columns p,q of A and V:  [ap aq] <- [ap aq] * [c s; -s c]
+      for (int e = threadIdx.x; e < npairs * N; e += blockDim.x) {
+        const int k = e / N, i = e % N;
+        const T sn = cs[2 * k + 1];
+        if (sn == T(0)) continue;
+        const T c = cs[2 * k];
+        int p, q;
+        rr_pair(Ne, r, k, p, q);
+        const T aip = A[i + p * ld], aiq = A[i + q * ld];
+        A[i + p * ld] = c * aip - sn * aiq;
+        A[i + q * ld] = sn * aip + c * aiq;
+        const T vip = V[i + p * ld], viq = V[i + q * ld];
+        V[i + p * ld] = c * vip - sn * viq;
+        V[i + q * ld] = sn * vip + c * viq;
+      }
+      __syncthreads();
+      // rows p,q of A
+      for (int e = threadIdx.x; e < npairs * N; e += blockDim.x) {
+        const int k = e / N, j = e % N;
+        const T sn = cs[2 * k + 1];
+        if (sn == T(0)) continue;
+        const T c = cs[2 * k];
+        int p, q;
+        rr_pair(Ne, r, k, p, q);
+        const T apj = A[p + j * ld], aqj = A[q + j * ld];
+        A[p + j * ld] = c * apj - sn * aqj;
+        A[q + j * ld] = sn * apj + c * aqj;
+      }
+      __syncthreads();
+    }
+    if (!rotated) { converged = true; break; }
+    __syncthreads();
+  }
+  if (!converged && threadIdx.x == 0 && fail_flag) atomicExch(fail_flag, 1);
+
+  if (mode == 1) {
+    T mx = -INFINITY;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) mx = fmax(mx, A[i + i * ld]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      T f = red[0];
+      for (int w = 1; w < kWarpsPerBlock; ++w) f = fmax(f, red[w]);
+      lam_max[blockIdx.x] = f;
+    }
+    return;
+  }
+  // ---- V <- V * diag(sqrt(max(lambda,0))) ; X+ = V V' (rank_k_update!, convexset.jl:243-263) ----
+  for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+    const int i = e % N, k = e / N;
+    const T lam = A[k + k * ld];
+    V[i + k * ld] *= (lam > T(0)) ? sqrt(lam) : T(0);
+  }
+  __syncthreads();
+  if (d.triangle) {
+    const int tri = N * (N + 1) / 2;
+    for (int e = threadIdx.x; e < tri; e += blockDim.x) {
+      // invert e -> (i, j), i <= j
+      int j = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
+      while ((long long)(j + 1) * (j + 2) / 2 <= e) ++j;
+      while ((long long)j * (j + 1) / 2 > e) --j;
+      const int i = e - j * (j + 1) / 2;
+      T acc = 0;
+      for (int k = 0; k < N; ++k) acc += V[i + k * ld] * V[j + k * ld];
+      s[d.off + e] = (i == j) ? acc : sqrt2 * acc;
+    }
+  } else {
+    for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+      const int i = e % N, j = e / N;
+      const int a = i < j ? i : j, b = i < j ? j : i;
+      T acc = 0;
+      for (int k = 0; k < N; ++k) acc += V[a + k * ld] * V[b + k * ld];
+      s[d.off + e] = acc;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Large cones: matrix + eigenvectors in global memory, one kernel triple per round.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kBlock) psd_large_load_kernel(PsdConeDesc d, const T* __restrict__ ws, T* __restrict__ A,
+                                                                T* __restrict__ V, T* __restrict__ fro_partials) {
+  const int N = d.N;
+  const T* x = ws + d.off;
+  const T inv_sqrt2 = T(0.70710678118654752440);
+  T fro = 0;
+  const long long total = (long long)N * N;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e % N), j = (int)(e / N);
+    T v;
+    if (d.triangle) {
+      const int a = i < j ? i : j, b = i < j ? j : i;
+      v = x[svec_pos(a, b)];
+      if (a != b) v *= inv_sqrt2;
+    } else {
+      v = (x[(long long)j * N + i] + x[(long long)i * N + j]) / T(2);
+    }
+    A[e] = v;
+    V[e] = (i == j) ? T(1) : T(0);
+    fro += v * v;
+  }
+  __shared__ T red[kWarpsPerBlock];
+  fro = warp_sum(fro);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = fro;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    T f = 0;
+    for (int w = 0; w < kWarpsPerBlock; ++w) f += red[w];
+    fro_partials[blockIdx.x] = f;
+  }
+}
+
+// thr = eps * sqrt(sum partials); rotated flag reset
+template <typename T>
+__global__ void psd_large_thr_kernel(const T* __restrict__ fro_partials, int nparts, T* __restrict__ thr, int* __restrict__ rotated) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    T f = 0;
+    for (int i = 0; i < nparts; ++i) f += fro_partials[i];
+    *thr = (T)(PsdEps<T>::v) * sqrt(f);
+    *rotated = 0;
+  }
+}
+
+template <typename T>
+__global__ void psd_large_params_kernel(int N, int r, const T* __restrict__ A, const T* __restrict__ thr, T* __restrict__ cs,
+                                        int* __restrict__ rotated) {
+  const int Ne = (N + 1) & ~1;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= Ne / 2) return;
+  int p, q;
+  rr_pair(Ne, r, k, p, q);
+  T c = T(1), sn = T(0);
+  if (q < N) {
+    const T apq = A[p + (long long)q * N];
+    if (tabs(apq) > *thr) {
+      sym_schur(A[p + (long long)p * N], A[q + (long long)q * N], apq, c, sn);
+      *rotated = 1;
+    }
+  }
+  cs[2 * k] = c;
+  cs[2 * k + 1] = sn;
+}
+
+// columns p,q of A and V (coalesced along i)
+template <typename T>
+__global__ void __launch_bounds__(kBlock) psd_large_cols_kernel(int N, int r, T* __restrict__ A, T* __restrict__ V,
+                                                                const T* __restrict__ cs) {
+  const int Ne = (N + 1) & ~1;
+  const int k = blockIdx.y;
+  const T sn = cs[2 * k + 1];
+  if (sn == T(0)) return;
+  const T c = cs[2 * k];
+  int p, q;
+  rr_pair(Ne, r, k, p, q);
+  T* Ap = A + (long long)p * N; T* Aq = A + (long long)q * N;
+  T* Vp = V + (long long)p * N; T* Vq = V + (long long)q * N;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    const T aip = Ap[i], aiq = Aq[i];
+    Ap[i] = c * aip - sn * aiq;
+    Aq[i] = sn * aip + c * aiq;
+    const T vip = Vp[i], viq = Vq[i];
+    Vp[i] = c * vip - sn * viq;
+    Vq[i] = sn * vip + c * viq;
+  }
+}
+
+// rows p,q of A: thread j handles column j for every pair (strided reads of 2 elements per pair)
+template <typename T>
+__global__ void __launch_bounds__(kBlock) psd_large_rows_kernel(int N, int r, T* __restrict__ A, const T* __restrict__ cs) {
+  const int Ne = (N + 1) & ~1;
+  const int npairs = Ne / 2;
+  extern __shared__ unsigned char smem_raw[];
+  T* scs = reinterpret_cast<T*>(smem_raw);
+  for (int k = threadIdx.x; k < 2 * npairs; k += blockDim.x) scs[k] = cs[k];
+  __syncthreads();
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  T* col = A + (long long)j * N;
+  for (int k = 0; k < npairs; ++k) {
+    const T sn = scs[2 * k + 1];
+    if (sn == T(0)) continue;
+    const T c = scs[2 * k];
+    int p, q;
+    rr_pair(Ne, r, k, p, q);
+    const T apj = col[p], aqj = col[q];
+    col[p] = c * apj - sn * aqj;
+    col[q] = sn * apj + c * aqj;
+  }
+}
+
+// V[:,k] *= sqrt(max(lambda_k, 0))
+template <typename T>
+__global__ void __launch_bounds__(kBlock) psd_large_scale_kernel(int N, const T* __restrict__ A, T* __restrict__ V) {
+  const long long total = (long long)N * N;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(e / N);
+    const T lam = A[k + (long long)k * N];
+    V[e] *= (lam > T(0)) ? sqrt(lam) : T(0);
+  }
+}
+
+// out = svec / square of (V V') upper triangle, 32x32 output tiles, K-tiles of 32 through shared memory
+template <typename T>
+__global__ void __launch_bounds__(256) psd_large_syrk_kernel(PsdConeDesc d, const T* __restrict__ V, T* __restrict__ s) {
+  const int N = d.N;
+  const int bi = blockIdx.x, bj = blockIdx.y;
+  if (bi > bj) return;  // upper triangle of tiles
+  __shared__ T Vi[32][33];
+  __shared__ T Vj[32][33];
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;  // ty in [0, 8)
+  T acc[4] = {0, 0, 0, 0};
+  for (int k0 = 0; k0 < N; k0 += 32) {
+    for (int rr = ty; rr < 32; rr += 8) {   // rr: k within tile, tx: row within tile (coalesced along rows)
+      const int k = k0 + rr;
+      const int gi = bi * 32 + tx, gj = bj * 32 + tx;
+      Vi[rr][tx] = (k < N && gi < N) ? V[gi + (long long)k * N] : T(0);
+      Vj[rr][tx] = (k < N && gj < N) ? V[gj + (long long)k * N] : T(0);
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      const T vi = Vi[k][tx];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] += vi * Vj[k][ty + 8 * u];
+    }
+    __syncthreads();
+  }
+  const T sqrt2 = T(1.41421356237309504880);
+  const int i = bi * 32 + tx;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int j = bj * 32 + ty + 8 * u;
+    if (i < N && j < N && i <= j) {
+      if (d.triangle) {
+        s[d.off + svec_pos(i, j)] = (i == j) ? acc[u] : sqrt2 * acc[u];
+      } else {
+        s[d.off + (long long)j * N + i] = acc[u];
+        s[d.off + (long long)i * N + j] = acc[u];   // mirror, convexset.jl:316-318
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void psd_large_lammax_kernel(int N, const T* __restrict__ A, T* __restrict__ out) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    T mx = -INFINITY;
+    for (int i = 0; i < N; ++i) mx = fmax(mx, A[i + (long long)i * N]);
+    *out = mx;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Host-side batch object
+// ---------------------------------------------------------------------------
+struct PsdError { std::string msg; };
+
+template <typename T>
+struct PsdBatch {
+  std::vector<PsdConeDesc> small_h, large_h;
+  PsdConeDesc* small_d = nullptr;
+  T* lam_small_d = nullptr;
+  int* fail_d = nullptr;
+  int small_maxN = 0;
+  // large-cone workspace (sized for the largest cone, cones processed one after another)
+  int large_maxN = 0;
+  T *A_d = nullptr, *V_d = nullptr, *cs_d = nullptr, *fro_d = nullptr, *thr_d = nullptr, *lam_large_d = nullptr;
+  int* rot_d = nullptr;
+  int* rot_h = nullptr;  // pinned
+  std::vector<T> lam_host;
+
+  ~PsdBatch() {
+    cudaFree(small_d); cudaFree(lam_small_d); cudaFree(fail_d); cudaFree(A_d); cudaFree(V_d); cudaFree(cs_d);
+    cudaFree(fro_d); cudaFree(thr_d); cudaFree(lam_large_d); cudaFree(rot_d);
+    if (rot_h) cudaFreeHost(rot_h);
+  }
+  bool empty() const { return small_h.empty() && large_h.empty(); }
+
+  static void ck(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) throw PsdError{std::string(what) + ": " + cudaGetErrorString(e)};
+  }
+
+  void init(const std::vector<PsdConeDesc>& descs, cudaStream_t st) {
+    for (const auto& d : descs) (d.N <= kPsdSmallMax ? small_h : large_h).push_back(d);
+    if (!small_h.empty()) {
+      for (const auto& d : small_h) small_maxN = std::max(small_maxN, d.N);
+      ck(cudaMalloc(&small_d, small_h.size() * sizeof(PsdConeDesc)), "cudaMalloc psd descs");
+      ck(cudaMemcpyAsync(small_d, small_h.data(), small_h.size() * sizeof(PsdConeDesc), cudaMemcpyHostToDevice, st), "copy psd descs");
+      ck(cudaMalloc(&lam_small_d, small_h.size() * sizeof(T)), "cudaMalloc lam");
+      const size_t smem = small_smem();
+      ck(cudaFuncSetAttribute(psd_small_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+    }
+    ck(cudaMalloc(&fail_d, sizeof(int)), "cudaMalloc fail flag");
+    ck(cudaMemsetAsync(fail_d, 0, sizeof(int), st), "memset");
+    if (!large_h.empty()) {
+      for (const auto& d : large_h) large_maxN = std::max(large_maxN, d.N);
+      const size_t nn = (size_t)large_maxN * large_maxN;
+      ck(cudaMalloc(&A_d, nn * sizeof(T)), "cudaMalloc psd A");
+      ck(cudaMalloc(&V_d, nn * sizeof(T)), "cudaMalloc psd V");
+      ck(cudaMalloc(&cs_d, (size_t)(large_maxN + 2) * sizeof(T)), "cudaMalloc cs");
+      ck(cudaMalloc(&fro_d, kMaxGrid * sizeof(T)), "cudaMalloc fro");
+      ck(cudaMalloc(&thr_d, sizeof(T)), "cudaMalloc thr");
+      ck(cudaMalloc(&lam_large_d, large_h.size() * sizeof(T)), "cudaMalloc lam");
+      ck(cudaMalloc(&rot_d, sizeof(int)), "cudaMalloc rot");
+      ck(cudaMallocHost(&rot_h, sizeof(int)), "cudaMallocHost rot");
+      const int npairs = ((large_maxN + 1) & ~1) / 2;
+      ck(cudaFuncSetAttribute(psd_large_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * npairs * sizeof(T))), "smem attr rows");
+    }
+    ck(cudaStreamSynchronize(st), "sync");
+  }
+  size_t small_smem() const {
+    const size_t ld = (size_t)(small_maxN | 1);
+    return (2 * ld * small_maxN + 2 * (size_t)(small_maxN / 2 + 2)) * sizeof(T);
+  }
+  void reset_warm_start() {}
+
+  // eigen-decompose one large cone into A_d (diagonal = eigenvalues) and V_d
+  void large_eig(const PsdConeDesc& d, const T* ws, cudaStream_t st, int max_sweeps, long long& launches) {
+    const int N = d.N;
+    const int Ne = (N + 1) & ~1, npairs = Ne / 2;
+    const int g = (int)std::min<long long>(((long long)N * N + kBlock - 1) / kBlock, kMaxGrid);
+    psd_large_load_kernel<T><<<g, kBlock, 0, st>>>(d, ws, A_d, V_d, fro_d);
+    psd_large_thr_kernel<T><<<1, 32, 0, st>>>(fro_d, g, thr_d, rot_d);
+    launches += 2;
+    bool converged = false;
+    for (int sweep = 0; sweep < max_sweeps && !converged; ++sweep) {
+      for (int r = 0; r < Ne - 1; ++r) {
+        psd_large_params_kernel<T><<<(npairs + 127) / 128, 128, 0, st>>>(N, r, A_d, thr_d, cs_d, rot_d);
+        dim3 gc((N + kBlock - 1) / kBlock, npairs);
+        psd_large_cols_kernel<T><<<gc, kBlock, 0, st>>>(N, r, A_d, V_d, cs_d);
+        psd_large_rows_kernel<T><<<(N + kBlock - 1) / kBlock, kBlock, 2 * npairs * sizeof(T), st>>>(N, r, A_d, cs_d);
+        launches += 3;
+      }
+      ck(cudaMemcpyAsync(rot_h, rot_d, sizeof(int), cudaMemcpyDeviceToHost, st), "copy rot");
+      ck(cudaMemsetAsync(rot_d, 0, sizeof(int), st), "memset rot");
+      ck(cudaStreamSynchronize(st), "sync");
+      if (*rot_h == 0) converged = true;
+    }
+    ck(cudaGetLastError(), "psd large kernels");
+    if (!converged) throw PsdError{"Jacobi eigensolver did not converge within psd_max_sweeps"};
+  }
+
+  // s[cone rows] = Pi_PSD(ws[cone rows]) for every PSD cone
+  void project(const T* ws, T* s, cudaStream_t st, int max_sweeps, long long& launches) {
+    if (empty()) return;
+    if (max_sweeps <= 0) max_sweeps = 30;
+    if (!small_h.empty()) {
+      psd_small_kernel<T><<<(int)small_h.size(), kBlock, small_smem(), st>>>(small_d, ws, s, 0, lam_small_d, max_sweeps, fail_d);
+      ck(cudaGetLastError(), "psd_small_kernel");
+      ++launches;
+    }
+    for (const auto& d : large_h) {
+      large_eig(d, ws, st, max_sweeps, launches);
+      const int N = d.N;
+      const int g = (int)std::min<long long>(((long long)N * N + kBlock - 1) / kBlock, kMaxGrid);
+      psd_large_scale_kernel<T><<<g, kBlock, 0, st>>>(N, A_d, V_d);
+      dim3 gt((N + 31) / 32, (N + 31) / 32);
+      psd_large_syrk_kernel<T><<<gt, 256, 0, st>>>(d, V_d, s);
+      ck(cudaGetLastError(), "psd large reconstruct");
+      launches += 2;
+    }
+  }
+
+  // true iff lambda_max(mat(v_cone)) < tol for every PSD cone, i.e. -mat(v) + tol I is
+  // positive definite (is_pos_def!/is_neg_def!, algebra.jl:226-238; convexset.jl:324-336,415-425)
+  bool certificate(const T* v, bool /*negate*/, double tol, cudaStream_t st, int max_sweeps, long long& launches) {
+    if (empty()) return true;
+    if (max_sweeps <= 0) max_sweeps = 30;
+    bool ok = true;
+    if (!small_h.empty()) {
+      psd_small_kernel<T><<<(int)small_h.size(), kBlock, small_smem(), st>>>(small_d, v, nullptr, 1, lam_small_d, max_sweeps, fail_d);
+      ck(cudaGetLastError(), "psd_small_kernel");
+      ++launches;
+      lam_host.resize(small_h.size());
+      ck(cudaMemcpyAsync(lam_host.data(), lam_small_d, small_h.size() * sizeof(T), cudaMemcpyDeviceToHost, st), "copy lam");
+      ck(cudaStreamSynchronize(st), "sync");
+      for (T l : lam_host) if (!((double)l < tol)) ok = false;
+    }
+    for (size_t k = 0; k < large_h.size(); ++k) {
+      large_eig(large_h[k], v, st, max_sweeps, launches);
+      psd_large_lammax_kernel<T><<<1, 32, 0, st>>>(large_h[k].N, A_d, lam_large_d + k);
+      ++launches;
+      T l;
+      ck(cudaMemcpyAsync(&l, lam_large_d + k, sizeof(T), cudaMemcpyDeviceToHost, st), "copy lam");
+      ck(cudaStreamSynchronize(st), "sync");
+      if (!((double)l < tol)) ok = false;
+    }
+    return ok;
+  }
+
+  bool failed(cudaStream_t st) {
+    int f = 0;
+    ck(cudaMemcpyAsync(&f, fail_d, sizeof(int), cudaMemcpyDeviceToHost, st), "copy fail");
+    ck(cudaStreamSynchronize(st), "sync");
+    return f != 0;
+  }
+};
+
+}  // namespace cosmo

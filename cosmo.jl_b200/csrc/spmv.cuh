@@ -1,0 +1,247 @@
+// spmv.cuh -- CSR SpMV family with fused epilogues (kernels K1-K3 of SURVEY.md 2a).
+//
+// Replaces the reference's single-threaded SparseArrays.mul! calls at
+//   src/linear_solver/kktsolver_indirect.jl:53,59-63,81   (KKT operator)
+//   src/residuals.jl:4,12,15,65,81,91,145                  (residuals / cost)
+//   src/infeasibility.jl:12,44,53                          (certificates)
+//
+// One kernel template serves every use: a row's dot product is taken over up
+// to two CSR matrices that share the row index (A' and P for the reduced KKT
+// operator  c = A'(rho.*(A u)) + P u + sigma u), then a functor epilogue turns
+// (row, sum) into the output and into up to 8 deterministic reductions.
+//
+// HBM-bound: 12 B per nonzero (8 B value + 4 B index) are streamed once with
+// 128-bit __ldcs loads (values: 2 x double2, indices: int4 per lane per step),
+// the gathered vector is read through L1/L2 with __ldg.  Rows are peeled to a
+// 4-element boundary so that the streams stay 16/32-byte aligned.
+#pragma once
+#include "common.cuh"
+
+namespace cosmo {
+
+// Partial dot product of one CSR row with a dense vector, LANES cooperating
+// lanes (32 => vectorised stream path).  Returns this lane's partial sum.
+template <typename T, int LANES>
+__device__ __forceinline__ T row_partial(const CsrView<T>& M, const T* __restrict__ x, int row, int lane) {
+  const int start = __ldg(M.rowptr + row);
+  const int end = __ldg(M.rowptr + row + 1);
+  T s0 = 0, s1 = 0;
+  if (LANES == 32) {
+    int a0 = (start + 3) & ~3;
+    if (a0 > end) a0 = end;
+    {  // head: < 4 unaligned elements
+      const int i = start + lane;
+      if (i < a0) s0 += __ldcs(M.val + i) * __ldg(x + __ldcs(M.col + i));
+    }
+    const int body_end = a0 + ((end - a0) & ~3);
+#pragma unroll 2
+    for (int j = a0 + lane * 4; j < body_end; j += 128) {
+      const int4 c = load4_stream(M.col + j);
+      T v[4];
+      load4_stream(M.val + j, v);
+      s0 += v[0] * __ldg(x + c.x);
+      s1 += v[1] * __ldg(x + c.y);
+      s0 += v[2] * __ldg(x + c.z);
+      s1 += v[3] * __ldg(x + c.w);
+    }
+    {  // tail: < 4 elements
+      const int i = body_end + lane;
+      if (i < end) s1 += __ldcs(M.val + i) * __ldg(x + __ldcs(M.col + i));
+    }
+  } else {
+    for (int j = start + lane; j < end; j += LANES) s0 += __ldcs(M.val + j) * __ldg(x + __ldcs(M.col + j));
+  }
+  return s0 + s1;
+}
+
+template <typename T, int LANES>
+__device__ __forceinline__ T group_sum(T v) {
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, LANES);
+  return v;
+}
+
+// Epi concept:
+//   static constexpr int NS, NM;            reduction slots (sums, maxes)
+//   const int* done;                        optional early-exit flag (nullptr = none)
+//   __device__ void row(int r, T sum, T* accS, T* accM) const;
+//   __device__ void finalize(T* out) const; scalar epilogue, one thread, after the fold
+template <typename T, int LANES, typename Epi>
+__global__ void __launch_bounds__(kBlock) spmv_kernel(CsrView<T> M1, const T* __restrict__ x1, CsrView<T> M2,
+                                                      const T* __restrict__ x2, int nrows, Epi epi, RedBuf<T> rb) {
+  if (epi.done != nullptr && *epi.done) return;
+  constexpr int GROUPS = kBlock / LANES;
+  const int lane = threadIdx.x % LANES;
+  const int group = threadIdx.x / LANES;
+  const int total_groups = gridDim.x * GROUPS;
+  T accS[Epi::NS > 0 ? Epi::NS : 1];
+  T accM[Epi::NM > 0 ? Epi::NM : 1];
+#pragma unroll
+  for (int k = 0; k < (Epi::NS > 0 ? Epi::NS : 1); ++k) accS[k] = 0;
+#pragma unroll
+  for (int k = 0; k < (Epi::NM > 0 ? Epi::NM : 1); ++k) accM[k] = 0;
+
+  for (int row = blockIdx.x * GROUPS + group; row < nrows; row += total_groups) {
+    T s = 0;
+    if (M1.rowptr != nullptr) s += row_partial<T, LANES>(M1, x1, row, lane);
+    if (M2.rowptr != nullptr) s += row_partial<T, LANES>(M2, x2, row, lane);
+    s = group_sum<T, LANES>(s);
+    if (lane == 0) epi.row(row, s, accS, accM);
+  }
+  if constexpr (Epi::NS + Epi::NM > 0) {
+    reduce_and_finalize<T, Epi::NS, Epi::NM>(accS, accM, rb, epi);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Epilogues
+// ---------------------------------------------------------------------------
+
+// y = sum                                   (plain mul!)
+template <typename T>
+struct EpiStore {
+  static constexpr int NS = 0, NM = 0;
+  const int* done;
+  T* y;
+  __device__ void row(int r, T s, T*, T*) const { y[r] = s; }
+  __device__ void operator()(T*) const {}
+};
+
+// t = rho .* (A u)                          (kktsolver_indirect.jl:59-60)
+template <typename T>
+struct EpiScale {
+  static constexpr int NS = 0, NM = 0;
+  const int* done;
+  T* y;
+  const T* rho;
+  __device__ void row(int r, T s, T*, T*) const { y[r] = rho[r] * s; }
+  __device__ void operator()(T*) const {}
+};
+
+// c = (A' t) + (P u) + sigma u ;  dot = u'c   (kktsolver_indirect.jl:61-65 + CG's dot(u, c))
+// add_local = 0 on ranks > 0 of a row-sharded run: only rank 0 adds the replicated P/sigma terms.
+template <typename T>
+struct EpiKktOp {
+  static constexpr int NS = 1, NM = 0;
+  const int* done;
+  T* c;
+  const T* u;
+  T sigma;
+  __device__ void row(int r, T s, T* accS, T*) const {
+    const T ur = u[r];
+    const T v = s + sigma * ur;
+    c[r] = v;
+    accS[0] += ur * v;
+  }
+  __device__ void operator()(T*) const {}
+};
+
+// rhs = x1 + A'(rho .* x2)                  (kktsolver_indirect.jl:52-54)
+template <typename T>
+struct EpiAddVec {
+  static constexpr int NS = 0, NM = 0;
+  const int* done;
+  T* y;
+  const T* add;  // may be nullptr (ranks > 0)
+  __device__ void row(int r, T s, T*, T*) const { y[r] = add ? s + add[r] : s; }
+  __device__ void operator()(T*) const {}
+};
+
+// nu = rho .* (A y1 - x2)                   (kktsolver_indirect.jl:80-83), plugin entry
+template <typename T>
+struct EpiY2 {
+  static constexpr int NS = 0, NM = 0;
+  const int* done;
+  T* nu;
+  const T* x2;
+  const T* rho;
+  __device__ void row(int r, T s, T*, T*) const { nu[r] = rho[r] * (s - x2[r]); }
+  __device__ void operator()(T*) const {}
+};
+
+// Fused ADMM tail on the last SpMV of the x-step:
+//   nu   = rho .* (A y1 - x2)               (kktsolver_indirect.jl:80-83)
+//   s_tl = 2 s - w_s - nu ./ rho            (solver.jl:55)
+//   w_s  = w_s + alpha (s_tl - s)           (solver.jl:64)
+template <typename T>
+struct EpiAdmmTail {
+  static constexpr int NS = 0, NM = 0;
+  const int* done;
+  const T* x2;
+  const T* rho;
+  const T* s;
+  const T* ws_in;
+  T* ws_out;
+  T alpha;
+  __device__ void row(int r, T sum, T*, T*) const {
+    const T rh = rho[r];
+    const T nu = rh * (sum - x2[r]);
+    const T sr = s[r], w = ws_in[r];
+    const T s_tl = T(2) * sr - w - nu / rh;
+    ws_out[r] = w + alpha * (s_tl - sr);
+  }
+  __device__ void operator()(T*) const {}
+};
+
+// Primal residual pass (residuals.jl:2-8,30-53,56-74):
+//   max0 = |Einv (A x + s - b)|_inf, max1 = |Einv A x|_inf, max2 = |Einv s|_inf, max3 = |Einv b|_inf
+template <typename T>
+struct EpiPrimalRes {
+  static constexpr int NS = 0, NM = 4;
+  const int* done;
+  const T* s;
+  const T* b;
+  const T* Einv;  // nullptr => identity
+  T* ax_out;      // optional store of A x (nullptr = skip)
+  __device__ void row(int r, T ax, T*, T* accM) const {
+    const T e = Einv ? Einv[r] : T(1);
+    const T sr = s[r], br = b[r];
+    accM[0] = nanmax(accM[0], tabs(e * (ax + sr - br)));
+    accM[1] = nanmax(accM[1], tabs(e * ax));
+    accM[2] = nanmax(accM[2], tabs(e * sr));
+    accM[3] = nanmax(accM[3], tabs(e * br));
+    if (ax_out) ax_out[r] = ax;
+  }
+  __device__ void operator()(T*) const {}
+};
+
+// Dual residual pass over P rows with A'mu precomputed (residuals.jl:11-18,76-94,143-147):
+//   max0 = |Dc (P x + q - A'mu)|_inf, max1 = |Dc P x|_inf, max2 = |Dc q|_inf, max3 = |Dc A'mu|_inf
+//   sum0 = x'(P x), sum1 = q'x            with Dc = cinv * Dinv
+template <typename T>
+struct EpiDualRes {
+  static constexpr int NS = 2, NM = 4;
+  const int* done;
+  const T* x;
+  const T* q;
+  const T* atmu;
+  const T* Dinv;  // nullptr => identity
+  T cinv;
+  __device__ void row(int r, T px, T* accS, T* accM) const {
+    const T d = (Dinv ? Dinv[r] : T(1)) * cinv;
+    const T qr = q[r], ar = atmu[r], xr = x[r];
+    accM[0] = nanmax(accM[0], tabs(d * (px + qr - ar)));
+    accM[1] = nanmax(accM[1], tabs(d * px));
+    accM[2] = nanmax(accM[2], tabs(d * qr));
+    accM[3] = nanmax(accM[3], tabs(d * ar));
+    accS[0] += xr * px;
+    accS[1] += qr * xr;
+  }
+  __device__ void operator()(T*) const {}
+};
+
+// y = sum, max0 = |scale .* sum|_inf        (infeasibility.jl:12-18, 44-50)
+template <typename T>
+struct EpiStoreScaledMax {
+  static constexpr int NS = 0, NM = 1;
+  const int* done;
+  T* y;              // may be nullptr
+  const T* scale;    // nullptr => identity
+  __device__ void row(int r, T s, T*, T* accM) const {
+    if (y) y[r] = s;
+    accM[0] = nanmax(accM[0], tabs((scale ? scale[r] : T(1)) * s));
+  }
+  __device__ void operator()(T*) const {}
+};
+
+}  // namespace cosmo

@@ -1,0 +1,93 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads and exports
+every symbol include/cosmo_b200.h declares; without a GPU the product path fails
+loudly (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cosmo_b200
+from cosmo_b200 import engine as E
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "cosmo_b200.h")).read()
+    return sorted(set(re.findall(r"\b(cosmo_b200_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    lib = E.load_library()
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(E.EXPORTS) == declared
+    assert lib.cosmo_b200_abi_version() == 1
+
+
+def test_default_settings_match_reference():
+    s = E.default_settings()  # src/settings.jl:101-139
+    assert (s.rho, s.sigma, s.alpha) == (0.1, 1e-6, 1.6)
+    assert (s.eps_abs, s.eps_rel, s.eps_prim_inf, s.eps_dual_inf) == (1e-5, 1e-5, 1e-4, 1e-4)
+    assert (s.max_iter, s.check_termination, s.check_infeasibility, s.scaling) == (5000, 25, 40, 10)
+    assert (s.adaptive_rho, s.adaptive_rho_interval, s.adaptive_rho_tolerance) == (1, 40, 5.0)
+    assert (s.RHO_MIN, s.RHO_MAX, s.RHO_TOL, s.RHO_EQ_OVER_RHO_INEQ) == (1e-6, 1e6, 1e-4, 1e3)
+    assert (s.tol_constant, s.tol_exponent) == (1.0, 1.5)
+
+
+def test_struct_sizes():
+    # keep the ctypes mirrors in sync with the C header layout
+    assert ctypes.sizeof(E.CscStruct) == 40
+    assert ctypes.sizeof(E.SetStruct) == 32
+    assert ctypes.sizeof(E.ProblemStruct) == 16 + 16 + 80 + 16 + 16 + 32 + 8
+    assert ctypes.sizeof(E.SettingsStruct) == 56 + 8 + 24 + 16 + 48 + 24 + 8
+    assert ctypes.sizeof(E.ResultStruct) == 24 + 24 + 8 + 40 + 24 + 56 + 24
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    P, q, A, b, sets = cosmo_b200.problems.random_sparse_qp(50, 100, 0.1, seed=0)
+    m = cosmo_b200.Model()
+    m.set(P, q, A, b, sets, cosmo_b200.Settings())
+    with pytest.raises(cosmo_b200.EngineError) as ei:
+        m.optimize()
+    assert ei.value.code == E.ERR_CUDA and "no CPU fallback" in str(ei.value)
+
+
+def test_host_mirror_assemble_matches_reference_ordering():
+    # moi_wrapper.jl:266-271 / interface.jl:411-475: merge Zero & Nonneg, stable sort by type
+    from tests import golden_problems as G
+    from oracle import cosmo_oracle as O
+    P, q, cons = G.g3_hs21()
+    Pm, qm, A, b, cones = O.assemble(P, q, cons)
+    mine = [cosmo_b200.Constraint(c.A, c.b, _conv(c.convex_set)) for c in cons]
+    m = cosmo_b200.Model()
+    m.assemble(P, q, mine, cosmo_b200.Settings())
+    assert [type(s).__name__ for s in m.sets0] == [type(c).__name__ for c in cones]
+    assert np.array_equal(m.A0.toarray(), A.toarray()) and np.array_equal(m.b0, b)
+
+
+def _conv(c):
+    from oracle import cosmo_oracle as O
+    if isinstance(c, O.Box):
+        return cosmo_b200.Box(c.l, c.u)
+    return getattr(cosmo_b200, type(c).__name__)(c.dim)
+
+
+def test_ruiz_matches_oracle():
+    from oracle import cosmo_oracle as O
+    P, q, A, b, sets = cosmo_b200.problems.random_sparse_qp(60, 90, 0.2, seed=3)
+    st = cosmo_b200.Settings()
+    P1, q1, A1, b1, s1, D, Em, c = cosmo_b200.ruiz_equilibrate(P, q, A, b, sets, st)
+    P2, q2, A2, b2, s2, sm = O.scale_ruiz(P, q, A, b, cosmo_b200.problems.to_oracle_cones(sets), O.Settings())
+    assert np.allclose(D, sm.D, rtol=1e-13) and np.allclose(Em, sm.E, rtol=1e-13) and abs(c - sm.c) < 1e-13 * abs(c)
+    assert np.allclose(A1.toarray(), A2.toarray(), rtol=1e-12, atol=1e-14)
+    assert np.allclose(P1.toarray(), P2.toarray(), rtol=1e-12, atol=1e-14)
+    assert np.allclose(q1, q2, rtol=1e-12) and np.allclose(b1, b2, rtol=1e-12)
+    assert np.allclose(s1[1].l, s2[1].l, rtol=1e-12) and np.allclose(s1[1].u, s2[1].u, rtol=1e-12)

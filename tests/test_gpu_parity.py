@@ -1,0 +1,376 @@
+"""GPU parity tests: every call goes through the C ABI (ctypes -> libcosmo_b200.so)
+and is compared with the CPU oracle on identical seeded inputs (SURVEY.md 8c
+parity protocol).  Tolerances are stated per test."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import cosmo_b200
+from cosmo_b200 import engine as E
+from oracle import cosmo_oracle as O
+from tests import golden_problems as G
+
+pytestmark = pytest.mark.gpu
+
+
+def _tuples(sets):
+    return [(S.code, S.dim, getattr(S, "l", None), getattr(S, "u", None)) for S in sets]
+
+
+def _engine(P, q, A, b, sets, dtype=np.float64, **kw):
+    st = cosmo_b200.Settings(**kw).to_struct()
+    return E.Engine(P, q, A, b, _tuples(sets), st, dtype=dtype)
+
+
+def _ragged_matrix(rng, m, n):
+    """rows of length 0, 1, 2, 3, 5, ~n/3 and full: exercises head/body/tail peeling"""
+    rows, cols, vals = [], [], []
+    for i in range(m):
+        k = [0, 1, 2, 3, 5, 7, n // 3, n][i % 8]
+        k = min(k, n)
+        c = np.sort(rng.choice(n, size=k, replace=False))
+        rows += [i] * k
+        cols += list(c)
+        vals += list(rng.standard_normal(k))
+    return sp.csc_matrix((vals, (rows, cols)), shape=(m, n))
+
+
+# ---------------------------------------------------------------------------
+# K1-K3: SpMV (kktsolver_indirect.jl:53-63 mul! calls)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("m,n", [(1, 1), (17, 9), (64, 257), (300, 131), (1000, 515)])
+def test_spmv_ragged(m, n):
+    rng = np.random.default_rng(m * 1000 + n)
+    A = _ragged_matrix(rng, m, n)
+    B = _ragged_matrix(rng, n, n)
+    P = sp.csc_matrix(B + B.T)
+    eng = _engine(P, np.zeros(n), A, np.zeros(m), [cosmo_b200.Nonnegatives(m)])
+    x = rng.standard_normal(n)
+    y = rng.standard_normal(m)
+    for which, M, v in ((0, A, x), (1, A.T, y), (2, P, x)):
+        got = eng.spmv(which, v)
+        ref = M @ v
+        scale = np.abs(M) @ np.abs(v) + 1e-300
+        assert np.max(np.abs(got - ref) / scale) < 1e-14, which  # summation order differs only
+
+
+@pytest.mark.parametrize("density,lanes", [(0.002, 2), (0.02, 8), (0.2, 32)])
+def test_spmv_lane_variants(density, lanes):
+    rng = np.random.default_rng(5)
+    m, n = 3000, 1500
+    A = sp.random(m, n, density=density, random_state=rng, data_rvs=rng.standard_normal, format="csc")
+    P = sp.identity(n, format="csc")
+    eng = _engine(P, np.zeros(n), A, np.zeros(m), [cosmo_b200.Nonnegatives(m)])
+    x, y = rng.standard_normal(n), rng.standard_normal(m)
+    assert np.allclose(eng.spmv(0, x), A @ x, rtol=1e-12, atol=1e-12)
+    assert np.allclose(eng.spmv(1, y), A.T @ y, rtol=1e-12, atol=1e-12)
+
+
+def test_spmv_float32():
+    rng = np.random.default_rng(6)
+    m, n = 500, 300
+    A = sp.random(m, n, density=0.1, random_state=rng, data_rvs=rng.standard_normal, format="csc")
+    eng = _engine(sp.identity(n, format="csc"), np.zeros(n), A, np.zeros(m), [cosmo_b200.Nonnegatives(m)], dtype=np.float32)
+    x = rng.standard_normal(n).astype(np.float32)
+    ref = A.astype(np.float32) @ x
+    assert np.allclose(eng.spmv(0, x), ref, rtol=2e-5, atol=2e-5)  # fp32 tolerance (Model{Float32})
+
+
+# ---------------------------------------------------------------------------
+# K5/K6: composite projection (convexset.jl:885-891)
+# ---------------------------------------------------------------------------
+def _composite(rng, psd_sizes=(1, 2, 5, 16), square=(3,), soc=(1, 2, 9, 20000)):
+    sets = [cosmo_b200.ZeroSet(7), cosmo_b200.Nonnegatives(33)]
+    l = rng.standard_normal(21) - 1.0
+    u = l + rng.random(21) * 2
+    l[3], u[5] = -np.inf, np.inf
+    l[7] = u[7]
+    sets.append(cosmo_b200.Box(l, u))
+    sets += [cosmo_b200.SecondOrderCone(d) for d in soc]
+    sets += [cosmo_b200.PsdCone(N * N) for N in square]
+    sets += [cosmo_b200.PsdConeTriangle(N * (N + 1) // 2) for N in psd_sizes]
+    return sets
+
+
+def test_project_composite_matches_oracle():
+    rng = np.random.default_rng(11)
+    sets = _composite(rng)
+    m = sum(S.dim for S in sets)
+    n = 4
+    A = sp.random(m, n, density=0.3, random_state=rng, format="csc")
+    eng = _engine(sp.identity(n, format="csc"), np.zeros(n), A, np.zeros(m), sets)
+    cones = cosmo_b200.problems.to_oracle_cones(sets)
+    for trial in range(3):
+        ws = rng.standard_normal(m) * (10.0 ** trial)
+        ws[3] = np.nan if trial == 2 else ws[3]          # NaN propagates through max(x, 0) like Julia
+        ref = ws.copy()
+        O.project(ref, cones)
+        got = eng.project(ws)
+        off = 0
+        for S in sets:
+            seg = slice(off, off + S.dim)
+            if isinstance(S, (cosmo_b200.ZeroSet, cosmo_b200.Nonnegatives, cosmo_b200.Box)):
+                assert np.array_equal(got[seg], ref[seg], equal_nan=True), type(S)     # bit-exact clamp cones
+            elif isinstance(S, cosmo_b200.SecondOrderCone):
+                assert np.allclose(got[seg], ref[seg], rtol=1e-14, atol=1e-14 * (1 + np.abs(ref[seg]).max()))
+            else:  # PSD: |Pi_gpu - Pi_lapack|_F / |X|_F <= 1e-12
+                nrm = np.linalg.norm(ws[seg]) + 1e-300
+                assert np.linalg.norm(got[seg] - ref[seg]) / nrm < 1e-12, (type(S), S.dim)
+            off += S.dim
+
+
+def test_soc_branches():
+    # convexset.jl:100-114: inside cone, inside polar cone, and the generic case
+    sets = [cosmo_b200.SecondOrderCone(4)] * 3
+    ws = np.array([5.0, 1, 1, 1, -5.0, 1, 1, 1, 0.5, 1, 2, 2])
+    eng = _engine(sp.identity(1, format="csc"), np.zeros(1), sp.csc_matrix((12, 1)), np.zeros(12), sets)
+    ref = ws.copy()
+    O.project(ref, cosmo_b200.problems.to_oracle_cones(sets))
+    got = eng.project(ws)
+    assert np.array_equal(got[:8], ref[:8])
+    assert np.allclose(got[8:], ref[8:], rtol=1e-15)
+
+
+@pytest.mark.parametrize("N", [97, 130])
+def test_project_psd_large_path(N):
+    rng = np.random.default_rng(N)
+    d = N * (N + 1) // 2
+    sets = [cosmo_b200.PsdConeTriangle(d)]
+    eng = _engine(sp.identity(1, format="csc"), np.zeros(1), sp.csc_matrix((d, 1)), np.zeros(d), sets)
+    ws = rng.standard_normal(d)
+    ref = ws.copy()
+    O.project(ref, cosmo_b200.problems.to_oracle_cones(sets))
+    got = eng.project(ws)
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ws) < 1e-12
+
+
+def test_project_psd_batch_of_cliques():
+    # many small cones in one launch (chordal-decomposition shape)
+    rng = np.random.default_rng(3)
+    sizes = rng.integers(2, 40, size=200)
+    sets = [cosmo_b200.PsdConeTriangle(int(N * (N + 1) // 2)) for N in sizes]
+    m = sum(S.dim for S in sets)
+    eng = _engine(sp.identity(1, format="csc"), np.zeros(1), sp.csc_matrix((m, 1)), np.zeros(m), sets)
+    ws = rng.standard_normal(m)
+    ref = ws.copy()
+    O.project(ref, cosmo_b200.problems.to_oracle_cones(sets))
+    got = eng.project(ws)
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ws) < 1e-12
+    # idempotence: projecting a projected point changes nothing (size-independent property)
+    again = eng.project(got)
+    assert np.linalg.norm(again - got) / np.linalg.norm(got) < 1e-12
+
+
+# ---------------------------------------------------------------------------
+# P4a: reduced-KKT CG solve (kktsolver_indirect.jl:36-88)
+# ---------------------------------------------------------------------------
+def _small_qp(seed=0, n=40, m=70):
+    return cosmo_b200.problems.random_sparse_qp(n, m, 0.15, seed=seed)
+
+
+def test_kkt_solve_matches_oracle_and_direct():
+    P, q, A, b, sets = _small_qp()
+    m, n = A.shape
+    eng = _engine(P, q, A, b, sets, scaling=0)
+    rng = np.random.default_rng(2)
+    rho = eng.rho_vec()
+    ocg = O.IndirectReducedKKT(P, A, 1e-6, rho.copy(), "CG")
+    direct = O.DirectKKT(P, A, 1e-6, rho)
+    for k in range(6):
+        rhs = rng.standard_normal(n + m)
+        sol, inner = eng.kkt_solve(rhs)
+        ref = ocg.solve(rhs)
+        assert inner == ocg.inner_iterations[-1]                 # same tolerance schedule & stopping rule
+        assert np.allclose(sol, ref, rtol=1e-9, atol=1e-9)
+        # and both are inexact solves of the same KKT system (kktsolver.jl:104-109)
+        tol = 1.0 / (k + 1) ** 1.5 / np.linalg.norm(rhs[:n] + A.T @ (rho * rhs[n:]))
+        exact = direct.solve(rhs)
+        assert np.linalg.norm(sol - exact) <= 1e3 * max(tol, 1e-12) * (1 + np.linalg.norm(exact))
+
+
+def test_residuals_match_oracle():
+    P, q, A, b, sets = _small_qp(seed=4)
+    m, n = A.shape
+    st = cosmo_b200.Settings()
+    Ps, qs, As, bs, ss, D, Em, c = cosmo_b200.ruiz_equilibrate(P, q, A, b, sets, st)
+    eng = E.Engine(Ps, qs, As, bs, _tuples(ss), st.to_struct(), D=D, E=Em, c=c)
+    rng = np.random.default_rng(8)
+    x, s, mu = rng.standard_normal(n), rng.standard_normal(m), rng.standard_normal(m)
+    ws = O.Workspace(P, q, A, b, cosmo_b200.problems.to_oracle_cones(sets), O.Settings())
+    ws.setup()
+    ws.xv, ws.s, ws.mu = x, s, mu
+    for ign in (False, True):
+        rp, rd = ws.calculate_residuals(ign)
+        mp, md = ws.max_res_component_norm(ign)
+        got = eng.residuals(x, s, mu, ign)
+        assert np.allclose(got[:4], [rp, rd, mp, md], rtol=1e-11)
+    assert np.isclose(eng.residuals(x, s, mu)[4], ws.calculate_cost(), rtol=1e-11)
+
+
+# ---------------------------------------------------------------------------
+# iterate-level parity: w trajectories vs the oracle
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("scaling", [0, 10])
+def test_iterate_parity_first_iterations(scaling):
+    P, q, A, b, sets = _small_qp(seed=7)
+    cones = cosmo_b200.problems.to_oracle_cones(sets)
+    for iters in (1, 5, 40, 90):   # 40/80: rho adaptation + infeasibility checks are crossed
+        ost = O.Settings(kkt_solver="cg", scaling=scaling, max_iter=iters, eps_abs=1e-14, eps_rel=1e-14)
+        ref = O.solve(P, q, A, b, cones, ost)
+        model = cosmo_b200.Model()
+        model.set(P, q, A, b, sets, cosmo_b200.Settings(scaling=scaling, max_iter=iters, eps_abs=1e-14, eps_rel=1e-14))
+        res = model.optimize()
+        w = model.engine.w()
+        assert res.iter == ref.iter == iters
+        assert np.allclose(model.engine.rho_vec(), ref.rho_vec, rtol=1e-9)
+        assert list(np.round(res.info.rho_updates, 9)) == list(np.round(ref.info.rho_updates, 9))
+        assert np.linalg.norm(w - ref.w) / np.linalg.norm(ref.w) < 1e-8, iters
+        assert np.allclose(res.x, ref.x, rtol=1e-7, atol=1e-9)
+        assert np.allclose(res.s, ref.s, rtol=1e-7, atol=1e-9)
+        assert np.allclose(res.y, ref.y, rtol=1e-7, atol=1e-9)
+        assert np.isclose(res.info.r_prim, ref.info.r_prim, rtol=1e-6, atol=1e-12)
+        assert np.isclose(res.info.r_dual, ref.info.r_dual, rtol=1e-6, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------
+# solve-level parity on the reference's literal problems
+# ---------------------------------------------------------------------------
+def _to_mine(cons):
+    out = []
+    for c in cons:
+        S = c.convex_set
+        S2 = cosmo_b200.Box(S.l, S.u) if isinstance(S, O.Box) else getattr(cosmo_b200, type(S).__name__)(S.dim)
+        out.append(cosmo_b200.Constraint(c.A, c.b, S2))
+    return out
+
+
+def _solve_mine(builder, **kw):
+    P, q, cons = builder()
+    model = cosmo_b200.Model()
+    cosmo_b200.assemble(model, P, q, _to_mine(cons), cosmo_b200.Settings(**kw))
+    return cosmo_b200.optimize(model), model
+
+
+def _solve_oracle(builder, **kw):
+    P, q, cons = builder()
+    Pm, qm, A, b, cones = O.assemble(P, q, cons)
+    return O.solve(Pm, qm, A, b, cones, O.Settings(kkt_solver="cg", **kw))
+
+
+@pytest.mark.parametrize("builder", [G.g1_qp_nonneg, G.g1_qp_box])
+@pytest.mark.parametrize("scaling", [0, 10])
+def test_g1_simple_qp(builder, scaling):
+    res, _ = _solve_mine(builder, scaling=scaling)
+    ref = _solve_oracle(builder, scaling=scaling)
+    assert res.status == "Solved" == ref.status
+    assert np.max(np.abs(res.x - G.G1_X)) < 1e-3 and abs(res.obj_val - G.G1_OBJ) < 1e-3   # examples/qp.jl:41-44
+    assert res.iter == ref.iter
+    assert np.allclose(res.x, ref.x, atol=1e-7) and np.allclose(res.y, ref.y, atol=1e-6) and np.allclose(res.s, ref.s, atol=1e-7)
+
+
+def test_g2_box_statuses():
+    assert abs(_solve_mine(G.g2_box_feasible)[0].obj_val + 0.5) < 1e-5
+    assert _solve_mine(G.g2_box_primal_infeasible_1)[0].status == "Primal_infeasible"
+    assert _solve_mine(G.g2_box_primal_infeasible_2)[0].status == "Primal_infeasible"
+    assert _solve_mine(G.g2_box_dual_infeasible, check_infeasibility=20, scaling=0)[0].status == "Dual_infeasible"
+    assert _solve_mine(G.g2_box_dual_infeasible, check_infeasibility=40, scaling=10)[0].status == "Dual_infeasible"
+    for bld, kw in ((G.g2_box_primal_infeasible_1, {}), (G.g2_box_dual_infeasible, dict(check_infeasibility=20, scaling=0))):
+        assert _solve_mine(bld, **kw)[0].iter == _solve_oracle(bld, **kw).iter
+
+
+def test_g3_hs21_with_soc_and_merging():
+    res, model = _solve_mine(G.g3_hs21)
+    ref = _solve_oracle(G.g3_hs21)
+    assert [type(S).__name__ for S in model.sets0] == ["ZeroSet", "Nonnegatives", "Box", "Box", "SecondOrderCone"]
+    assert res.status == "Solved" and abs(res.obj_val - G.G3_OBJ) < 1e-3 and np.max(np.abs(res.x - G.G3_X)) < 1e-3
+    assert res.iter == ref.iter and np.allclose(res.x, ref.x, atol=1e-6)
+
+
+def test_g12_lp():
+    res, _ = _solve_mine(G.g12_lp, eps_abs=1e-4, eps_rel=1e-5)
+    assert res.status == "Solved" and np.max(np.abs(res.x - G.G12_X)) < 1e-2 and abs(res.obj_val - G.G12_OBJ) < 1e-2
+
+
+@pytest.mark.parametrize("scaling", [0, 10])
+def test_g13_lovasz_petersen_sdp(scaling):
+    res, _ = _solve_mine(G.g13_lovasz_petersen, scaling=scaling, eps_abs=1e-6, eps_rel=1e-6)
+    ref = _solve_oracle(G.g13_lovasz_petersen, scaling=scaling, eps_abs=1e-6, eps_rel=1e-6)
+    assert res.status == "Solved" and abs(res.obj_val - G.G13_OBJ) < 1e-3
+    assert abs(res.obj_val - ref.obj_val) < 1e-6 and abs(res.iter - ref.iter) <= 25
+
+
+def test_g14_model_updates_and_warm_start():
+    P, q, cons = G.g1_qp_nonneg()
+    model = cosmo_b200.Model()
+    cosmo_b200.assemble(model, P, q, _to_mine(cons), cosmo_b200.Settings(check_termination=1))
+    r1 = model.optimize()
+    r2 = model.optimize()
+    assert abs(r1.obj_val - r2.obj_val) <= 1e-3 and r2.iter <= r1.iter       # model_modifications.jl:29-31
+    model = cosmo_b200.Model()
+    cosmo_b200.assemble(model, P, q, _to_mine(cons), cosmo_b200.Settings())
+    model.optimize()
+    model.update(q=np.array([2.0, 3.0]))
+    r = model.optimize()
+    assert abs(r.obj_val - 3.5) < 1e-3 and np.linalg.norm(r.x - [0.5, 0.5]) < 1e-3   # :41-43
+    model = cosmo_b200.Model()
+    cosmo_b200.assemble(model, np.zeros((2, 2)), np.array([1.0, 1.0]),
+                        cosmo_b200.Constraint(np.eye(2), np.array([-2.0, -3.0]), cosmo_b200.Nonnegatives),
+                        cosmo_b200.Settings(check_termination=20))
+    r = model.optimize()
+    assert np.linalg.norm(r.x - [2.0, 3.0]) < 1e-3
+    model.update(b=np.array([0.0, 1.0]))
+    assert np.linalg.norm(model.optimize().x - [0.0, -1.0]) < 1e-4               # :57-59
+
+
+# ---------------------------------------------------------------------------
+# solve-level parity on the BASELINE problem families at oracle-sized instances
+# ---------------------------------------------------------------------------
+def _parity(P, q, A, b, sets, tol_x=1e-5, **kw):
+    cones = cosmo_b200.problems.to_oracle_cones(sets)
+    ref = O.solve(P, q, A, b, cones, O.Settings(kkt_solver="cg", **kw))
+    model = cosmo_b200.Model()
+    model.set(P, q, A, b, sets, cosmo_b200.Settings(**kw))
+    res = model.optimize()
+    assert res.status == ref.status
+    scale = max(1.0, np.abs(ref.x).max())
+    assert abs(res.obj_val - ref.obj_val) <= 1e-6 * max(1.0, abs(ref.obj_val)) * 10
+    assert np.max(np.abs(res.x - ref.x)) <= tol_x * scale
+    assert np.max(np.abs(res.s - ref.s)) <= tol_x * max(1.0, np.abs(ref.s).max())
+    assert np.max(np.abs(res.y - ref.y)) <= tol_x * max(1.0, np.abs(ref.y).max())
+    return res, ref
+
+
+@pytest.mark.parametrize("scaling", [0, 10])
+def test_c2_random_sparse_qp_small(scaling):
+    P, q, A, b, sets = cosmo_b200.problems.random_sparse_qp(2000, 4000, 0.01, seed=2)
+    res, ref = _parity(P, q, A, b, sets, scaling=scaling)
+    assert res.status == "Solved" and res.iter == ref.iter
+
+
+def test_c3_portfolio_socp_small():
+    P, q, A, b, sets = cosmo_b200.problems.portfolio_socp(n=400, k=40, seed=1)
+    res, ref = _parity(P, q, A, b, sets, tol_x=1e-4, max_iter=3000)
+    assert res.status == "Solved"
+
+
+def test_c4_closest_correlation_small():
+    P, q, A, b, sets = cosmo_b200.problems.closest_correlation_sdp(N=40, seed=12345)
+    res, ref = _parity(P, q, A, b, sets, tol_x=1e-4)
+    assert res.status == "Solved"
+    N = 40
+    X = np.zeros((N, N))
+    iu = np.triu_indices(N)
+    order = np.lexsort((iu[0], iu[1]))
+    r, c = iu[0][order], iu[1][order]
+    X[r, c] = np.where(r == c, res.x, res.x / np.sqrt(2))
+    X = X + np.triu(X, 1).T
+    assert np.max(np.abs(np.diag(X) - 1.0)) < 1e-4 and np.linalg.eigvalsh(X).min() > -1e-3   # closestcorr.jl:70-80
+
+
+def test_float32_model_solves_g1():
+    # Model{Float32} (test/run_cosmo_tests.jl:9); tolerance of the reference's own test: 1e-3
+    P, q, cons = G.g1_qp_box()
+    model = cosmo_b200.Model(dtype=np.float32)
+    cosmo_b200.assemble(model, P, q, _to_mine(cons), cosmo_b200.Settings(eps_abs=1e-4, eps_rel=1e-4))
+    res = model.optimize()
+    assert res.status == "Solved" and np.max(np.abs(res.x - G.G1_X)) < 1e-3 and abs(res.obj_val - G.G1_OBJ) < 1e-3
