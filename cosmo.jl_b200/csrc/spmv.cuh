@@ -81,12 +81,18 @@ __global__ void __launch_bounds__(kBlock) spmv_kernel(CsrView<T> M1, const T* __
 #pragma unroll
   for (int k = 0; k < (Epi::NM > 0 ? Epi::NM : 1); ++k) accM[k] = 0;
 
-  for (int row = blockIdx.x * GROUPS + group; row < nrows; row += total_groups) {
+  // `base` is block-uniform so every lane of a warp runs the same number of trips:
+  // the full-mask shuffles below (and in the reduction) must be reached by all 32 lanes.
+  for (int base = blockIdx.x * GROUPS; base < nrows; base += total_groups) {
+    const int row = base + group;
+    const bool valid = row < nrows;
     T s = 0;
-    if (M1.rowptr != nullptr) s += row_partial<T, LANES>(M1, x1, row, lane);
-    if (M2.rowptr != nullptr) s += row_partial<T, LANES>(M2, x2, row, lane);
+    if (valid) {
+      if (M1.rowptr != nullptr) s += row_partial<T, LANES>(M1, x1, row, lane);
+      if (M2.rowptr != nullptr) s += row_partial<T, LANES>(M2, x2, row, lane);
+    }
     s = group_sum<T, LANES>(s);
-    if (lane == 0) epi.row(row, s, accS, accM);
+    if (valid && lane == 0) epi.row(row, s, accS, accM);
   }
   if constexpr (Epi::NS + Epi::NM > 0) {
     reduce_and_finalize<T, Epi::NS, Epi::NM>(accS, accM, rb, epi);
