@@ -46,6 +46,47 @@ __device__ __forceinline__ void load4_stream(const float* p, float (&v)[4]) {
 __device__ __forceinline__ int4 load4_stream(const int* p) {
   return __ldcs(reinterpret_cast<const int4*>(p));
 }
+__device__ __forceinline__ void load8_stream(const double* p, double (&v)[8]) {
+  const double2* q = reinterpret_cast<const double2*>(p);
+  double2 a = __ldcs(q), b = __ldcs(q + 1), c = __ldcs(q + 2), d = __ldcs(q + 3);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+__device__ __forceinline__ void load8_stream(const float* p, float (&v)[8]) {
+  const float4* q = reinterpret_cast<const float4*>(p);
+  float4 a = __ldcs(q), b = __ldcs(q + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// ---- mbarrier + 1-D bulk (TMA) copy global -> shared ------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_load_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(addr),
+      "r"(parity)
+      : "memory");
+}
 
 // NaN-propagating max of non-negative magnitudes (Julia's norm(x, Inf) returns NaN
 // when an entry is NaN; fmax would silently drop it).
@@ -73,12 +114,12 @@ __device__ __forceinline__ T warp_nanmax(T v) {
 // Fold per-thread accumulators (NS sums, NM maxes) over the block, publish the
 // block partial, and let the last block fold all partials and call fin(out).
 // Must be called by all kBlock threads of every block of the grid.
-template <typename T, int NS, int NM, typename Fin>
+template <typename T, int NS, int NM, typename Fin, int NWARPS = kWarpsPerBlock>
 __device__ __forceinline__ void reduce_and_finalize(const T* accS, const T* accM, const RedBuf<T>& rb,
                                                     const Fin& fin) {
   constexpr int NR = NS + NM;
   static_assert(NR >= 1 && NR <= kMaxRed, "reduction slots");
-  __shared__ T sm[kWarpsPerBlock][NR];
+  __shared__ T sm[NWARPS][NR];
   __shared__ int is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -95,7 +136,7 @@ __device__ __forceinline__ void reduce_and_finalize(const T* accS, const T* accM
   if (threadIdx.x < NR) {
     const int k = threadIdx.x;
     T v = sm[0][k];
-    for (int w = 1; w < kWarpsPerBlock; ++w) v = (k < NS) ? v + sm[w][k] : nanmax(v, sm[w][k]);
+    for (int w = 1; w < NWARPS; ++w) v = (k < NS) ? v + sm[w][k] : nanmax(v, sm[w][k]);
     rb.partials[(size_t)blockIdx.x * NR + k] = v;
   }
   __threadfence();
@@ -107,7 +148,7 @@ __device__ __forceinline__ void reduce_and_finalize(const T* accS, const T* accM
   __syncthreads();
   if (is_last) {
     __threadfence();
-    for (int k = warp; k < NR; k += kWarpsPerBlock) {
+    for (int k = warp; k < NR; k += NWARPS) {
       T v = 0;
       for (int b = lane; b < (int)gridDim.x; b += 32) {
         T p = __ldcg(rb.partials + (size_t)b * NR + k);

@@ -12,6 +12,7 @@
 #include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -91,7 +92,7 @@ struct DevBuf {
   void alloc(size_t count, bool zero = true) {
     if (p) { cudaFree(p); p = nullptr; }
     n = count;
-    size_t bytes = std::max<size_t>(count, 1) * sizeof(U);
+    size_t bytes = (count + 8) * sizeof(U);   // +8: bulk (TMA) copies round the tail up to 16 bytes
     cudaError_t e = cudaMalloc(&p, bytes);
     if (e != cudaSuccess) throw EngineError{COSMO_B200_ERR_ALLOC, std::string("cudaMalloc failed: ") + cudaGetErrorString(e)};
     if (zero) CUDA_TRY(cudaMemset(p, 0, bytes));
@@ -112,6 +113,14 @@ struct DevCsr {
   DevBuf<int> rowptr, col;
   DevBuf<T> val;
   int lanes = 32;
+  // column-windowed copy (spmv_win_kernel); absent when the rows are too short to pay off
+  bool windowed = false;
+  int nwin = 0, W = 0, nctas = 0;
+  DevBuf<int> w_rowptr, w_cta_rows;
+  DevBuf<unsigned short> w_col;
+  DevBuf<T> w_val;
+  long long w_elems = 0;
+  WcsrView<T> wview() const { return WcsrView<T>{w_rowptr.p, w_col.p, w_val.p, w_cta_rows.p, nwin, W, nrows, ncols}; }
   CsrView<T> view() const { return CsrView<T>{rowptr.p, col.p, val.p}; }
   double spmv_bytes() const {  // 12 nnz + 4 (rows+1) + 8 cols + 8 rows   (fp64)
     return (double)nnz * (sizeof(T) + 4) + 4.0 * (nrows + 1) + (double)sizeof(T) * ncols + (double)sizeof(T) * nrows;
@@ -204,7 +213,9 @@ class Engine : public EngineBase {
   int last_cg_iters_ = 1;
   long long total_inner_ = 0, total_mults_ = 0;
   // scratch
-  DevBuf<T> vec_m_, vec_n_, vec_n2_, dy_, dx_;
+  DevBuf<T> vec_m_, vec_n_, vec_n2_, dy_, dx_, ypart_;
+  int num_sms_ = 148;
+  bool use_windows_ = true;
   DevBuf<T> sc_;       // device scalars
   DevBuf<int> isc_;
   DevBuf<T> partials_;
@@ -235,6 +246,7 @@ class Engine : public EngineBase {
   void upload_vec(DevBuf<T>& dst, const void* host, size_t count);
   void download_vec(void* host, const T* src, size_t count);
   void build_csr(DevCsr<T>& dst, const HostCsr& h);
+  void build_windows(DevCsr<T>& dst, const HostCsr& h);
   void classify_and_set_rho(bool reset_rho);
   void allreduce_sum(T* buf, size_t count);
   void allreduce_max(T* buf, size_t count);
@@ -295,6 +307,84 @@ void Engine<T>::build_csr(DevCsr<T>& dst, const HostCsr& h) {
   sync();
 }
 
+// Column-windowed storage for spmv_win_kernel (see spmv.cuh).
+template <typename T>
+void Engine<T>::build_windows(DevCsr<T>& dst, const HostCsr& h) {
+  dst.windowed = false;
+  if (!use_windows_ || h.nrows == 0 || h.ncols == 0) return;
+  const long long nnz = (long long)h.col.size();
+  const int Wmax = (int)(204800 / sizeof(T));
+  const int nwin = (h.ncols + Wmax - 1) / Wmax;
+  if (nwin > 16) return;
+  const double per_seg = (double)nnz / ((double)h.nrows * nwin);
+  if (per_seg < 24.0) return;                     // short rows: padding + per-row overhead would dominate
+  int W = (h.ncols + nwin - 1) / nwin;
+  W = (W + 31) & ~31;
+  if (W > 65536) return;                          // 16-bit window-local indices
+  const int nr = h.nrows;
+  std::vector<int> rp((size_t)nwin * (nr + 1), 0);
+  // pass 1: padded segment lengths
+  std::vector<int> cnt(nwin);
+  long long total = 0;
+  std::vector<long long> row_cost(nr, 0);
+  for (int r = 0; r < nr; ++r) {
+    std::fill(cnt.begin(), cnt.end(), 0);
+    for (int k = h.rowptr[r]; k < h.rowptr[r + 1]; ++k) cnt[h.col[k] / W]++;
+    for (int w = 0; w < nwin; ++w) {
+      const int padded = (cnt[w] + 7) & ~7;
+      rp[(size_t)w * (nr + 1) + r + 1] = padded;
+      row_cost[r] += padded + 8;
+      total += padded;
+    }
+  }
+  if (total >= (1LL << 31) - 16) return;
+  // window-major layout: all rows of window 0, then window 1, ...
+  long long run = 0;
+  for (int w = 0; w < nwin; ++w) {
+    int* p = rp.data() + (size_t)w * (nr + 1);
+    p[0] = (int)run;
+    for (int r = 0; r < nr; ++r) { run += p[r + 1]; p[r + 1] = (int)run; }
+  }
+  std::vector<unsigned short> wc((size_t)total + 8, 0);
+  std::vector<T> wv((size_t)total + 8, T(0));
+  std::vector<int> fill(nwin);
+  for (int r = 0; r < nr; ++r) {
+    for (int w = 0; w < nwin; ++w) fill[w] = rp[(size_t)w * (nr + 1) + r];
+    for (int k = h.rowptr[r]; k < h.rowptr[r + 1]; ++k) {
+      const int w = h.col[k] / W;
+      const int pos = fill[w]++;
+      wc[pos] = (unsigned short)(h.col[k] - w * W);
+      wv[pos] = (T)h.val[k];
+    }
+    for (int w = 0; w < nwin; ++w) {   // padding repeats the last real column with a zero value
+      const int end = rp[(size_t)w * (nr + 1) + r + 1];
+      const int first = rp[(size_t)w * (nr + 1) + r];
+      for (int pos = fill[w]; pos < end; ++pos) { wc[pos] = (fill[w] > first) ? wc[fill[w] - 1] : 0; wv[pos] = T(0); }
+    }
+  }
+  // contiguous row chunks per CTA, balanced by padded nnz (+ per-row overhead)
+  const int nctas = num_sms_;
+  std::vector<int> cta_rows(nctas + 1, nr);
+  long long all_cost = 0;
+  for (int r = 0; r < nr; ++r) all_cost += row_cost[r];
+  cta_rows[0] = 0;
+  long long acc = 0;
+  int g = 1;
+  for (int r = 0; r < nr && g < nctas; ++r) {
+    acc += row_cost[r];
+    while (g < nctas && acc * nctas >= all_cost * g) { cta_rows[g] = r + 1; ++g; }
+  }
+  for (; g < nctas; ++g) cta_rows[g] = nr;
+  cta_rows[nctas] = nr;
+  dst.nwin = nwin; dst.W = W; dst.nctas = nctas; dst.w_elems = total;
+  dst.w_rowptr.upload(rp, stream_);
+  dst.w_cta_rows.upload(cta_rows, stream_);
+  dst.w_col.upload(wc, stream_);
+  dst.w_val.upload(wv, stream_);
+  sync();
+  dst.windowed = true;
+}
+
 // Julia CSC -> (a) CSR of the transpose (zero conversion: same arrays, rebased)
 //              (b) CSR of the matrix itself (stable counting-sort transposition)
 template <typename T>
@@ -351,6 +441,12 @@ Engine<T>::Engine(const cosmo_b200_problem& p, const cosmo_b200_settings& st) : 
     throw EngineError{COSMO_B200_ERR_CUDA, "no CUDA device available: the COSMO B200 engine has no CPU fallback"};
   if (device_ < 0 || device_ >= ndev) throw EngineError{COSMO_B200_ERR_INVALID, "bad device ordinal"};
   CUDA_TRY(cudaSetDevice(device_));
+  CUDA_TRY(cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, device_));
+  if (num_sms_ < 1 || num_sms_ > kMaxGrid) num_sms_ = 148;
+  {
+    const char* e = getenv("COSMO_B200_NO_WINDOWS");
+    use_windows_ = !(e && e[0] == '1');
+  }
   CUDA_TRY(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&ev0_));
   CUDA_TRY(cudaEventCreate(&ev1_));
@@ -420,7 +516,9 @@ Engine<T>::Engine(const cosmo_b200_problem& p, const cosmo_b200_settings& st) : 
     HostCsr a, at, pp, ppt;
     csc_to_host_csrs<T>(p.A, p.index_base, a, at);
     build_csr(A_, a);
+    build_windows(A_, a);
     build_csr(At_, at);
+    build_windows(At_, at);
     csc_to_host_csrs<T>(p.P, p.index_base, pp, ppt);
     build_csr(P_, pp);
     // A' and P rows are traversed by the same lane group in the fused operator kernel
@@ -472,6 +570,7 @@ Engine<T>::Engine(const cosmo_b200_problem& p, const cosmo_b200_settings& st) : 
   ls_.alloc(n_ + m_); t0_.alloc(m_); tm_.alloc(m_); xsol_.alloc(n_);
   rhsb_.alloc(n_ + 8); cb_.alloc(n_ + 8); r_.alloc(n_); u_.alloc(n_); nu_.alloc(m_);
   vec_m_.alloc(m_); vec_n_.alloc(n_ + 8); vec_n2_.alloc(n_); dy_.alloc(m_); dx_.alloc(n_);
+  ypart_.alloc(std::max(n_, m_));
   sc_.alloc(SC_COUNT); isc_.alloc(ISC_COUNT);
   partials_.alloc((size_t)kMaxGrid * kMaxRed); ticket_.alloc(1);
   {
@@ -603,6 +702,17 @@ template <typename Epi>
 void Engine<T>::launch_spmv(const DevCsr<T>& M1, const T* x1, const DevCsr<T>* M2, const T* x2, int nrows,
                             const Epi& epi, RedBuf<T> rb, const char* name) {
   const CsrView<T> v2 = M2 ? M2->view() : CsrView<T>{nullptr, nullptr, nullptr};
+  if (M1.windowed) {
+    const size_t smem = (size_t)M1.W * sizeof(T);
+    static bool configured = false;   // one flag per (T, Epi) instantiation
+    if (!configured) {
+      CUDA_TRY(cudaFuncSetAttribute(spmv_win_kernel<T, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204800));
+      configured = true;
+    }
+    spmv_win_kernel<T, Epi><<<M1.nctas, kWinThreads, smem, stream_>>>(M1.wview(), x1, v2, x2, epi, rb, ypart_.p);
+    check_launch(name);
+    return;
+  }
   const int lanes = M1.lanes;
   const int grid = sgrid(nrows, lanes);
   if (lanes == 32) spmv_kernel<T, 32, Epi><<<grid, kBlock, 0, stream_>>>(M1.view(), x1, v2, x2, nrows, epi, rb);

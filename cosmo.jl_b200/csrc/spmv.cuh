@@ -100,6 +100,107 @@ __global__ void __launch_bounds__(kBlock) spmv_kernel(CsrView<T> M1, const T* __
 }
 
 // ---------------------------------------------------------------------------
+// Column-windowed SpMV: the gathered vector is staged in shared memory.
+//
+// The plain kernel above is limited by the L1TEX wavefront rate (one scattered
+// 8-byte gather per cycle per SM), not by HBM.  Here the matrix is stored as
+// `nwin` column slabs ("windows") of width W <= 25.6k doubles; a persistent CTA
+// per SM pulls the W-slice of x into its 200 KB of shared memory with one TMA
+// bulk copy (cp.async.bulk + mbarrier), then streams its rows of that slab
+// from HBM (8-byte values + 16-bit window-local column indices, rows padded to
+// 8 entries so every lane issues aligned 128-bit loads) and gathers from
+// shared memory at ~5 operands/clk/SM.  Partial row sums are carried between
+// windows in a small global vector; the epilogue runs on the last window.
+// Algorithmic HBM traffic drops from 12 to 10 B/nnz (+1.4 % padding).
+// ---------------------------------------------------------------------------
+template <typename T>
+struct WcsrView {
+  const int* rowptr;            // nwin * (nrows + 1), element offsets (multiples of 8)
+  const unsigned short* col;    // window-local column index
+  const T* val;
+  const int* cta_row_start;     // gridDim.x + 1 contiguous row chunks, balanced by nnz
+  int nwin, W, nrows, ncols;
+};
+
+constexpr int kWinThreads = 1024;
+constexpr int kWinWarps = kWinThreads / 32;
+
+template <typename T>
+__device__ __forceinline__ T win_row_partial(const int* __restrict__ rp, const unsigned short* __restrict__ col,
+                                             const T* __restrict__ val, const T* xs, int row, int lane) {
+  const int start = __ldg(rp + row), end = __ldg(rp + row + 1);
+  T s0 = 0, s1 = 0;
+  for (int j = start + lane * 8; j < end; j += 256) {
+    const uint4 c = __ldcs(reinterpret_cast<const uint4*>(col + j));
+    T v[8];
+    load8_stream(val + j, v);
+    s0 += v[0] * xs[c.x & 0xffffu];
+    s1 += v[1] * xs[c.x >> 16];
+    s0 += v[2] * xs[c.y & 0xffffu];
+    s1 += v[3] * xs[c.y >> 16];
+    s0 += v[4] * xs[c.z & 0xffffu];
+    s1 += v[5] * xs[c.z >> 16];
+    s0 += v[6] * xs[c.w & 0xffffu];
+    s1 += v[7] * xs[c.w >> 16];
+  }
+  return s0 + s1;
+}
+
+template <typename T, typename Epi>
+__global__ void __launch_bounds__(kWinThreads, 1) spmv_win_kernel(WcsrView<T> M, const T* __restrict__ x, CsrView<T> M2,
+                                                                  const T* __restrict__ x2, Epi epi, RedBuf<T> rb,
+                                                                  T* __restrict__ ypart) {
+  if (epi.done != nullptr && *epi.done) return;
+  extern __shared__ __align__(128) unsigned char win_smem[];
+  T* xs = reinterpret_cast<T*>(win_smem);
+  __shared__ __align__(8) uint64_t bar;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const int r0 = M.cta_row_start[blockIdx.x], r1 = M.cta_row_start[blockIdx.x + 1];
+  T accS[Epi::NS > 0 ? Epi::NS : 1];
+  T accM[Epi::NM > 0 ? Epi::NM : 1];
+#pragma unroll
+  for (int k = 0; k < (Epi::NS > 0 ? Epi::NS : 1); ++k) accS[k] = 0;
+#pragma unroll
+  for (int k = 0; k < (Epi::NM > 0 ? Epi::NM : 1); ++k) accM[k] = 0;
+
+  unsigned phase = 0;
+  for (int w = 0; w < M.nwin; ++w) {
+    if (threadIdx.x == 0) {
+      int cnt = M.ncols - w * M.W;
+      if (cnt > M.W) cnt = M.W;
+      const unsigned bytes = ((unsigned)cnt * (unsigned)sizeof(T) + 15u) & ~15u;   // source buffers are padded
+      mbar_expect_tx(&bar, bytes);
+      bulk_load_g2s(xs, x + (size_t)w * M.W, bytes, &bar);
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1u;
+    const int* rp = M.rowptr + (size_t)w * (M.nrows + 1);
+    const bool last = (w == M.nwin - 1);
+    for (int row = r0 + warp; row < r1; row += kWinWarps) {   // warp-uniform trip count
+      T carry = T(0);
+      if (w > 0 && lane == 0) carry = ypart[row];
+      T s = win_row_partial<T>(rp, M.col, M.val, xs, row, lane);
+      if (last && M2.rowptr != nullptr) s += row_partial<T, 32>(M2, x2, row, lane);
+      s = warp_sum(s);
+      if (lane == 0) {
+        s += carry;
+        if (last) epi.row(row, s, accS, accM);
+        else ypart[row] = s;
+      }
+    }
+    __syncthreads();   // everyone is done with this window before the next bulk copy lands
+  }
+  if constexpr (Epi::NS + Epi::NM > 0) {
+    reduce_and_finalize<T, Epi::NS, Epi::NM, Epi, kWinWarps>(accS, accM, rb, epi);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Epilogues
 // ---------------------------------------------------------------------------
 

@@ -66,6 +66,39 @@ def test_spmv_lane_variants(density, lanes):
     assert np.allclose(eng.spmv(1, y), A.T @ y, rtol=1e-12, atol=1e-12)
 
 
+@pytest.mark.parametrize("m,n,per_row", [(400, 30000, 100), (30000, 400, 100), (3000, 60000, 300)])
+def test_spmv_windowed_smem_path(m, n, per_row):
+    """rows long enough for the column-windowed kernel (x slices staged in shared memory by TMA bulk
+    copies): 1, 2 and 3 windows, rows with empty window segments, multi-step segments, fused P rows."""
+    rng = np.random.default_rng(m + n)
+    rows = np.repeat(np.arange(m), per_row)
+    cols = rng.integers(0, n, size=m * per_row)
+    cols[: per_row] = rng.integers(0, min(n, 50), size=per_row)        # row 0 lives in window 0 only
+    A = sp.csc_matrix((rng.standard_normal(m * per_row), (rows, cols)), shape=(m, n))
+    B = sp.random(n, n, density=3.0 / n, random_state=rng, format="csr")
+    P = sp.csc_matrix(B + B.T + sp.identity(n))
+    eng = _engine(P, np.zeros(n), A, np.zeros(m), [cosmo_b200.Nonnegatives(m)], scaling=0)
+    x, y = rng.standard_normal(n), rng.standard_normal(m)
+    for which, M, v in ((0, A, x), (1, A.T, y)):
+        got, ref = eng.spmv(which, v), M @ v
+        scale = np.abs(M) @ np.abs(v) + 1e-300
+        assert np.max(np.abs(got - ref) / scale) < 1e-14, which
+    # the fused reduced-KKT operator (A' slab kernel + P rows + dot) through the CG solve
+    rho = eng.rho_vec()
+    ocg = O.IndirectReducedKKT(P, A, 1e-6, rho.copy(), "CG")
+    for k in range(2):
+        rhs = rng.standard_normal(n + m)
+        sol, inner = eng.kkt_solve(rhs)
+        ref = ocg.solve(rhs)
+        assert abs(inner - ocg.inner_iterations[-1]) <= 1
+        assert np.linalg.norm(sol - ref) <= 1e-8 * np.linalg.norm(ref)
+    xr, sr, mur = rng.standard_normal(n), rng.standard_normal(m), rng.standard_normal(m)
+    got = eng.residuals(xr, sr, mur)
+    rp = np.max(np.abs(A @ xr + sr))
+    rd = np.max(np.abs(P @ xr - A.T @ mur))
+    assert np.isclose(got[0], rp, rtol=1e-12) and np.isclose(got[1], rd, rtol=1e-12)
+
+
 def test_spmv_float32():
     rng = np.random.default_rng(6)
     m, n = 500, 300
