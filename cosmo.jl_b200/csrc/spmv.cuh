@@ -125,25 +125,32 @@ struct WcsrView {
 constexpr int kWinThreads = 1024;
 constexpr int kWinWarps = kWinThreads / 32;
 
+// gather-FMA of one lane's 8 (value, local column) pairs against the staged x slice
 template <typename T>
-__device__ __forceinline__ T win_row_partial(const int* __restrict__ rp, const unsigned short* __restrict__ col,
-                                             const T* __restrict__ val, const T* xs, int row, int lane) {
-  const int start = __ldg(rp + row), end = __ldg(rp + row + 1);
-  T s0 = 0, s1 = 0;
-  for (int j = start + lane * 8; j < end; j += 256) {
+__device__ __forceinline__ T win_fma8(const T (&v)[8], const uint4& c, const T* xs) {
+  T s0 = v[0] * xs[c.x & 0xffffu];
+  T s1 = v[1] * xs[c.x >> 16];
+  s0 += v[2] * xs[c.y & 0xffffu];
+  s1 += v[3] * xs[c.y >> 16];
+  s0 += v[4] * xs[c.z & 0xffffu];
+  s1 += v[5] * xs[c.z >> 16];
+  s0 += v[6] * xs[c.w & 0xffffu];
+  s1 += v[7] * xs[c.w >> 16];
+  return s0 + s1;
+}
+
+// steps beyond the first 256 entries of a row segment (rare: long rows)
+template <typename T>
+__device__ __forceinline__ T win_row_rest(const unsigned short* __restrict__ col, const T* __restrict__ val, const T* xs,
+                                          int start, int end, int lane) {
+  T s = 0;
+  for (int j = start + 256 + lane * 8; j < end; j += 256) {
     const uint4 c = __ldcs(reinterpret_cast<const uint4*>(col + j));
     T v[8];
     load8_stream(val + j, v);
-    s0 += v[0] * xs[c.x & 0xffffu];
-    s1 += v[1] * xs[c.x >> 16];
-    s0 += v[2] * xs[c.y & 0xffffu];
-    s1 += v[3] * xs[c.y >> 16];
-    s0 += v[4] * xs[c.z & 0xffffu];
-    s1 += v[5] * xs[c.z >> 16];
-    s0 += v[6] * xs[c.w & 0xffffu];
-    s1 += v[7] * xs[c.w >> 16];
+    s += win_fma8<T>(v, c, xs);
   }
-  return s0 + s1;
+  return s;
 }
 
 template <typename T, typename Epi>
@@ -177,22 +184,71 @@ __global__ void __launch_bounds__(kWinThreads, 1) spmv_win_kernel(WcsrView<T> M,
       mbar_expect_tx(&bar, bytes);
       bulk_load_g2s(xs, x + (size_t)w * M.W, bytes, &bar);
     }
-    mbar_wait(&bar, phase);
-    phase ^= 1u;
     const int* rp = M.rowptr + (size_t)w * (M.nrows + 1);
     const bool last = (w == M.nwin - 1);
-    for (int row = r0 + warp; row < r1; row += kWinWarps) {   // warp-uniform trip count
-      T carry = T(0);
-      if (w > 0 && lane == 0) carry = ypart[row];
-      T s = win_row_partial<T>(rp, M.col, M.val, xs, row, lane);
-      if (last && M2.rowptr != nullptr) s += row_partial<T, 32>(M2, x2, row, lane);
-      s = warp_sum(s);
-      if (lane == 0) {
-        s += carry;
-        if (last) epi.row(row, s, accS, accM);
-        else ypart[row] = s;
+    // This warp owns rows r0 + warp + k * kWinWarps.  Row pointers of the next 32 of them are
+    // fetched by the 32 lanes at once (off the per-row critical path) while the x slice is in flight.
+    int kbase = 0;
+    const int nmine = (r1 - r0 - warp + kWinWarps - 1) / kWinWarps;   // rows of this warp (<= 0: none)
+    bool waited = false;
+    for (; kbase < nmine; kbase += 32) {
+      int my_start = 0, my_end = 0;
+      T my_carry = T(0);
+      {
+        const int k = kbase + lane;
+        if (k < nmine) {
+          const int row = r0 + warp + k * kWinWarps;
+          my_start = __ldg(rp + row);
+          my_end = __ldg(rp + row + 1);
+          if (w > 0) my_carry = ypart[row];
+        }
+      }
+      if (!waited) { mbar_wait(&bar, phase); waited = true; }
+      const int kcount = min(32, nmine - kbase);
+      for (int kk = 0; kk < kcount; kk += 2) {   // two rows in flight per warp
+        const bool has_b = (kk + 1 < kcount);
+        const int sa = __shfl_sync(0xffffffffu, my_start, kk), ea = __shfl_sync(0xffffffffu, my_end, kk);
+        const int sb = __shfl_sync(0xffffffffu, my_start, kk + 1 < 32 ? kk + 1 : kk);
+        const int eb = __shfl_sync(0xffffffffu, my_end, kk + 1 < 32 ? kk + 1 : kk);
+        const T ca = __shfl_sync(0xffffffffu, my_carry, kk);
+        const T cb = __shfl_sync(0xffffffffu, my_carry, kk + 1 < 32 ? kk + 1 : kk);
+        const int ja = sa + lane * 8, jb = sb + lane * 8;
+        const bool la = ja < ea, lb = has_b && (jb < eb);
+        uint4 cxa = make_uint4(0, 0, 0, 0), cxb = make_uint4(0, 0, 0, 0);
+        T va[8], vb[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { va[i] = T(0); vb[i] = T(0); }
+        if (la) { cxa = __ldcs(reinterpret_cast<const uint4*>(M.col + ja)); load8_stream(M.val + ja, va); }
+        if (lb) { cxb = __ldcs(reinterpret_cast<const uint4*>(M.col + jb)); load8_stream(M.val + jb, vb); }
+        T pa = la ? win_fma8<T>(va, cxa, xs) : T(0);
+        T pb = lb ? win_fma8<T>(vb, cxb, xs) : T(0);
+        if (ea - sa > 256) pa += win_row_rest<T>(M.col, M.val, xs, sa, ea, lane);
+        if (has_b && eb - sb > 256) pb += win_row_rest<T>(M.col, M.val, xs, sb, eb, lane);
+        const int rowa = r0 + warp + (kbase + kk) * kWinWarps;
+        const int rowb = rowa + kWinWarps;
+        if (last && M2.rowptr != nullptr) {
+          pa += row_partial<T, 32>(M2, x2, rowa, lane);
+          if (has_b) pb += row_partial<T, 32>(M2, x2, rowb, lane);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          pa += __shfl_xor_sync(0xffffffffu, pa, o);
+          pb += __shfl_xor_sync(0xffffffffu, pb, o);
+        }
+        if (lane == 0) {
+          pa += ca;
+          if (last) epi.row(rowa, pa, accS, accM);
+          else ypart[rowa] = pa;
+        }
+        if (has_b && lane == 1) {
+          pb += cb;
+          if (last) epi.row(rowb, pb, accS, accM);
+          else ypart[rowb] = pb;
+        }
       }
     }
+    if (!waited) mbar_wait(&bar, phase);   // every thread observes every phase
+    phase ^= 1u;
     __syncthreads();   // everyone is done with this window before the next bulk copy lands
   }
   if constexpr (Epi::NS + Epi::NM > 0) {

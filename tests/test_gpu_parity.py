@@ -75,8 +75,8 @@ def test_spmv_windowed_smem_path(m, n, per_row):
     cols = rng.integers(0, n, size=m * per_row)
     cols[: per_row] = rng.integers(0, min(n, 50), size=per_row)        # row 0 lives in window 0 only
     A = sp.csc_matrix((rng.standard_normal(m * per_row), (rows, cols)), shape=(m, n))
-    B = sp.random(n, n, density=3.0 / n, random_state=rng, format="csr")
-    P = sp.csc_matrix(B + B.T + sp.identity(n))
+    B = sp.random(n, n, density=3.0 / n, random_state=rng, format="csr") * 0.05
+    P = sp.csc_matrix(B + B.T + sp.identity(n))          # diagonally dominant: well-conditioned reduced system
     eng = _engine(P, np.zeros(n), A, np.zeros(m), [cosmo_b200.Nonnegatives(m)], scaling=0)
     x, y = rng.standard_normal(n), rng.standard_normal(m)
     for which, M, v in ((0, A, x), (1, A.T, y)):
