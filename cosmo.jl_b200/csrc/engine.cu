@@ -16,6 +16,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
+#include <thread>
 #include <chrono>
 #include <string>
 #include <vector>
@@ -308,6 +310,83 @@ void Engine<T>::build_csr(DevCsr<T>& dst, const HostCsr& h) {
 }
 
 // Column-windowed storage for spmv_win_kernel (see spmv.cuh).
+//
+// Inside one 256-entry step of a row segment, lane l / slot i reads entry l*8+i, and the
+// shared-memory gather of slot i is issued per half-warp: the 16 lanes of a half-warp hit
+// distinct 8-byte banks iff their window-local columns differ mod 16.  The order of the
+// nonzeros inside a row is ours to choose (a dot product does not care), so the builder
+// deals the entries of every residue class (col mod 16) over the (step, half-warp, slot)
+// groups such that a group holds at most one entry per class whenever that is possible:
+// the gathers become (nearly) bank-conflict free.
+namespace {
+struct WinGroupScratch {
+  std::vector<int> cap, load, order;
+  std::vector<unsigned short> used;
+  std::vector<std::vector<int>> members;
+  std::vector<int> bucket[16];
+};
+}  // namespace
+
+template <typename T>
+static void win_fill_segment(const int* cols, const double* vals, const int* idx, int k, int wbase, long long start,
+                             unsigned short* wc, T* wv, WinGroupScratch& S) {
+  const int kpad = (k + 7) & ~7;
+  if (kpad == 0) return;
+  const int lanes_total = kpad / 8;
+  const int steps = (lanes_total + 31) / 32;
+  const int G = steps * 16;
+  S.cap.assign(G, 0); S.load.assign(G, 0); S.used.assign(G, 0);
+  if ((int)S.members.size() < G) S.members.resize(G);
+  for (int g = 0; g < G; ++g) S.members[g].clear();
+  for (int st = 0; st < steps; ++st) {
+    const int ls = std::min(32, lanes_total - 32 * st);
+    const int cap0 = std::min(16, ls), cap1 = ls - cap0;
+    for (int i = 0; i < 8; ++i) { S.cap[st * 16 + i] = cap0; S.cap[st * 16 + 8 + i] = cap1; }
+  }
+  for (int r = 0; r < 16; ++r) S.bucket[r].clear();
+  for (int e = 0; e < k; ++e) S.bucket[(cols[idx[e]] - wbase) & 15].push_back(idx[e]);
+  int cls[16];
+  for (int r = 0; r < 16; ++r) cls[r] = r;
+  std::sort(cls, cls + 16, [&](int a, int b) { return S.bucket[a].size() > S.bucket[b].size(); });
+  int cursor = 0;   // rotating start keeps the scan short and the loads balanced
+  for (int ci = 0; ci < 16; ++ci) {
+    const int r = cls[ci];
+    for (int e : S.bucket[r]) {
+      int best = -1, best_free = 0, fallback = -1, fb_free = 0;
+      for (int t = 0; t < G; ++t) {
+        const int g = (cursor + t) % G;
+        const int free_slots = S.cap[g] - S.load[g];
+        if (free_slots <= 0) continue;
+        if (!((S.used[g] >> r) & 1)) { if (free_slots > best_free) { best = g; best_free = free_slots; if (free_slots == 16) break; } }
+        else if (free_slots > fb_free) { fallback = g; fb_free = free_slots; }
+      }
+      const int g = best >= 0 ? best : fallback;
+      S.members[g].push_back(e);
+      S.used[g] |= (unsigned short)(1u << r);
+      S.load[g]++;
+      cursor = (g + 1) % G;
+    }
+  }
+  for (int g = 0; g < G; ++g) {
+    const int st = g / 16, h = (g % 16) / 8, i = g % 8;
+    const int nl = S.cap[g];
+    for (int t = 0; t < nl; ++t) {
+      const long long pos = start + (long long)st * 256 + (long long)(16 * h + t) * 8 + i;
+      if (t < S.load[g]) {
+        const int e = S.members[g][t];
+        wc[pos] = (unsigned short)(cols[e] - wbase);
+        wv[pos] = (T)vals[e];
+      } else {   // padding: zero value on a bank this group does not use yet
+        int r0 = 0;
+        while (r0 < 15 && ((S.used[g] >> r0) & 1)) ++r0;
+        S.used[g] |= (unsigned short)(1u << r0);
+        wc[pos] = (unsigned short)r0;
+        wv[pos] = T(0);
+      }
+    }
+  }
+}
+
 template <typename T>
 void Engine<T>::build_windows(DevCsr<T>& dst, const HostCsr& h) {
   dst.windowed = false;
@@ -323,45 +402,54 @@ void Engine<T>::build_windows(DevCsr<T>& dst, const HostCsr& h) {
   if (W > 65536) return;                          // 16-bit window-local indices
   const int nr = h.nrows;
   std::vector<int> rp((size_t)nwin * (nr + 1), 0);
-  // pass 1: padded segment lengths
-  std::vector<int> cnt(nwin);
-  long long total = 0;
   std::vector<long long> row_cost(nr, 0);
-  for (int r = 0; r < nr; ++r) {
-    std::fill(cnt.begin(), cnt.end(), 0);
-    for (int k = h.rowptr[r]; k < h.rowptr[r + 1]; ++k) cnt[h.col[k] / W]++;
-    for (int w = 0; w < nwin; ++w) {
-      const int padded = (cnt[w] + 7) & ~7;
-      rp[(size_t)w * (nr + 1) + r + 1] = padded;
-      row_cost[r] += padded + 8;
-      total += padded;
+  const int nthreads = (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  auto parallel_rows = [&](const std::function<void(int, int)>& fn) {
+    std::vector<std::thread> th;
+    const int chunk = (nr + nthreads - 1) / nthreads;
+    for (int t = 0; t < nthreads; ++t) {
+      const int a = t * chunk, b = std::min(nr, a + chunk);
+      if (a < b) th.emplace_back(fn, a, b);
     }
-  }
-  if (total >= (1LL << 31) - 16) return;
+    for (auto& x : th) x.join();
+  };
+  // pass 1: padded segment lengths
+  parallel_rows([&](int a, int b) {
+    std::vector<int> cnt(nwin);
+    for (int r = a; r < b; ++r) {
+      std::fill(cnt.begin(), cnt.end(), 0);
+      for (int k = h.rowptr[r]; k < h.rowptr[r + 1]; ++k) cnt[h.col[k] / W]++;
+      for (int w = 0; w < nwin; ++w) {
+        const int padded = (cnt[w] + 7) & ~7;
+        rp[(size_t)w * (nr + 1) + r + 1] = padded;
+        row_cost[r] += padded + 8;
+      }
+    }
+  });
   // window-major layout: all rows of window 0, then window 1, ...
   long long run = 0;
   for (int w = 0; w < nwin; ++w) {
     int* p = rp.data() + (size_t)w * (nr + 1);
-    p[0] = (int)run;
-    for (int r = 0; r < nr; ++r) { run += p[r + 1]; p[r + 1] = (int)run; }
+    long long prev = run;
+    for (int r = 0; r < nr; ++r) { const int len = p[r + 1]; p[r] = (int)prev; prev += len; if (prev >= (1LL << 31) - 16) return; }
+    p[nr] = (int)prev;
+    run = prev;
   }
+  const long long total = run;
   std::vector<unsigned short> wc((size_t)total + 8, 0);
   std::vector<T> wv((size_t)total + 8, T(0));
-  std::vector<int> fill(nwin);
-  for (int r = 0; r < nr; ++r) {
-    for (int w = 0; w < nwin; ++w) fill[w] = rp[(size_t)w * (nr + 1) + r];
-    for (int k = h.rowptr[r]; k < h.rowptr[r + 1]; ++k) {
-      const int w = h.col[k] / W;
-      const int pos = fill[w]++;
-      wc[pos] = (unsigned short)(h.col[k] - w * W);
-      wv[pos] = (T)h.val[k];
+  // pass 2: bank-aware placement of every row segment
+  parallel_rows([&](int a, int b) {
+    WinGroupScratch S;
+    std::vector<std::vector<int>> seg(nwin);
+    for (int r = a; r < b; ++r) {
+      for (int w = 0; w < nwin; ++w) seg[w].clear();
+      for (int k = h.rowptr[r]; k < h.rowptr[r + 1]; ++k) seg[h.col[k] / W].push_back(k);
+      for (int w = 0; w < nwin; ++w)
+        win_fill_segment<T>(h.col.data(), h.val.data(), seg[w].data(), (int)seg[w].size(), w * W,
+                            rp[(size_t)w * (nr + 1) + r], wc.data(), wv.data(), S);
     }
-    for (int w = 0; w < nwin; ++w) {   // padding repeats the last real column with a zero value
-      const int end = rp[(size_t)w * (nr + 1) + r + 1];
-      const int first = rp[(size_t)w * (nr + 1) + r];
-      for (int pos = fill[w]; pos < end; ++pos) { wc[pos] = (fill[w] > first) ? wc[fill[w] - 1] : 0; wv[pos] = T(0); }
-    }
-  }
+  });
   // contiguous row chunks per CTA, balanced by padded nnz (+ per-row overhead)
   const int nctas = num_sms_;
   std::vector<int> cta_rows(nctas + 1, nr);
