@@ -114,9 +114,12 @@ __device__ __forceinline__ T warp_nanmax(T v) {
 // Fold per-thread accumulators (NS sums, NM maxes) over the block, publish the
 // block partial, and let the last block fold all partials and call fin(out).
 // Must be called by all kBlock threads of every block of the grid.
+// `slot` / `nslots`: position of this block's partial and the number of participating blocks
+// (default: every block of the grid, indexed by blockIdx.x).
 template <typename T, int NS, int NM, typename Fin, int NWARPS = kWarpsPerBlock>
 __device__ __forceinline__ void reduce_and_finalize(const T* accS, const T* accM, const RedBuf<T>& rb,
-                                                    const Fin& fin) {
+                                                    const Fin& fin, int slot = -1, int nslots = -1) {
+  if (slot < 0) { slot = blockIdx.x; nslots = gridDim.x; }
   constexpr int NR = NS + NM;
   static_assert(NR >= 1 && NR <= kMaxRed, "reduction slots");
   __shared__ T sm[NWARPS][NR];
@@ -137,20 +140,20 @@ __device__ __forceinline__ void reduce_and_finalize(const T* accS, const T* accM
     const int k = threadIdx.x;
     T v = sm[0][k];
     for (int w = 1; w < NWARPS; ++w) v = (k < NS) ? v + sm[w][k] : nanmax(v, sm[w][k]);
-    rb.partials[(size_t)blockIdx.x * NR + k] = v;
+    rb.partials[(size_t)slot * NR + k] = v;
   }
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned t = atomicAdd(rb.ticket, 1u);
-    is_last = (t == gridDim.x - 1);
+    is_last = (t == (unsigned)nslots - 1u);
   }
   __syncthreads();
   if (is_last) {
     __threadfence();
     for (int k = warp; k < NR; k += NWARPS) {
       T v = 0;
-      for (int b = lane; b < (int)gridDim.x; b += 32) {
+      for (int b = lane; b < nslots; b += 32) {
         T p = __ldcg(rb.partials + (size_t)b * NR + k);
         v = (k < NS) ? v + p : nanmax(v, p);
       }

@@ -216,6 +216,7 @@ class Engine : public EngineBase {
   long long total_inner_ = 0, total_mults_ = 0;
   // scratch
   DevBuf<T> vec_m_, vec_n_, vec_n2_, dy_, dx_, ypart_;
+  DevBuf<unsigned> chunk_ticket_;
   int num_sms_ = 148;
   bool use_windows_ = true;
   DevBuf<T> sc_;       // device scalars
@@ -451,19 +452,21 @@ void Engine<T>::build_windows(DevCsr<T>& dst, const HostCsr& h) {
     }
   });
   // contiguous row chunks per CTA, balanced by padded nnz (+ per-row overhead)
-  const int nctas = num_sms_;
-  std::vector<int> cta_rows(nctas + 1, nr);
+  // one CTA per (row chunk, window): chunks are contiguous row ranges balanced by padded nnz
+  const int nchunks = std::max(1, num_sms_ / nwin);
+  const int nctas = nchunks * nwin;
+  std::vector<int> cta_rows(nchunks + 1, nr);
   long long all_cost = 0;
   for (int r = 0; r < nr; ++r) all_cost += row_cost[r];
   cta_rows[0] = 0;
   long long acc = 0;
   int g = 1;
-  for (int r = 0; r < nr && g < nctas; ++r) {
+  for (int r = 0; r < nr && g < nchunks; ++r) {
     acc += row_cost[r];
-    while (g < nctas && acc * nctas >= all_cost * g) { cta_rows[g] = r + 1; ++g; }
+    while (g < nchunks && acc * nchunks >= all_cost * g) { cta_rows[g] = r + 1; ++g; }
   }
-  for (; g < nctas; ++g) cta_rows[g] = nr;
-  cta_rows[nctas] = nr;
+  for (; g < nchunks; ++g) cta_rows[g] = nr;
+  cta_rows[nchunks] = nr;
   dst.nwin = nwin; dst.W = W; dst.nctas = nctas; dst.w_elems = total;
   dst.w_rowptr.upload(rp, stream_);
   dst.w_cta_rows.upload(cta_rows, stream_);
@@ -658,7 +661,8 @@ Engine<T>::Engine(const cosmo_b200_problem& p, const cosmo_b200_settings& st) : 
   ls_.alloc(n_ + m_); t0_.alloc(m_); tm_.alloc(m_); xsol_.alloc(n_);
   rhsb_.alloc(n_ + 8); cb_.alloc(n_ + 8); r_.alloc(n_); u_.alloc(n_); nu_.alloc(m_);
   vec_m_.alloc(m_); vec_n_.alloc(n_ + 8); vec_n2_.alloc(n_); dy_.alloc(m_); dx_.alloc(n_);
-  ypart_.alloc(std::max(n_, m_));
+  ypart_.alloc((size_t)std::max(n_, m_) * 16);   // nwin <= 16 per-window partial sums
+  chunk_ticket_.alloc(kMaxGrid);
   sc_.alloc(SC_COUNT); isc_.alloc(ISC_COUNT);
   partials_.alloc((size_t)kMaxGrid * kMaxRed); ticket_.alloc(1);
   {
@@ -797,7 +801,8 @@ void Engine<T>::launch_spmv(const DevCsr<T>& M1, const T* x1, const DevCsr<T>* M
       CUDA_TRY(cudaFuncSetAttribute(spmv_win_kernel<T, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204800));
       configured = true;
     }
-    spmv_win_kernel<T, Epi><<<M1.nctas, kWinThreads, smem, stream_>>>(M1.wview(), x1, v2, x2, epi, rb, ypart_.p);
+    spmv_win_kernel<T, Epi><<<M1.nctas, kWinThreads, smem, stream_>>>(M1.wview(), x1, v2, x2, epi, rb, ypart_.p,
+                                                                      chunk_ticket_.p);
     check_launch(name);
     return;
   }

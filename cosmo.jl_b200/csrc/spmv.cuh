@@ -153,21 +153,35 @@ __device__ __forceinline__ T win_row_rest(const unsigned short* __restrict__ col
   return s;
 }
 
+// One CTA per (row chunk j, window w): b = j * nwin + w.  The CTA stages its W-slice of x once
+// (a single TMA bulk copy that overlaps the first row loads), streams the rows of chunk j in
+// slab w and writes per-window partial sums.  The last of the nwin CTAs of a chunk to finish
+// (per-chunk ticket) folds the partials in window order -- deterministic -- adds the optional
+// second matrix (P rows, plain L2 gather) and runs the epilogue; only those "finishing" CTAs
+// take part in the scalar reduction, whose partials are indexed by chunk, not by CTA.
 template <typename T, typename Epi>
 __global__ void __launch_bounds__(kWinThreads, 1) spmv_win_kernel(WcsrView<T> M, const T* __restrict__ x, CsrView<T> M2,
                                                                   const T* __restrict__ x2, Epi epi, RedBuf<T> rb,
-                                                                  T* __restrict__ ypart) {
+                                                                  T* __restrict__ ypart, unsigned* __restrict__ chunk_ticket) {
   if (epi.done != nullptr && *epi.done) return;
   extern __shared__ __align__(128) unsigned char win_smem[];
   T* xs = reinterpret_cast<T*>(win_smem);
   __shared__ __align__(8) uint64_t bar;
+  __shared__ int fin_flag;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int w = blockIdx.x % M.nwin, chunk = blockIdx.x / M.nwin;
+  const int nchunks = gridDim.x / M.nwin;
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
     mbar_fence_init();
+    int cnt = M.ncols - w * M.W;
+    if (cnt > M.W) cnt = M.W;
+    const unsigned bytes = ((unsigned)cnt * (unsigned)sizeof(T) + 15u) & ~15u;   // source buffers are padded
+    mbar_expect_tx(&bar, bytes);
+    bulk_load_g2s(xs, x + (size_t)w * M.W, bytes, &bar);
   }
   __syncthreads();
-  const int r0 = M.cta_row_start[blockIdx.x], r1 = M.cta_row_start[blockIdx.x + 1];
+  const int r0 = M.cta_row_start[chunk], r1 = M.cta_row_start[chunk + 1];
   T accS[Epi::NS > 0 ? Epi::NS : 1];
   T accM[Epi::NM > 0 ? Epi::NM : 1];
 #pragma unroll
@@ -175,84 +189,91 @@ __global__ void __launch_bounds__(kWinThreads, 1) spmv_win_kernel(WcsrView<T> M,
 #pragma unroll
   for (int k = 0; k < (Epi::NM > 0 ? Epi::NM : 1); ++k) accM[k] = 0;
 
-  unsigned phase = 0;
-  for (int w = 0; w < M.nwin; ++w) {
+  const int* rp = M.rowptr + (size_t)w * (M.nrows + 1);
+  const bool single = (M.nwin == 1);
+  T* yw = ypart + (size_t)w * M.nrows;
+  // This warp owns rows r0 + warp + k * kWinWarps, two of them in flight at a time.  Row
+  // pointers of the NEXT pair are fetched (warp-uniform loads) before the current pair is
+  // consumed, so they stay off the critical path.
+  const int nmine = (r1 - r0 - warp + kWinWarps - 1) / kWinWarps;   // rows of this warp (<= 0: none)
+  bool waited = false;
+  int sa = 0, ea = 0, sb = 0, eb = 0;
+  auto fetch_ptrs = [&](int k, int& s_a, int& e_a, int& s_b, int& e_b) {
+    s_a = e_a = s_b = e_b = 0;
+    if (k < nmine) {
+      const int row = r0 + warp + k * kWinWarps;
+      s_a = __ldg(rp + row);
+      e_a = __ldg(rp + row + 1);
+    }
+    if (k + 1 < nmine) {
+      const int row = r0 + warp + (k + 1) * kWinWarps;
+      s_b = __ldg(rp + row);
+      e_b = __ldg(rp + row + 1);
+    }
+  };
+  fetch_ptrs(0, sa, ea, sb, eb);
+  for (int k = 0; k < nmine; k += 2) {
+    const bool has_b = (k + 1 < nmine);
+    const int ja = sa + lane * 8, jb = sb + lane * 8;
+    const bool la = ja < ea, lb = jb < eb;
+    uint4 cxa = make_uint4(0, 0, 0, 0), cxb = make_uint4(0, 0, 0, 0);
+    T va[8], vb[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { va[i] = T(0); vb[i] = T(0); }
+    if (la) { cxa = __ldcs(reinterpret_cast<const uint4*>(M.col + ja)); load8_stream(M.val + ja, va); }
+    if (lb) { cxb = __ldcs(reinterpret_cast<const uint4*>(M.col + jb)); load8_stream(M.val + jb, vb); }
+    const int csa = sa, cea = ea, csb = sb, ceb = eb;
+    fetch_ptrs(k + 2, sa, ea, sb, eb);          // next pair
+    if (!waited) { mbar_wait(&bar, 0); waited = true; }
+    T pa = la ? win_fma8<T>(va, cxa, xs) : T(0);
+    T pb = lb ? win_fma8<T>(vb, cxb, xs) : T(0);
+    if (cea - csa > 256) pa += win_row_rest<T>(M.col, M.val, xs, csa, cea, lane);
+    if (ceb - csb > 256) pb += win_row_rest<T>(M.col, M.val, xs, csb, ceb, lane);
+    const int rowa = r0 + warp + k * kWinWarps;
+    const int rowb = rowa + kWinWarps;
+    if (single && M2.rowptr != nullptr) {
+      pa += row_partial<T, 32>(M2, x2, rowa, lane);
+      if (has_b) pb += row_partial<T, 32>(M2, x2, rowb, lane);
+    }
+    // paired reduction: lanes 0-15 fold row a, lanes 16-31 fold row b (5 shuffles for 2 rows)
+    const bool hi = (lane & 16) != 0;
+    T keep = hi ? pb : pa;
+    const T send = hi ? pa : pb;
+    keep += __shfl_xor_sync(0xffffffffu, send, 16);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+    if (lane == 0 || (lane == 16 && has_b)) {
+      const int row = hi ? rowb : rowa;
+      if (single) epi.row(row, keep, accS, accM);
+      else yw[row] = keep;
+    }
+  }
+  if (!waited) mbar_wait(&bar, 0);   // never leave a bulk copy in flight
+
+  if (!single) {
+    __threadfence();
+    __syncthreads();
     if (threadIdx.x == 0) {
-      int cnt = M.ncols - w * M.W;
-      if (cnt > M.W) cnt = M.W;
-      const unsigned bytes = ((unsigned)cnt * (unsigned)sizeof(T) + 15u) & ~15u;   // source buffers are padded
-      mbar_expect_tx(&bar, bytes);
-      bulk_load_g2s(xs, x + (size_t)w * M.W, bytes, &bar);
+      const unsigned t = atomicAdd(chunk_ticket + chunk, 1u);
+      fin_flag = (t == (unsigned)M.nwin - 1u);
+      if (fin_flag) chunk_ticket[chunk] = 0u;
     }
-    const int* rp = M.rowptr + (size_t)w * (M.nrows + 1);
-    const bool last = (w == M.nwin - 1);
-    // This warp owns rows r0 + warp + k * kWinWarps.  Row pointers of the next 32 of them are
-    // fetched by the 32 lanes at once (off the per-row critical path) while the x slice is in flight.
-    int kbase = 0;
-    const int nmine = (r1 - r0 - warp + kWinWarps - 1) / kWinWarps;   // rows of this warp (<= 0: none)
-    bool waited = false;
-    for (; kbase < nmine; kbase += 32) {
-      int my_start = 0, my_end = 0;
-      T my_carry = T(0);
-      {
-        const int k = kbase + lane;
-        if (k < nmine) {
-          const int row = r0 + warp + k * kWinWarps;
-          my_start = __ldg(rp + row);
-          my_end = __ldg(rp + row + 1);
-          if (w > 0) my_carry = ypart[row];
-        }
-      }
-      if (!waited) { mbar_wait(&bar, phase); waited = true; }
-      const int kcount = min(32, nmine - kbase);
-      for (int kk = 0; kk < kcount; kk += 2) {   // two rows in flight per warp
-        const bool has_b = (kk + 1 < kcount);
-        const int sa = __shfl_sync(0xffffffffu, my_start, kk), ea = __shfl_sync(0xffffffffu, my_end, kk);
-        const int sb = __shfl_sync(0xffffffffu, my_start, kk + 1 < 32 ? kk + 1 : kk);
-        const int eb = __shfl_sync(0xffffffffu, my_end, kk + 1 < 32 ? kk + 1 : kk);
-        const T ca = __shfl_sync(0xffffffffu, my_carry, kk);
-        const T cb = __shfl_sync(0xffffffffu, my_carry, kk + 1 < 32 ? kk + 1 : kk);
-        const int ja = sa + lane * 8, jb = sb + lane * 8;
-        const bool la = ja < ea, lb = has_b && (jb < eb);
-        uint4 cxa = make_uint4(0, 0, 0, 0), cxb = make_uint4(0, 0, 0, 0);
-        T va[8], vb[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { va[i] = T(0); vb[i] = T(0); }
-        if (la) { cxa = __ldcs(reinterpret_cast<const uint4*>(M.col + ja)); load8_stream(M.val + ja, va); }
-        if (lb) { cxb = __ldcs(reinterpret_cast<const uint4*>(M.col + jb)); load8_stream(M.val + jb, vb); }
-        T pa = la ? win_fma8<T>(va, cxa, xs) : T(0);
-        T pb = lb ? win_fma8<T>(vb, cxb, xs) : T(0);
-        if (ea - sa > 256) pa += win_row_rest<T>(M.col, M.val, xs, sa, ea, lane);
-        if (has_b && eb - sb > 256) pb += win_row_rest<T>(M.col, M.val, xs, sb, eb, lane);
-        const int rowa = r0 + warp + (kbase + kk) * kWinWarps;
-        const int rowb = rowa + kWinWarps;
-        if (last && M2.rowptr != nullptr) {
-          pa += row_partial<T, 32>(M2, x2, rowa, lane);
-          if (has_b) pb += row_partial<T, 32>(M2, x2, rowb, lane);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          pa += __shfl_xor_sync(0xffffffffu, pa, o);
-          pb += __shfl_xor_sync(0xffffffffu, pb, o);
-        }
-        if (lane == 0) {
-          pa += ca;
-          if (last) epi.row(rowa, pa, accS, accM);
-          else ypart[rowa] = pa;
-        }
-        if (has_b && lane == 1) {
-          pb += cb;
-          if (last) epi.row(rowb, pb, accS, accM);
-          else ypart[rowb] = pb;
-        }
+    __syncthreads();
+    if (!fin_flag) return;
+    __threadfence();
+    for (int row = r0 + warp; row < r1; row += kWinWarps) {   // warp-uniform trips
+      T s = T(0);
+      if (M2.rowptr != nullptr) s = warp_sum(row_partial<T, 32>(M2, x2, row, lane));
+      if (lane == 0) {
+        T tot = __ldcg(ypart + row);
+        for (int ww = 1; ww < M.nwin; ++ww) tot += __ldcg(ypart + (size_t)ww * M.nrows + row);
+        epi.row(row, tot + s, accS, accM);
       }
     }
-    if (!waited) mbar_wait(&bar, phase);   // every thread observes every phase
-    phase ^= 1u;
-    __syncthreads();   // everyone is done with this window before the next bulk copy lands
   }
   if constexpr (Epi::NS + Epi::NM > 0) {
-    reduce_and_finalize<T, Epi::NS, Epi::NM, Epi, kWinWarps>(accS, accM, rb, epi);
+    // finishing CTAs only: partials indexed by chunk => the fold order is run-independent
+    reduce_and_finalize<T, Epi::NS, Epi::NM, Epi, kWinWarps>(accS, accM, rb, epi, chunk, nchunks);
   }
 }
 
