@@ -156,9 +156,10 @@ __device__ __forceinline__ T win_row_rest(const unsigned short* __restrict__ col
 // One CTA per (row chunk j, window w): b = j * nwin + w.  The CTA stages its W-slice of x once
 // (a single TMA bulk copy that overlaps the first row loads), streams the rows of chunk j in
 // slab w and writes per-window partial sums.  The last of the nwin CTAs of a chunk to finish
-// (per-chunk ticket) folds the partials in window order -- deterministic -- adds the optional
-// second matrix (P rows, plain L2 gather) and runs the epilogue; only those "finishing" CTAs
-// take part in the scalar reduction, whose partials are indexed by chunk, not by CTA.
+// (per-chunk ticket) folds the partials in window order -- deterministic -- and runs the epilogue
+// (one thread per row); only those "finishing" CTAs take part in the scalar reduction, whose
+// partials are indexed by chunk, not by CTA.  An optional second matrix (P rows, plain L2
+// gather) is folded into window 0's partial sums.
 template <typename T, typename Epi>
 __global__ void __launch_bounds__(kWinThreads, 1) spmv_win_kernel(WcsrView<T> M, const T* __restrict__ x, CsrView<T> M2,
                                                                   const T* __restrict__ x2, Epi epi, RedBuf<T> rb,
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(kWinThreads, 1) spmv_win_kernel(WcsrView<T> M,
     if (ceb - csb > 256) pb += win_row_rest<T>(M.col, M.val, xs, csb, ceb, lane);
     const int rowa = r0 + warp + k * kWinWarps;
     const int rowb = rowa + kWinWarps;
-    if (single && M2.rowptr != nullptr) {
+    if (w == 0 && M2.rowptr != nullptr) {   // second matrix (P rows): folded into window 0's partial
       pa += row_partial<T, 32>(M2, x2, rowa, lane);
       if (has_b) pb += row_partial<T, 32>(M2, x2, rowb, lane);
     }
@@ -261,14 +262,10 @@ __global__ void __launch_bounds__(kWinThreads, 1) spmv_win_kernel(WcsrView<T> M,
     __syncthreads();
     if (!fin_flag) return;
     __threadfence();
-    for (int row = r0 + warp; row < r1; row += kWinWarps) {   // warp-uniform trips
-      T s = T(0);
-      if (M2.rowptr != nullptr) s = warp_sum(row_partial<T, 32>(M2, x2, row, lane));
-      if (lane == 0) {
-        T tot = __ldcg(ypart + row);
-        for (int ww = 1; ww < M.nwin; ++ww) tot += __ldcg(ypart + (size_t)ww * M.nrows + row);
-        epi.row(row, tot + s, accS, accM);
-      }
+    for (int row = r0 + (int)threadIdx.x; row < r1; row += kWinThreads) {   // one thread per row, coalesced
+      T tot = __ldcg(ypart + row);
+      for (int ww = 1; ww < M.nwin; ++ww) tot += __ldcg(ypart + (size_t)ww * M.nrows + row);
+      epi.row(row, tot, accS, accM);
     }
   }
   if constexpr (Epi::NS + Epi::NM > 0) {
