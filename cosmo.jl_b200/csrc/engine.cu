@@ -97,7 +97,12 @@ struct DevBuf {
     size_t bytes = (count + 8) * sizeof(U);   // +8: bulk (TMA) copies round the tail up to 16 bytes
     cudaError_t e = cudaMalloc(&p, bytes);
     if (e != cudaSuccess) throw EngineError{COSMO_B200_ERR_ALLOC, std::string("cudaMalloc failed: ") + cudaGetErrorString(e)};
-    if (zero) CUDA_TRY(cudaMemset(p, 0, bytes));
+    if (zero) {
+      // cudaMemset runs on the legacy default stream, which does NOT order against the engine's
+      // non-blocking stream: wait for it here or a later kernel may race with the pending fill.
+      CUDA_TRY(cudaMemset(p, 0, bytes));
+      CUDA_TRY(cudaDeviceSynchronize());
+    }
   }
   void upload(const U* host, size_t count, cudaStream_t st) {
     if (count) CUDA_TRY(cudaMemcpyAsync(p, host, count * sizeof(U), cudaMemcpyHostToDevice, st));
