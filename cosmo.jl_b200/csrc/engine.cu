@@ -265,6 +265,7 @@ class Engine : public EngineBase {
   void project_device(const T* w, bool with_rhs, const T* ws_rhs);
   void soc_norms(const T* ws, T* norm_out);
   void kkt_core(bool fused_tail, const T* w_src, T* w_dst);
+  void kkt_op_stage2(const int* done, const T* u);
   void compute_residuals(const T* x, const T* s, const T* mu, bool ignore_scaling, double out[5]);
   bool adapt_rho(const T* x);
   bool primal_infeasible();
@@ -846,6 +847,26 @@ void Engine<T>::project_device(const T* w, bool with_rhs, const T* ws_rhs) {
   check_launch("proj_rhs");
 }
 
+// c = A' tm + P u + sigma u ; cb[n] = u'c   (second half of reduced_mul!, kktsolver_indirect.jl:61-65)
+// Rank 0 alone adds the replicated P / sigma terms of a row-sharded run.
+template <typename T>
+void Engine<T>::kkt_op_stage2(const int* done, const T* u) {
+  const bool lead = (rank_ == 0);
+  if (At_.windowed) {
+    // the slab kernel cannot walk P's rows without unbalancing its window-0 CTAs: P u goes first
+    const T* pu = nullptr;
+    if (lead && P_.nnz > 0) {
+      launch_spmv(P_, u, (const DevCsr<T>*)nullptr, (const T*)nullptr, n_, EpiStore<T>{done, vec_n2_.p}, red(SC_TMP0), "spmv_P");
+      pu = vec_n2_.p;
+    }
+    launch_spmv(At_, tm_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, n_,
+                EpiKktOp<T>{done, cb_.p, u, lead ? (T)st_.sigma : (T)0, pu}, red_ptr(cb_.p + n_), "spmv_kkt_op");
+  } else {
+    launch_spmv(At_, tm_.p, lead ? &P_ : nullptr, u, n_,
+                EpiKktOp<T>{done, cb_.p, u, lead ? (T)st_.sigma : (T)0, nullptr}, red_ptr(cb_.p + n_), "spmv_kkt_op");
+  }
+}
+
 // solve!(S::IndirectReducedKKTSolver, y, x) with CG (kktsolver_indirect.jl:36-88).
 // Inputs: ls_ = [x1; x2], t0_ = rho .* x2.  Output: xsol_ = y1; then either
 //   fused_tail: w_dst = admm_w!(...) computed in the epilogue of the last SpMV, or
@@ -863,8 +884,7 @@ void Engine<T>::kkt_core(bool fused_tail, const T* w_src, T* w_dst) {
   // c = L x0 (warm start => one product for the initial residual)
   launch_spmv(A_, xsol_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, m_, EpiScale<T>{nullptr, tm_.p, rho_vec_.p},
               red(SC_TMP0), "spmv_A_scale");
-  launch_spmv(At_, tm_.p, lead ? &P_ : nullptr, xsol_.p, n_,
-              EpiKktOp<T>{nullptr, cb_.p, xsol_.p, lead ? (T)st_.sigma : (T)0}, red_ptr(cb_.p + n_), "spmv_kkt_op");
+  kkt_op_stage2(nullptr, xsol_.p);
   allreduce_sum(cb_.p, n_ + 1);
   const double tol_num = st_.tol_constant / pow((double)kkt_counter_, st_.tol_exponent);
   cg_init_kernel<T><<<vgrid(n_), kBlock, 0, stream_>>>(n_, rhsb_.p, cb_.p, r_.p, u_.p, red(SC_RES2),
@@ -879,8 +899,7 @@ void Engine<T>::kkt_core(bool fused_tail, const T* w_src, T* w_dst) {
       check_launch("cg_update_u");
       launch_spmv(A_, u_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, m_, EpiScale<T>{done, tm_.p, rho_vec_.p},
                   red(SC_TMP0), "spmv_A_scale");
-      launch_spmv(At_, tm_.p, lead ? &P_ : nullptr, u_.p, n_,
-                  EpiKktOp<T>{done, cb_.p, u_.p, lead ? (T)st_.sigma : (T)0}, red_ptr(cb_.p + n_), "spmv_kkt_op");
+      kkt_op_stage2(done, u_.p);
       allreduce_sum(cb_.p, n_ + 1);
       cg_update_xr_kernel<T><<<vgrid(n_), kBlock, 0, stream_>>>(n_, u_.p, cb_.p, cb_.p + n_, xsol_.p, r_.p, sc_.p, isc_.p,
                                                              red(SC_RES2), CgStepFin<T>{sc_.p, isc_.p});
@@ -1264,8 +1283,8 @@ void Engine<T>::spmv_bench(int which, int reps, double* ms, double* bytes) {
       launch_spmv(At_, tm_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, n_, EpiStore<T>{nullptr, vec_n_.p}, red(SC_TMP0), "spmv_At");
     else if (which == 2)
       launch_spmv(P_, xsol_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, n_, EpiStore<T>{nullptr, vec_n_.p}, red(SC_TMP0), "spmv_P");
-    else  // 3: the fused reduced-KKT operator stage 2 (A' and P rows + dot)
-      launch_spmv(At_, tm_.p, &P_, xsol_.p, n_, EpiKktOp<T>{nullptr, cb_.p, xsol_.p, (T)st_.sigma}, red_ptr(cb_.p + n_), "spmv_kkt_op");
+    else  // 3: the reduced-KKT operator stage 2 (A' and P rows + dot)
+      kkt_op_stage2(nullptr, xsol_.p);
   };
   for (int i = 0; i < 3; ++i) one();
   CUDA_TRY(cudaEventRecord(ev0_, stream_));

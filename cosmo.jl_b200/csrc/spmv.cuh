@@ -158,8 +158,8 @@ __device__ __forceinline__ T win_row_rest(const unsigned short* __restrict__ col
 // slab w and writes per-window partial sums.  The last of the nwin CTAs of a chunk to finish
 // (per-chunk ticket) folds the partials in window order -- deterministic -- and runs the epilogue
 // (one thread per row); only those "finishing" CTAs take part in the scalar reduction, whose
-// partials are indexed by chunk, not by CTA.  An optional second matrix (P rows, plain L2
-// gather) is folded into window 0's partial sums.
+// partials are indexed by chunk, not by CTA.  (The small P-row product of the reduced KKT
+// operator is computed by a separate launch and enters through the epilogue's `add` vector.)
 template <typename T, typename Epi>
 __global__ void __launch_bounds__(kWinThreads, 1) spmv_win_kernel(WcsrView<T> M, const T* __restrict__ x, CsrView<T> M2,
                                                                   const T* __restrict__ x2, Epi epi, RedBuf<T> rb,
@@ -232,10 +232,6 @@ __global__ void __launch_bounds__(kWinThreads, 1) spmv_win_kernel(WcsrView<T> M,
     if (ceb - csb > 256) pb += win_row_rest<T>(M.col, M.val, xs, csb, ceb, lane);
     const int rowa = r0 + warp + k * kWinWarps;
     const int rowb = rowa + kWinWarps;
-    if (w == 0 && M2.rowptr != nullptr) {   // second matrix (P rows): folded into window 0's partial
-      pa += row_partial<T, 32>(M2, x2, rowa, lane);
-      if (has_b) pb += row_partial<T, 32>(M2, x2, rowb, lane);
-    }
     // paired reduction: lanes 0-15 fold row a, lanes 16-31 fold row b (5 shuffles for 2 rows)
     const bool hi = (lane & 16) != 0;
     T keep = hi ? pb : pa;
@@ -308,9 +304,10 @@ struct EpiKktOp {
   T* c;
   const T* u;
   T sigma;
+  const T* add;   // optional precomputed P u (nullptr: P rows are traversed by the same kernel)
   __device__ void row(int r, T s, T* accS, T*) const {
     const T ur = u[r];
-    const T v = s + sigma * ur;
+    const T v = (add ? s + add[r] : s) + sigma * ur;
     c[r] = v;
     accS[0] += ur * v;
   }
