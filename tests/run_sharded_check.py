@@ -1,0 +1,71 @@
+"""Launched under torchrun (one rank per GPU) by tests/test_gpu_sharded.py: solves the same
+problems row-sharded over WORLD_SIZE GPUs and checks them against the CPU oracle on rank 0."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch
+import torch.distributed as dist
+
+import cosmo_b200
+from cosmo_b200 import sharding
+from oracle import cosmo_oracle as O
+
+
+def gather_rows(local, rows, m, world):
+    parts = [None] * world
+    dist.all_gather_object(parts, (rows, local))
+    full = np.zeros(m)
+    for r, v in parts:
+        full[r] = v
+    return full
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pr = cosmo_b200.problems
+    cases = [("qp_default", pr.random_sparse_qp(600, 1500, 0.05, seed=4), dict()),
+             ("qp_scaled_off", pr.random_sparse_qp(600, 1500, 0.05, seed=5), dict(scaling=0)),
+             ("socp", pr.portfolio_socp(n=300, k=30, seed=2), dict(max_iter=3000, scaling=0)),
+             ("sdp", pr.closest_correlation_sdp(N=24, seed=7), dict(scaling=0))]
+    ok = True
+    for name, (P, q, A, b, sets), kw in cases:
+        st = cosmo_b200.Settings(**kw)
+        m, n = A.shape
+        if st.scaling != 0:
+            Ps, qs, As, bs, ss, D, E, c = cosmo_b200.ruiz_equilibrate(P, q, A, b, sets, st)
+        else:
+            Ps, qs, As, bs, ss, D, E, c = P, q, A, b, sets, None, None, 1.0
+        sh = sharding.make_shard(Ps, qs, As, bs, ss, rank, world)
+        eng = sharding.create_engine(sh, st, device=local_rank, dist=dist, D=D, E=E, c=c)
+        out = eng.solve()
+        x = out.x if D is None else D * out.x
+        s = gather_rows(out.s, sh.rows, m, world)
+        mu = gather_rows(out.mu, sh.rows, m, world)
+        if E is not None:
+            s, mu = s / E, E * mu / c
+        if rank == 0:
+            ref = O.solve(P, q, A, b, pr.to_oracle_cones(sets), O.Settings(kkt_solver="cg", **kw))
+            good = (out.status == ref.status and abs(out.obj_val - ref.obj_val) <= 1e-5 * max(1, abs(ref.obj_val))
+                    and np.max(np.abs(x - ref.x)) <= 1e-5 * max(1, np.abs(ref.x).max())
+                    and np.max(np.abs(s - ref.s)) <= 1e-5 * max(1, np.abs(ref.s).max())
+                    and np.max(np.abs(-mu - ref.y)) <= 1e-5 * max(1, np.abs(ref.y).max()))
+            print("%-14s world=%d status=%s/%s iter=%d/%d obj=%.9g/%.9g dx=%.2e %s" % (
+                name, world, out.status, ref.status, out.iter, ref.iter, out.obj_val, ref.obj_val,
+                np.max(np.abs(x - ref.x)), "OK" if good else "MISMATCH"), flush=True)
+            ok = ok and good
+        eng.close()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
