@@ -216,6 +216,8 @@ class Engine : public EngineBase {
   bool is_optimized_ = false;
   // KKT (reduced CG)
   DevBuf<T> ls_, t0_, tm_, xsol_, rhsb_, cb_, r_, u_, nu_;
+  DevBuf<T> mr_[6], mr_x_, mr_c_, mr_b_;   // MINRES Lanczos / direction vectors, solution, operator output, rhs
+  int cur_maxit_ = -1;
   long long kkt_counter_ = 1;   // S.iteration_counter
   int last_cg_iters_ = 1;
   long long total_inner_ = 0, total_mults_ = 0;
@@ -265,7 +267,10 @@ class Engine : public EngineBase {
   void project_device(const T* w, bool with_rhs, const T* ws_rhs);
   void soc_norms(const T* ws, T* norm_out);
   void kkt_core(bool fused_tail, const T* w_src, T* w_dst);
-  void kkt_op_stage2(const int* done, const T* u);
+  void kkt_op_stage2(const int* done, const T* u, const T* t_in, T* c_out);
+  void kkt_cg(const int* done);
+  void kkt_minres(bool full);
+  void set_maxit(int v);
   void compute_residuals(const T* x, const T* s, const T* mu, bool ignore_scaling, double out[5]);
   bool adapt_rho(const T* x);
   bool primal_infeasible();
@@ -759,6 +764,7 @@ void Engine<T>::reset() {
   CUDA_TRY(cudaMemsetAsync(xsol_.p, 0, std::max(n_, 1) * sizeof(T), stream_));
   CUDA_TRY(cudaMemsetAsync(W_[0].p, 0, std::max(n_ + m_, 1) * sizeof(T), stream_));
   CUDA_TRY(cudaMemsetAsync(W_[1].p, 0, std::max(n_ + m_, 1) * sizeof(T), stream_));
+  if (mr_x_.p) CUDA_TRY(cudaMemsetAsync(mr_x_.p, 0, mr_x_.n * sizeof(T), stream_));
   kkt_counter_ = 1;
   last_cg_iters_ = 1;
   is_optimized_ = false;
@@ -850,7 +856,7 @@ void Engine<T>::project_device(const T* w, bool with_rhs, const T* ws_rhs) {
 // c = A' tm + P u + sigma u ; cb[n] = u'c   (second half of reduced_mul!, kktsolver_indirect.jl:61-65)
 // Rank 0 alone adds the replicated P / sigma terms of a row-sharded run.
 template <typename T>
-void Engine<T>::kkt_op_stage2(const int* done, const T* u) {
+void Engine<T>::kkt_op_stage2(const int* done, const T* u, const T* t_in, T* c_out) {
   const bool lead = (rank_ == 0);
   if (At_.windowed) {
     // the slab kernel cannot walk P's rows without unbalancing its window-0 CTAs: P u goes first
@@ -859,12 +865,21 @@ void Engine<T>::kkt_op_stage2(const int* done, const T* u) {
       launch_spmv(P_, u, (const DevCsr<T>*)nullptr, (const T*)nullptr, n_, EpiStore<T>{done, vec_n2_.p}, red(SC_TMP0), "spmv_P");
       pu = vec_n2_.p;
     }
-    launch_spmv(At_, tm_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, n_,
-                EpiKktOp<T>{done, cb_.p, u, lead ? (T)st_.sigma : (T)0, pu}, red_ptr(cb_.p + n_), "spmv_kkt_op");
+    launch_spmv(At_, t_in, (const DevCsr<T>*)nullptr, (const T*)nullptr, n_,
+                EpiKktOp<T>{done, c_out, u, lead ? (T)st_.sigma : (T)0, pu}, red_ptr(cb_.p + n_), "spmv_kkt_op");
   } else {
-    launch_spmv(At_, tm_.p, lead ? &P_ : nullptr, u, n_,
-                EpiKktOp<T>{done, cb_.p, u, lead ? (T)st_.sigma : (T)0, nullptr}, red_ptr(cb_.p + n_), "spmv_kkt_op");
+    launch_spmv(At_, t_in, lead ? &P_ : nullptr, u, n_,
+                EpiKktOp<T>{done, c_out, u, lead ? (T)st_.sigma : (T)0, nullptr}, red_ptr(cb_.p + n_), "spmv_kkt_op");
   }
+}
+
+template <typename T>
+void Engine<T>::set_maxit(int v) {
+  if (cur_maxit_ == v) return;
+  h_isc_[ISC_MAXIT] = v;
+  CUDA_TRY(cudaMemcpyAsync(isc_.p + ISC_MAXIT, h_isc_ + ISC_MAXIT, sizeof(int), cudaMemcpyHostToDevice, stream_));
+  sync();
+  cur_maxit_ = v;
 }
 
 // solve!(S::IndirectReducedKKTSolver, y, x) with CG (kktsolver_indirect.jl:36-88).
@@ -873,50 +888,26 @@ void Engine<T>::kkt_op_stage2(const int* done, const T* u) {
 //   plain:      nu_ = y2 = rho .* (A y1 - x2).
 template <typename T>
 void Engine<T>::kkt_core(bool fused_tail, const T* w_src, T* w_dst) {
-  if (st_.kkt_solver != COSMO_B200_KKT_CG)
-    throw EngineError{COSMO_B200_ERR_UNSUPPORTED, "only the CG reduced-KKT solver is implemented in this build"};
-  const int* done = isc_.p + ISC_DONE;
   const bool lead = (rank_ == 0);
-  // rhs = x1 + A' (rho .* x2)
+  const bool full = (st_.kkt_solver == COSMO_B200_KKT_MINRES);
+  if (st_.kkt_solver != COSMO_B200_KKT_CG && st_.kkt_solver != COSMO_B200_KKT_MINRES_REDUCED && !full)
+    throw EngineError{COSMO_B200_ERR_UNSUPPORTED, "unknown kkt_solver"};
+  if (full && nranks_ > 1)
+    throw EngineError{COSMO_B200_ERR_UNSUPPORTED, "full-KKT MINRES is single-GPU in this build (use CG or reduced MINRES when sharded)"};
+  if (full) {
+    kkt_minres(true);   // xsol_ = y1, nu_ = y2
+    if (fused_tail) {
+      admm_tail_kernel<T><<<vgrid(m_), kBlock, 0, stream_>>>(m_, nu_.p, rho_vec_.p, s_.p, w_src + n_, w_dst + n_, (T)st_.alpha);
+      check_launch("admm_tail");
+    }
+    return;
+  }
+  // reduced system: rhs = x1 + A' (rho .* x2)   (kktsolver_indirect.jl:50-54)
   launch_spmv(At_, t0_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, n_,
               EpiAddVec<T>{nullptr, rhsb_.p, lead ? ls_.p : nullptr}, red(SC_TMP0), "spmv_rhs");
   allreduce_sum(rhsb_.p, n_);
-  // c = L x0 (warm start => one product for the initial residual)
-  launch_spmv(A_, xsol_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, m_, EpiScale<T>{nullptr, tm_.p, rho_vec_.p},
-              red(SC_TMP0), "spmv_A_scale");
-  kkt_op_stage2(nullptr, xsol_.p);
-  allreduce_sum(cb_.p, n_ + 1);
-  const double tol_num = st_.tol_constant / pow((double)kkt_counter_, st_.tol_exponent);
-  cg_init_kernel<T><<<vgrid(n_), kBlock, 0, stream_>>>(n_, rhsb_.p, cb_.p, r_.p, u_.p, red(SC_RES2),
-                                                      CgInitFin<T>{sc_.p, isc_.p, (T)tol_num});
-  check_launch("cg_init");
-  long long mults = 1;
-  int launched = 0;
-  int chunk = std::max(last_cg_iters_, 0);
-  for (;;) {
-    for (int i = 0; i < chunk; ++i) {
-      cg_update_u_kernel<T><<<vgrid(n_), kBlock, 0, stream_>>>(n_, r_.p, u_.p, sc_.p, isc_.p);
-      check_launch("cg_update_u");
-      launch_spmv(A_, u_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, m_, EpiScale<T>{done, tm_.p, rho_vec_.p},
-                  red(SC_TMP0), "spmv_A_scale");
-      kkt_op_stage2(done, u_.p);
-      allreduce_sum(cb_.p, n_ + 1);
-      cg_update_xr_kernel<T><<<vgrid(n_), kBlock, 0, stream_>>>(n_, u_.p, cb_.p, cb_.p + n_, xsol_.p, r_.p, sc_.p, isc_.p,
-                                                             red(SC_RES2), CgStepFin<T>{sc_.p, isc_.p});
-      check_launch("cg_update_xr");
-      ++launched;
-    }
-    CUDA_TRY(cudaMemcpyAsync(h_isc_, isc_.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream_));
-    sync();
-    if (h_isc_[ISC_DONE]) break;
-    chunk = 1;
-  }
-  const int iters = h_isc_[ISC_IT];
-  (void)launched;
-  last_cg_iters_ = iters;
-  total_inner_ += iters;
-  mults += iters;
-  total_mults_ += mults;
+  if (st_.kkt_solver == COSMO_B200_KKT_CG) kkt_cg(isc_.p + ISC_DONE);
+  else kkt_minres(false);
   kkt_counter_ += 1;
   if (fused_tail) {
     launch_spmv(A_, xsol_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, m_,
@@ -925,6 +916,114 @@ void Engine<T>::kkt_core(bool fused_tail, const T* w_src, T* w_dst) {
   } else {
     launch_spmv(A_, xsol_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, m_,
                 EpiY2<T>{nullptr, nu_.p, ls_.p + n_, rho_vec_.p}, red(SC_TMP0), "spmv_y2");
+  }
+}
+
+// cg!(previous_solution, L, y1; abstol = tol_k/|y1|, reltol = 0) (kktsolver_indirect.jl:70)
+template <typename T>
+void Engine<T>::kkt_cg(const int* done) {
+  set_maxit(n_);   // IterativeSolvers default maxiter = size(A, 2)
+  // c = L x0 (warm start => one product for the initial residual)
+  launch_spmv(A_, xsol_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, m_, EpiScale<T>{nullptr, tm_.p, rho_vec_.p},
+              red(SC_TMP0), "spmv_A_scale");
+  kkt_op_stage2(nullptr, xsol_.p, tm_.p, cb_.p);
+  allreduce_sum(cb_.p, n_ + 1);
+  const double tol_num = st_.tol_constant / pow((double)kkt_counter_, st_.tol_exponent);
+  cg_init_kernel<T><<<vgrid(n_), kBlock, 0, stream_>>>(n_, rhsb_.p, cb_.p, r_.p, u_.p, red(SC_RES2),
+                                                      CgInitFin<T>{sc_.p, isc_.p, (T)tol_num});
+  check_launch("cg_init");
+  int chunk = std::max(last_cg_iters_, 0);
+  for (;;) {
+    for (int i = 0; i < chunk; ++i) {
+      cg_update_u_kernel<T><<<vgrid(n_), kBlock, 0, stream_>>>(n_, r_.p, u_.p, sc_.p, isc_.p);
+      check_launch("cg_update_u");
+      launch_spmv(A_, u_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, m_, EpiScale<T>{done, tm_.p, rho_vec_.p},
+                  red(SC_TMP0), "spmv_A_scale");
+      kkt_op_stage2(done, u_.p, tm_.p, cb_.p);
+      allreduce_sum(cb_.p, n_ + 1);
+      cg_update_xr_kernel<T><<<vgrid(n_), kBlock, 0, stream_>>>(n_, u_.p, cb_.p, cb_.p + n_, xsol_.p, r_.p, sc_.p, isc_.p,
+                                                             red(SC_RES2), CgStepFin<T>{sc_.p, isc_.p});
+      check_launch("cg_update_xr");
+    }
+    CUDA_TRY(cudaMemcpyAsync(h_isc_, isc_.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    sync();
+    if (h_isc_[ISC_DONE]) break;
+    chunk = 1;
+  }
+  const int iters = h_isc_[ISC_IT];
+  last_cg_iters_ = iters;
+  total_inner_ += iters;
+  total_mults_ += 1 + iters;
+}
+
+// minres!(previous_solution, L, b; abstol = tol_k/|L x0 - b|, reltol = 0) on the reduced system
+// (kktsolver_indirect.jl:72-73) or on the full KKT operator (:123-162).
+template <typename T>
+void Engine<T>::kkt_minres(bool full) {
+  const int npad = (n_ + 3) & ~3;                 // x2 starts 16-byte aligned (TMA bulk copies of v + npad)
+  const int L = full ? npad + m_ : n_;
+  if (mr_c_.n < (size_t)L) {
+    for (auto& b : mr_) b.alloc(L);
+    mr_c_.alloc(L);
+    if (full) { mr_x_.alloc(L); mr_b_.alloc(L); }
+  }
+  const int* done = isc_.p + ISC_DONE;
+  T* x = full ? mr_x_.p : xsol_.p;
+  const T* b = full ? mr_b_.p : rhsb_.p;
+  set_maxit(full ? n_ + m_ : n_);
+  if (full) {
+    CUDA_TRY(cudaMemcpyAsync(mr_b_.p, ls_.p, n_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+    CUDA_TRY(cudaMemcpyAsync(mr_b_.p + npad, ls_.p + n_, m_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+  }
+  // y = L v : reduced (P + sigma I + A' rho A) v  or  full [P + sigma I, A'; A, -1/rho] v
+  auto apply = [&](const int* dn, const T* v, T* y) {
+    if (full) {
+      kkt_op_stage2(dn, v, v + npad, y);                                                        // y1 = A'x2 + P x1 + sigma x1
+      launch_spmv(A_, v, (const DevCsr<T>*)nullptr, (const T*)nullptr, m_,
+                  EpiKktFullLower<T>{dn, y + npad, v + npad, rho_vec_.p}, red(SC_TMP0), "spmv_kkt_lower");  // y2 = A x1 - x2/rho
+    } else {
+      launch_spmv(A_, v, (const DevCsr<T>*)nullptr, (const T*)nullptr, m_, EpiScale<T>{dn, tm_.p, rho_vec_.p}, red(SC_TMP0),
+                  "spmv_A_scale");
+      kkt_op_stage2(dn, v, tm_.p, y);
+      allreduce_sum(y, n_);
+    }
+  };
+  T* v_prev = mr_[0].p; T* v_curr = mr_[1].p; T* v_next = mr_[2].p;
+  T* w_prev = mr_[3].p; T* w_curr = mr_[4].p; T* w_next = mr_[5].p;
+  apply(nullptr, x, mr_c_.p);
+  const double tol_num = st_.tol_constant / pow((double)kkt_counter_, st_.tol_exponent);
+  minres_init_kernel<T><<<vgrid(L), kBlock, 0, stream_>>>(L, b, mr_c_.p, v_curr, red(SC_RES2), MinresInitFin<T>{sc_.p, isc_.p, (T)tol_num});
+  check_launch("minres_init");
+  minres_start_kernel<T><<<vgrid(L), kBlock, 0, stream_>>>(L, v_curr, v_prev, w_prev, w_curr, sc_.p);
+  check_launch("minres_start");
+  int it_host = 0;
+  int chunk = std::max(last_cg_iters_, 0);
+  for (;;) {
+    for (int i = 0; i < chunk; ++i) {
+      ++it_host;
+      apply(done, v_curr, mr_c_.p);
+      minres_lanczos1_kernel<T><<<vgrid(L), kBlock, 0, stream_>>>(L, mr_c_.p, v_prev, v_curr, v_next, sc_.p, isc_.p, red(SC_H3));
+      check_launch("minres_lanczos1");
+      minres_lanczos2_kernel<T><<<vgrid(L), kBlock, 0, stream_>>>(L, v_curr, v_next, sc_.p, isc_.p, red(SC_RES2), MinresStepFin<T>{sc_.p, isc_.p});
+      check_launch("minres_lanczos2");
+      minres_update_kernel<T><<<vgrid(L), kBlock, 0, stream_>>>(L, it_host, v_curr, v_next, w_prev, w_curr, w_next, x, sc_.p, isc_.p);
+      check_launch("minres_update");
+      T* t = v_prev; v_prev = v_curr; v_curr = v_next; v_next = t;
+      t = w_prev; w_prev = w_curr; w_curr = w_next; w_next = t;
+    }
+    CUDA_TRY(cudaMemcpyAsync(h_isc_, isc_.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    sync();
+    if (h_isc_[ISC_DONE]) break;
+    chunk = 1;
+  }
+  const int iters = h_isc_[ISC_IT];
+  last_cg_iters_ = iters;
+  total_inner_ += iters;
+  total_mults_ += 2 + iters;   // + init residual + the reference's explicit L*x0 - b (kktsolver_indirect.jl:72,151)
+  if (full) {
+    CUDA_TRY(cudaMemcpyAsync(xsol_.p, mr_x_.p, n_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+    CUDA_TRY(cudaMemcpyAsync(nu_.p, mr_x_.p + npad, m_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+    kkt_counter_ += 1;
   }
 }
 
@@ -1284,7 +1383,7 @@ void Engine<T>::spmv_bench(int which, int reps, double* ms, double* bytes) {
     else if (which == 2)
       launch_spmv(P_, xsol_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, n_, EpiStore<T>{nullptr, vec_n_.p}, red(SC_TMP0), "spmv_P");
     else  // 3: the reduced-KKT operator stage 2 (A' and P rows + dot)
-      kkt_op_stage2(nullptr, xsol_.p);
+      kkt_op_stage2(nullptr, xsol_.p, tm_.p, cb_.p);
   };
   for (int i = 0; i < 3; ++i) one();
   CUDA_TRY(cudaEventRecord(ev0_, stream_));

@@ -337,6 +337,18 @@ struct EpiY2 {
   __device__ void operator()(T*) const {}
 };
 
+// y2 = A x1 - x2 ./ rho                    (kkt_mul!, kktsolver_indirect.jl:141-143)
+template <typename T>
+struct EpiKktFullLower {
+  static constexpr int NS = 0, NM = 0;
+  const int* done;
+  T* y;
+  const T* x2;
+  const T* rho;
+  __device__ void row(int r, T s, T*, T*) const { y[r] = s - x2[r] / rho[r]; }
+  __device__ void operator()(T*) const {}
+};
+
 // Fused ADMM tail on the last SpMV of the x-step:
 //   nu   = rho .* (A y1 - x2)               (kktsolver_indirect.jl:80-83)
 //   s_tl = 2 s - w_s - nu ./ rho            (solver.jl:55)

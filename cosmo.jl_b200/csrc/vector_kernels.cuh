@@ -24,6 +24,8 @@ enum {
   SC_H1 = 16, SC_H2 = 17, SC_H3 = 18, SC_H4 = 19,
   SC_RHS_1 = 20, SC_RHS_2 = 21,
   SC_C_PREV = 22, SC_S_PREV = 23, SC_C_CURR = 24, SC_S_CURR = 25,
+  // per-iteration coefficients handed from the scalar epilogue to the vector update kernel
+  SC_K3_INV_H4 = 26, SC_K3_H2 = 27, SC_K3_H1 = 28, SC_K3_INV_H3 = 29, SC_K3_RHS1 = 30,
   SC_COUNT = 32
 };
 enum { ISC_DONE = 0, ISC_IT = 1, ISC_MAXIT = 2, ISC_COUNT = 8 };
@@ -346,6 +348,173 @@ __global__ void __launch_bounds__(kBlock) soc_cert_kernel(int ncones, const int*
     if (!(norm[k] <= tol - v[off[k]])) bad = 1;
   bad = __syncthreads_or(bad);
   if (threadIdx.x == 0) flag[0] = bad ? T(1) : T(0);
+}
+
+// ---------------------------------------------------------------------------
+// MINRES (IterativeSolvers.jl v0.9 minres!, called from kktsolver_indirect.jl:73,152)
+// on an L-vector (L = n: reduced system, L = n+m: full KKT).  H[1..4], rhs[1..2] and
+// the two stored Givens rotations live in sc[SC_H1..]; every kernel is a no-op once
+// isc[ISC_DONE] is set, except the vector update of the iteration that set it.
+// ---------------------------------------------------------------------------
+template <typename T>
+struct MinresInitFin {
+  T* sc; int* isc; T tol_num;
+  __device__ void operator()(T* out) const {   // out[0] = |b - L x|^2
+    const T res = sqrt(out[0]);
+    sc[SC_RES] = res;
+    sc[SC_TOL] = tol_num / res;                // abstol = get_tolerance(S) / init_residual, reltol = 0
+    sc[SC_H1] = sc[SC_H2] = sc[SC_H3] = sc[SC_H4] = T(0);
+    sc[SC_RHS_1] = res; sc[SC_RHS_2] = T(0);
+    sc[SC_C_PREV] = T(1); sc[SC_S_PREV] = T(0); sc[SC_C_CURR] = T(1); sc[SC_S_CURR] = T(0);
+    isc[ISC_IT] = 0;
+    isc[ISC_DONE] = (res <= sc[SC_TOL] || isc[ISC_MAXIT] <= 0) ? 1 : 0;
+  }
+};
+
+// v_curr = b - c ; |v_curr|^2
+template <typename T>
+__global__ void __launch_bounds__(kBlock) minres_init_kernel(int L, const T* __restrict__ b, const T* __restrict__ c,
+                                                             T* __restrict__ v_curr, RedBuf<T> rb, MinresInitFin<T> fin) {
+  T accS[1] = {0};
+  T accM[1] = {0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L; i += gridDim.x * blockDim.x) {
+    const T v = b[i] - c[i];
+    v_curr[i] = v;
+    accS[0] += v * v;
+  }
+  reduce_and_finalize<T, 1, 0>(accS, accM, rb, fin);
+}
+
+// v_curr /= resnorm ; v_prev = w_prev = w_curr = 0
+template <typename T>
+__global__ void __launch_bounds__(kBlock) minres_start_kernel(int L, T* __restrict__ v_curr, T* __restrict__ v_prev,
+                                                              T* __restrict__ w_prev, T* __restrict__ w_curr,
+                                                              const T* __restrict__ sc) {
+  const T inv = T(1) / sc[SC_RES];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L; i += gridDim.x * blockDim.x) {
+    v_curr[i] *= inv;
+    v_prev[i] = T(0);
+    w_prev[i] = T(0);
+    w_curr[i] = T(0);
+  }
+}
+
+struct MinresProjFin {
+  template <typename T>
+  __device__ void operator()(T*) const {}
+};
+
+// v_next = c - H[2] v_prev ; proj = v_curr' v_next  -> sc[SC_H3]
+template <typename T>
+__global__ void __launch_bounds__(kBlock) minres_lanczos1_kernel(int L, const T* __restrict__ c, const T* __restrict__ v_prev,
+                                                                 const T* __restrict__ v_curr, T* __restrict__ v_next,
+                                                                 const T* __restrict__ sc, const int* __restrict__ isc,
+                                                                 RedBuf<T> rb) {
+  if (isc[ISC_DONE]) return;
+  const T h2 = sc[SC_H2];
+  T accS[1] = {0};
+  T accM[1] = {0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L; i += gridDim.x * blockDim.x) {
+    const T v = c[i] - h2 * v_prev[i];
+    v_next[i] = v;
+    accS[0] += v_curr[i] * v;
+  }
+  reduce_and_finalize<T, 1, 0>(accS, accM, rb, NoFin());
+}
+
+// LinearAlgebra.givensAlgorithm, real case: [c s; -s c] [f; g] = [r; 0]
+template <typename T>
+__device__ __forceinline__ void givens_rot(T f, T g, T& c, T& s, T& r) {
+  if (g == T(0)) { c = T(1); s = T(0); r = f; return; }
+  if (f == T(0)) { c = T(0); s = T(1); r = g; return; }
+  r = hypot(f, g);
+  c = f / r;
+  s = g / r;
+  if (tabs(f) > tabs(g) && c < T(0)) { c = -c; s = -s; r = -r; }
+}
+
+template <typename T>
+struct MinresStepFin {
+  T* sc; int* isc;
+  __device__ void operator()(T* out) const {   // out[0] = |v_next|^2 ; sc[SC_H3] holds proj
+    T H1 = sc[SC_H1], H2 = sc[SC_H2], H3 = sc[SC_H3];
+    const T H4 = sqrt(out[0]);
+    const int it = isc[ISC_IT] + 1;            // 1-based index of the iteration being completed
+    const T c_prev = sc[SC_C_PREV], s_prev = sc[SC_S_PREV], c_curr = sc[SC_C_CURR], s_curr = sc[SC_S_CURR];
+    if (it > 2) { H1 = s_prev * H2; H2 = c_prev * H2; }
+    if (it > 1) {
+      const T tmp = -s_curr * H2 + c_curr * H3;
+      H2 = c_curr * H2 + s_curr * H3;
+      H3 = tmp;
+    }
+    T c, s, r;
+    givens_rot(H3, H4, c, s, r);
+    H3 = r;
+    const T rhs2 = -s * sc[SC_RHS_1];
+    const T rhs1 = c * sc[SC_RHS_1];
+    // coefficients for the vector update of this iteration
+    sc[SC_K3_INV_H4] = T(1) / H4;
+    sc[SC_K3_H2] = H2;
+    sc[SC_K3_H1] = (it > 2) ? H1 : T(0);
+    sc[SC_K3_INV_H3] = T(1) / H3;
+    sc[SC_K3_RHS1] = rhs1;
+    // move on
+    sc[SC_C_PREV] = c_curr; sc[SC_S_PREV] = s_curr; sc[SC_C_CURR] = c; sc[SC_S_CURR] = s;
+    sc[SC_RHS_1] = rhs2; sc[SC_RHS_2] = rhs2;
+    sc[SC_H1] = H1; sc[SC_H2] = H4; sc[SC_H3] = H3; sc[SC_H4] = H4;
+    const T resnorm = tabs(rhs2);
+    sc[SC_RES] = resnorm;
+    isc[ISC_IT] = it;
+    isc[ISC_DONE] = (resnorm <= sc[SC_TOL] || it >= isc[ISC_MAXIT]) ? 1 : 0;
+  }
+};
+
+// v_next -= proj v_curr ; |v_next|^2 ; scalar recurrences in the epilogue
+template <typename T>
+__global__ void __launch_bounds__(kBlock) minres_lanczos2_kernel(int L, const T* __restrict__ v_curr, T* __restrict__ v_next,
+                                                                 const T* __restrict__ sc, const int* __restrict__ isc,
+                                                                 RedBuf<T> rb, MinresStepFin<T> fin) {
+  if (isc[ISC_DONE]) return;
+  const T proj = sc[SC_H3];
+  T accS[1] = {0};
+  T accM[1] = {0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L; i += gridDim.x * blockDim.x) {
+    const T v = v_next[i] - proj * v_curr[i];
+    v_next[i] = v;
+    accS[0] += v * v;
+  }
+  reduce_and_finalize<T, 1, 0>(accS, accM, rb, fin);
+}
+
+// v_next /= H[4] ; w_next = (v_curr - H[2] w_curr - H[1] w_prev) / H[3] ; x += rhs[1] w_next
+// Runs iff iteration `it_host` was completed on the device (also for the iteration that set done).
+template <typename T>
+__global__ void __launch_bounds__(kBlock) minres_update_kernel(int L, int it_host, const T* __restrict__ v_curr,
+                                                               T* __restrict__ v_next, const T* __restrict__ w_prev,
+                                                               const T* __restrict__ w_curr, T* __restrict__ w_next,
+                                                               T* __restrict__ x, const T* __restrict__ sc,
+                                                               const int* __restrict__ isc) {
+  if (isc[ISC_IT] < it_host) return;
+  const T inv_h4 = sc[SC_K3_INV_H4], h2 = sc[SC_K3_H2], h1 = sc[SC_K3_H1], inv_h3 = sc[SC_K3_INV_H3], rhs1 = sc[SC_K3_RHS1];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L; i += gridDim.x * blockDim.x) {
+    v_next[i] *= inv_h4;
+    const T w = (v_curr[i] - h2 * w_curr[i] - h1 * w_prev[i]) * inv_h3;
+    w_next[i] = w;
+    x[i] += rhs1 * w;
+  }
+}
+
+// elementwise ADMM tail for solvers that return nu directly (full-KKT MINRES):
+//   s_tl = 2 s - w_s - nu ./ rho ; w_s += alpha (s_tl - s)         (solver.jl:55,64)
+template <typename T>
+__global__ void __launch_bounds__(kBlock) admm_tail_kernel(int m, const T* __restrict__ nu, const T* __restrict__ rho,
+                                                           const T* __restrict__ s, const T* __restrict__ ws_in,
+                                                           T* __restrict__ ws_out, T alpha) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    const T sr = s[i], w = ws_in[i];
+    const T s_tl = T(2) * sr - w - nu[i] / rho[i];
+    ws_out[i] = w + alpha * (s_tl - sr);
+  }
 }
 
 }  // namespace cosmo

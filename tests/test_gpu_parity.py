@@ -221,6 +221,44 @@ def test_kkt_solve_matches_oracle_and_direct():
         assert np.linalg.norm(sol - exact) <= 1e3 * max(tol, 1e-12) * (1 + np.linalg.norm(exact))
 
 
+@pytest.mark.parametrize("name,kind", [("MINRESIndirectKKTSolver", "minres"), ("IndirectReducedKKTSolver:MINRES", "minres_reduced")])
+def test_minres_kkt_solve_matches_oracle(name, kind):
+    # IndirectKKTSolver / IndirectReducedKKTSolver(:MINRES), kktsolver_indirect.jl:72-73, 123-162
+    P, q, A, b, sets = _small_qp(seed=3, n=41, m=70)      # odd n: exercises the padded x2 offset
+    m, n = A.shape
+    eng = _engine(P, q, A, b, sets, scaling=0, kkt_solver=name)
+    rho = eng.rho_vec()
+    ref_solver = O.make_kkt_solver(kind, P, A, 1e-6, rho.copy(), O.Settings())
+    direct = O.DirectKKT(P, A, 1e-6, rho)
+    rng = np.random.default_rng(9)
+    for k in range(5):
+        rhs = rng.standard_normal(n + m)
+        sol, inner = eng.kkt_solve(rhs)
+        ref = ref_solver.solve(rhs)
+        assert abs(inner - ref_solver.inner_iterations[-1]) <= 2
+        assert np.linalg.norm(sol - ref) <= 1e-6 * (1 + np.linalg.norm(ref))
+    # both converge to the direct solution when the tolerance schedule has tightened
+    for k in range(40):
+        sol, _ = eng.kkt_solve(rhs)
+    assert np.linalg.norm(sol - direct.solve(rhs)) <= 1e-3 * (1 + np.linalg.norm(sol))
+
+
+@pytest.mark.parametrize("name,kind", [("MINRESIndirectKKTSolver", "minres"), ("IndirectReducedKKTSolver:MINRES", "minres_reduced")])
+def test_minres_solve_matches_oracle(name, kind):
+    P, q, A, b, sets = _small_qp(seed=12)
+    cones = cosmo_b200.problems.to_oracle_cones(sets)
+    ref = O.solve(P, q, A, b, cones, O.Settings(kkt_solver=kind, max_iter=300))
+    model = cosmo_b200.Model()
+    model.set(P, q, A, b, sets, cosmo_b200.Settings(kkt_solver=name, max_iter=300))
+    res = model.optimize()
+    # the reference's MINRES tolerance rule (abstol = tol_k / initial residual) makes the outer
+    # iteration plateau (see tests/test_oracle_golden.py); inner iteration counts sit on a knife
+    # edge there, so the two trajectories are only compared loosely.  kkt_solve above is the tight check.
+    assert res.status == ref.status and res.iter == ref.iter
+    assert abs(res.obj_val - ref.obj_val) <= 2e-2 * max(1, abs(ref.obj_val))
+    assert np.max(np.abs(res.x - ref.x)) <= 5e-2 * max(1, np.abs(ref.x).max())
+
+
 def test_residuals_match_oracle():
     P, q, A, b, sets = _small_qp(seed=4)
     m, n = A.shape
