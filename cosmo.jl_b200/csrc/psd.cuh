@@ -335,6 +335,217 @@ __global__ void __launch_bounds__(kBlock) psd_large_rows_kernel(int N, int r, T*
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Large cones, block Jacobi (two-sided, block size 32): per round the Nb/2 disjoint block
+// pairs (I,J) of the round-robin ordering are handled in three launches
+//   1. bj_pivot_kernel : one CTA per pair diagonalises its 64x64 pivot [A_II A_IJ; A_JI A_JJ]
+//                        in shared memory (<= 2 cyclic Jacobi sweeps) and stores R (64x64)
+//   2. bj_cols_kernel  : A[:, I|J] <- A[:, I|J] R  and  V[:, I|J] <- V[:, I|J] R   (64x64x64 tiles)
+//   3. bj_rows_kernel  : A[I|J, :] <- R' A[I|J, :]
+// so the O(N^3) work is GEMM-shaped and L2-resident; pairs whose pivot is already diagonal
+// (to eps |A|_F) are skipped, which is what makes warm starts cheap.
+// ---------------------------------------------------------------------------
+constexpr int kBjB = 32;          // block size
+constexpr int kBjP = 2 * kBjB;    // pivot size
+
+__device__ __forceinline__ int bj_col(int I, int J, int k) { return (k < kBjB) ? I * kBjB + k : J * kBjB + (k - kBjB); }
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock) bj_pivot_kernel(int N, int Nb, int r, const T* __restrict__ A, const T* __restrict__ thr_p,
+                                                          T* __restrict__ Rbuf, int* __restrict__ active, int* __restrict__ rotated,
+                                                          int inner_sweeps) {
+  extern __shared__ unsigned char smem_raw[];
+  constexpr int P = kBjP, ld = P + 1;
+  T* Sa = reinterpret_cast<T*>(smem_raw);
+  T* Sv = Sa + ld * P;
+  T* cs = Sv + ld * P;
+  __shared__ int any_big, rot_flag;
+  const int k = blockIdx.x;
+  int I, J;
+  rr_pair(Nb, r, k, I, J);
+  const T thr = *thr_p;
+  if (threadIdx.x == 0) { any_big = 0; }
+  __syncthreads();
+  for (int e = threadIdx.x; e < P * P; e += blockDim.x) {
+    const int i = e % P, j = e / P;
+    const int gi = bj_col(I, J, i), gj = bj_col(I, J, j);
+    T v = T(0);
+    if (gi < N && gj < N) v = A[gi + (long long)gj * N];
+    Sa[i + j * ld] = v;
+    Sv[i + j * ld] = (i == j) ? T(1) : T(0);
+    if (i != j && tabs(v) > thr) any_big = 1;
+  }
+  __syncthreads();
+  if (!any_big) {
+    if (threadIdx.x == 0) active[k] = 0;
+    return;
+  }
+  // symmetrise the pivot copy (the two triangles of A drift by rounding)
+  for (int e = threadIdx.x; e < P * P; e += blockDim.x) {
+    const int i = e % P, j = e / P;
+    if (i < j) {
+      const T v = T(0.5) * (Sa[i + j * ld] + Sa[j + i * ld]);
+      Sa[i + j * ld] = v;
+      Sa[j + i * ld] = v;
+    }
+  }
+  __syncthreads();
+  const int npairs = P / 2;
+  for (int sweep = 0; sweep < inner_sweeps; ++sweep) {
+    if (threadIdx.x == 0) rot_flag = 0;
+    __syncthreads();
+    for (int rr = 0; rr < P - 1; ++rr) {
+      for (int kk = threadIdx.x; kk < npairs; kk += blockDim.x) {
+        int p, q;
+        rr_pair(P, rr, kk, p, q);
+        T c = T(1), sn = T(0);
+        const T apq = Sa[p + q * ld];
+        if (tabs(apq) > thr) {
+          sym_schur(Sa[p + p * ld], Sa[q + q * ld], apq, c, sn);
+          rot_flag = 1;
+        }
+        cs[2 * kk] = c;
+        cs[2 * kk + 1] = sn;
+      }
+      __syncthreads();
+      for (int e = threadIdx.x; e < npairs * P; e += blockDim.x) {
+        const int kk = e / P, i = e % P;
+        const T sn = cs[2 * kk + 1];
+        if (sn == T(0)) continue;
+        const T c = cs[2 * kk];
+        int p, q;
+        rr_pair(P, rr, kk, p, q);
+        const T aip = Sa[i + p * ld], aiq = Sa[i + q * ld];
+        Sa[i + p * ld] = c * aip - sn * aiq;
+        Sa[i + q * ld] = sn * aip + c * aiq;
+        const T vip = Sv[i + p * ld], viq = Sv[i + q * ld];
+        Sv[i + p * ld] = c * vip - sn * viq;
+        Sv[i + q * ld] = sn * vip + c * viq;
+      }
+      __syncthreads();
+      for (int e = threadIdx.x; e < npairs * P; e += blockDim.x) {
+        const int kk = e / P, j = e % P;
+        const T sn = cs[2 * kk + 1];
+        if (sn == T(0)) continue;
+        const T c = cs[2 * kk];
+        int p, q;
+        rr_pair(P, rr, kk, p, q);
+        const T apj = Sa[p + j * ld], aqj = Sa[q + j * ld];
+        Sa[p + j * ld] = c * apj - sn * aqj;
+        Sa[q + j * ld] = sn * apj + c * aqj;
+      }
+      __syncthreads();
+    }
+    if (!rot_flag) break;
+    __syncthreads();
+  }
+  T* R = Rbuf + (size_t)k * P * P;
+  for (int e = threadIdx.x; e < P * P; e += blockDim.x) R[e] = Sv[(e % P) + (e / P) * ld];
+  if (threadIdx.x == 0) { active[k] = 1; *rotated = 1; }
+}
+
+// C_tile(64 x 64) = S_tile(64 x 64) * R, in place; S = 64 rows x the 64 columns [I|J] of X (A or V)
+template <typename T>
+__global__ void __launch_bounds__(kBlock) bj_cols_kernel(int N, int Nb, int r, T* __restrict__ A, T* __restrict__ V,
+                                                         const T* __restrict__ Rbuf, const int* __restrict__ active) {
+  const int k = blockIdx.y;
+  if (!active[k]) return;
+  extern __shared__ unsigned char smem_raw[];
+  constexpr int P = kBjP, ld = P + 1;
+  T* S = reinterpret_cast<T*>(smem_raw);     // S[row + col*ld]
+  T* Rs = S + ld * P;                        // Rs[kk + j*P]
+  T* X = (blockIdx.z == 0) ? A : V;
+  int I, J;
+  rr_pair(Nb, r, k, I, J);
+  const int row0 = blockIdx.x * P;
+  const T* R = Rbuf + (size_t)k * P * P;
+  for (int e = threadIdx.x; e < P * P; e += blockDim.x) {
+    const int i = e % P, j = e / P;
+    const int gi = row0 + i, gj = bj_col(I, J, j);
+    S[i + j * ld] = (gi < N && gj < N) ? X[gi + (long long)gj * N] : T(0);
+    Rs[e] = R[e];
+  }
+  __syncthreads();
+  const int ti = (threadIdx.x % 16) * 4, tj = (threadIdx.x / 16) * 4;   // 4x4 micro-tile
+  T acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = T(0);
+#pragma unroll 4
+  for (int kk = 0; kk < P; ++kk) {
+    T sv[4], rv[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) sv[a] = S[ti + a + kk * ld];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) rv[b] = Rs[kk + (tj + b) * P];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] += sv[a] * rv[b];
+  }
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int gj = bj_col(I, J, tj + b);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int gi = row0 + ti + a;
+      if (gi < N && gj < N) X[gi + (long long)gj * N] = acc[a][b];
+    }
+  }
+}
+
+// T_tile(64 x 64) = R' * T_tile, in place; T = the 64 rows [I|J] of A x 64 columns
+template <typename T>
+__global__ void __launch_bounds__(kBlock) bj_rows_kernel(int N, int Nb, int r, T* __restrict__ A, const T* __restrict__ Rbuf,
+                                                         const int* __restrict__ active) {
+  const int k = blockIdx.y;
+  if (!active[k]) return;
+  extern __shared__ unsigned char smem_raw[];
+  constexpr int P = kBjP, ld = P + 1;
+  T* S = reinterpret_cast<T*>(smem_raw);     // S[i + j*ld], i: pivot row, j: column in tile
+  T* Rs = S + ld * P;                        // Rs[kk + i*P] = R[kk][i]
+  int I, J;
+  rr_pair(Nb, r, k, I, J);
+  const int col0 = blockIdx.x * P;
+  const T* R = Rbuf + (size_t)k * P * P;
+  for (int e = threadIdx.x; e < P * P; e += blockDim.x) {
+    const int i = e % P, j = e / P;
+    const int gi = bj_col(I, J, i), gj = col0 + j;
+    S[i + j * ld] = (gi < N && gj < N) ? A[gi + (long long)gj * N] : T(0);
+    Rs[e] = R[e];
+  }
+  __syncthreads();
+  const int ti = (threadIdx.x % 16) * 4, tj = (threadIdx.x / 16) * 4;
+  T acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = T(0);
+#pragma unroll 4
+  for (int kk = 0; kk < P; ++kk) {
+    T rv[4], sv[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) rv[a] = Rs[kk + (ti + a) * P];   // R[kk][ti+a] = (R')[ti+a][kk]
+#pragma unroll
+    for (int b = 0; b < 4; ++b) sv[b] = S[kk + (tj + b) * ld];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] += rv[a] * sv[b];
+  }
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int gj = col0 + tj + b;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int gi = bj_col(I, J, ti + a);
+      if (gi < N && gj < N) A[gi + (long long)gj * N] = acc[a][b];
+    }
+  }
+}
+
 // V[:,k] *= sqrt(max(lambda_k, 0))
 template <typename T>
 __global__ void __launch_bounds__(kBlock) psd_large_scale_kernel(int N, const T* __restrict__ A, T* __restrict__ V) {
@@ -414,11 +625,13 @@ struct PsdBatch {
   T *A_d = nullptr, *V_d = nullptr, *cs_d = nullptr, *fro_d = nullptr, *thr_d = nullptr, *lam_large_d = nullptr;
   int* rot_d = nullptr;
   int* rot_h = nullptr;  // pinned
+  T* R_d = nullptr;      // npairs * 64 * 64 pivot rotations
+  int* act_d = nullptr;  // per pair: pivot needed work this round
   std::vector<T> lam_host;
 
   ~PsdBatch() {
     cudaFree(small_d); cudaFree(lam_small_d); cudaFree(fail_d); cudaFree(A_d); cudaFree(V_d); cudaFree(cs_d);
-    cudaFree(fro_d); cudaFree(thr_d); cudaFree(lam_large_d); cudaFree(rot_d);
+    cudaFree(fro_d); cudaFree(thr_d); cudaFree(lam_large_d); cudaFree(rot_d); cudaFree(R_d); cudaFree(act_d);
     if (rot_h) cudaFreeHost(rot_h);
   }
   bool empty() const { return small_h.empty() && large_h.empty(); }
@@ -450,8 +663,15 @@ struct PsdBatch {
       ck(cudaMalloc(&lam_large_d, large_h.size() * sizeof(T)), "cudaMalloc lam");
       ck(cudaMalloc(&rot_d, sizeof(int)), "cudaMalloc rot");
       ck(cudaMallocHost(&rot_h, sizeof(int)), "cudaMallocHost rot");
-      const int npairs = ((large_maxN + 1) & ~1) / 2;
-      ck(cudaFuncSetAttribute(psd_large_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * npairs * sizeof(T))), "smem attr rows");
+      int Nb = (large_maxN + kBjB - 1) / kBjB;
+      if (Nb & 1) ++Nb;
+      ck(cudaMalloc(&R_d, (size_t)(Nb / 2) * kBjP * kBjP * sizeof(T)), "cudaMalloc R");
+      ck(cudaMalloc(&act_d, (size_t)(Nb / 2) * sizeof(int)), "cudaMalloc act");
+      const int smem_pivot = (int)((2 * (size_t)(kBjP + 1) * kBjP + kBjP + 2) * sizeof(T));
+      const int smem_upd = (int)(((size_t)(kBjP + 1) * kBjP + (size_t)kBjP * kBjP) * sizeof(T));
+      ck(cudaFuncSetAttribute(bj_pivot_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pivot), "smem attr pivot");
+      ck(cudaFuncSetAttribute(bj_cols_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_upd), "smem attr cols");
+      ck(cudaFuncSetAttribute(bj_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_upd), "smem attr rows");
     }
     ck(cudaStreamSynchronize(st), "sync");
   }
@@ -461,21 +681,25 @@ struct PsdBatch {
   }
   void reset_warm_start() {}
 
-  // eigen-decompose one large cone into A_d (diagonal = eigenvalues) and V_d
+  // eigen-decompose one large cone into A_d (diagonal = eigenvalues) and V_d (block Jacobi)
   void large_eig(const PsdConeDesc& d, const T* ws, cudaStream_t st, int max_sweeps, long long& launches) {
     const int N = d.N;
-    const int Ne = (N + 1) & ~1, npairs = Ne / 2;
+    int Nb = (N + kBjB - 1) / kBjB;
+    if (Nb & 1) ++Nb;                                 // even number of blocks (zero padding decouples)
+    const int npairs = Nb / 2;
     const int g = (int)std::min<long long>(((long long)N * N + kBlock - 1) / kBlock, kMaxGrid);
     psd_large_load_kernel<T><<<g, kBlock, 0, st>>>(d, ws, A_d, V_d, fro_d);
     psd_large_thr_kernel<T><<<1, 32, 0, st>>>(fro_d, g, thr_d, rot_d);
     launches += 2;
+    const size_t smem_pivot = (2 * (size_t)(kBjP + 1) * kBjP + kBjP + 2) * sizeof(T);
+    const size_t smem_upd = ((size_t)(kBjP + 1) * kBjP + (size_t)kBjP * kBjP) * sizeof(T);
+    const int tiles = (N + kBjP - 1) / kBjP;
     bool converged = false;
     for (int sweep = 0; sweep < max_sweeps && !converged; ++sweep) {
-      for (int r = 0; r < Ne - 1; ++r) {
-        psd_large_params_kernel<T><<<(npairs + 127) / 128, 128, 0, st>>>(N, r, A_d, thr_d, cs_d, rot_d);
-        dim3 gc((N + kBlock - 1) / kBlock, npairs);
-        psd_large_cols_kernel<T><<<gc, kBlock, 0, st>>>(N, r, A_d, V_d, cs_d);
-        psd_large_rows_kernel<T><<<(N + kBlock - 1) / kBlock, kBlock, 2 * npairs * sizeof(T), st>>>(N, r, A_d, cs_d);
+      for (int r = 0; r < Nb - 1; ++r) {
+        bj_pivot_kernel<T><<<npairs, kBlock, smem_pivot, st>>>(N, Nb, r, A_d, thr_d, R_d, act_d, rot_d, 2);
+        bj_cols_kernel<T><<<dim3(tiles, npairs, 2), kBlock, smem_upd, st>>>(N, Nb, r, A_d, V_d, R_d, act_d);
+        bj_rows_kernel<T><<<dim3(tiles, npairs, 1), kBlock, smem_upd, st>>>(N, Nb, r, A_d, R_d, act_d);
         launches += 3;
       }
       ck(cudaMemcpyAsync(rot_h, rot_d, sizeof(int), cudaMemcpyDeviceToHost, st), "copy rot");
@@ -483,8 +707,8 @@ struct PsdBatch {
       ck(cudaStreamSynchronize(st), "sync");
       if (*rot_h == 0) converged = true;
     }
-    ck(cudaGetLastError(), "psd large kernels");
-    if (!converged) throw PsdError{"Jacobi eigensolver did not converge within psd_max_sweeps"};
+    ck(cudaGetLastError(), "psd block-Jacobi kernels");
+    if (!converged) throw PsdError{"block Jacobi eigensolver did not converge within psd_max_sweeps"};
   }
 
   // s[cone rows] = Pi_PSD(ws[cone rows]) for every PSD cone
