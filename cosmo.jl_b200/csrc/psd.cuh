@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(kBlock) bj_pivot_kernel(int N, int Nb, int r, 
     if (gi < N && gj < N) v = A[gi + (long long)gj * N];
     Sa[i + j * ld] = v;
     Sv[i + j * ld] = (i == j) ? T(1) : T(0);
-    if (i != j && tabs(v) > thr) any_big = 1;
+    if (i != j && tabs(v) > T(8) * thr) any_big = 1;   // activity threshold above the GEMM-update noise floor
   }
   __syncthreads();
   if (!any_big) {
