@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(kBlock) bj_pivot_kernel(int N, int Nb, int r, 
   T* Sa = reinterpret_cast<T*>(smem_raw);
   T* Sv = Sa + ld * P;
   T* cs = Sv + ld * P;
-  __shared__ int any_big, rot_flag;
+  __shared__ int any_big, rot_flag, round_rot[2];
   const int k = blockIdx.x;
   int I, J;
   rr_pair(Nb, r, k, I, J);
@@ -396,6 +396,9 @@ __global__ void __launch_bounds__(kBlock) bj_pivot_kernel(int N, int Nb, int r, 
     if (threadIdx.x == 0) rot_flag = 0;
     __syncthreads();
     for (int rr = 0; rr < P - 1; ++rr) {
+      const int f = rr & 1;   // alternating flag: its reset two rounds later cannot race with this round's reads
+      if (threadIdx.x == 0) round_rot[f] = 0;
+      __syncthreads();
       for (int kk = threadIdx.x; kk < npairs; kk += blockDim.x) {
         int p, q;
         rr_pair(P, rr, kk, p, q);
@@ -404,11 +407,13 @@ __global__ void __launch_bounds__(kBlock) bj_pivot_kernel(int N, int Nb, int r, 
         if (tabs(apq) > thr) {
           sym_schur(Sa[p + p * ld], Sa[q + q * ld], apq, c, sn);
           rot_flag = 1;
+          round_rot[f] = 1;
         }
         cs[2 * kk] = c;
         cs[2 * kk + 1] = sn;
       }
       __syncthreads();
+      if (!round_rot[f]) continue;   // nothing to rotate in this round (block-uniform)
       for (int e = threadIdx.x; e < npairs * P; e += blockDim.x) {
         const int kk = e / P, i = e % P;
         const T sn = cs[2 * kk + 1];
@@ -697,7 +702,7 @@ struct PsdBatch {
     bool converged = false;
     for (int sweep = 0; sweep < max_sweeps && !converged; ++sweep) {
       for (int r = 0; r < Nb - 1; ++r) {
-        bj_pivot_kernel<T><<<npairs, kBlock, smem_pivot, st>>>(N, Nb, r, A_d, thr_d, R_d, act_d, rot_d, 2);
+        bj_pivot_kernel<T><<<npairs, kBlock, smem_pivot, st>>>(N, Nb, r, A_d, thr_d, R_d, act_d, rot_d, 1);
         bj_cols_kernel<T><<<dim3(tiles, npairs, 2), kBlock, smem_upd, st>>>(N, Nb, r, A_d, V_d, R_d, act_d);
         bj_rows_kernel<T><<<dim3(tiles, npairs, 1), kBlock, smem_upd, st>>>(N, Nb, r, A_d, R_d, act_d);
         launches += 3;
