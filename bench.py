@@ -282,11 +282,11 @@ def main():
                                 "model upload (setup!) excluded like in the reference's iter_time"},
                 "gpu_launches": int(out.kernel_launches),
                 "clocks": clocks,
-                "roofline": {"bound": "hbm", "kernel": "spmv_kernel<double,32,EpiScale> (t = rho.*(A u))",
+                "roofline": {"bound": "hbm", "kernel": "spmv_win_kernel<double,EpiScale> (t = rho.*(A u), x staged in smem by TMA bulk copy)",
                              "achieved": ach_A, "peak": peak, "unit": "GB/s", "frac": ach_A / peak,
                              "traffic": traffic, "peak_source": peak_src, "ms_per_launch": ms_A,
                              "algorithmic_bytes_per_launch": bytes_A,
-                             "other": {"kernel": "spmv_kernel<double,32,EpiKktOp> (c = A't + P u + sigma u, dot)",
+                             "other": {"kernel": "spmv_kernel<P> + spmv_win_kernel<double,EpiKktOp> (c = A't + P u + sigma u, dot u'c)",
                                        "achieved": ach_At, "frac": ach_At / peak, "ms_per_launch": ms_At,
                                        "algorithmic_bytes_per_launch": bytes_At}}}
         if not a.no_cpu_baseline and world == 1:
