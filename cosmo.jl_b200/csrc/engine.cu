@@ -226,6 +226,7 @@ class Engine : public EngineBase {
   DevBuf<unsigned> chunk_ticket_;
   int num_sms_ = 148;
   bool use_windows_ = true;
+  int win_group_ = 16;
   DevBuf<T> sc_;       // device scalars
   DevBuf<int> isc_;
   DevBuf<T> partials_;
@@ -341,19 +342,24 @@ struct WinGroupScratch {
 
 template <typename T>
 static void win_fill_segment(const int* cols, const double* vals, const int* idx, int k, int wbase, long long start,
-                             unsigned short* wc, T* wv, WinGroupScratch& S) {
+                             unsigned short* wc, T* wv, WinGroupScratch& S, int GL) {
+  // GL = lanes that share one shared-memory wavefront (16: half-warp, 8: quarter-warp)
   const int kpad = (k + 7) & ~7;
   if (kpad == 0) return;
   const int lanes_total = kpad / 8;
   const int steps = (lanes_total + 31) / 32;
-  const int G = steps * 16;
+  const int SUB = 32 / GL;              // lane groups per step
+  const int GPS = SUB * 8;              // (lane group, slot) groups per step
+  const int G = steps * GPS;
   S.cap.assign(G, 0); S.load.assign(G, 0); S.used.assign(G, 0);
   if ((int)S.members.size() < G) S.members.resize(G);
   for (int g = 0; g < G; ++g) S.members[g].clear();
   for (int st = 0; st < steps; ++st) {
     const int ls = std::min(32, lanes_total - 32 * st);
-    const int cap0 = std::min(16, ls), cap1 = ls - cap0;
-    for (int i = 0; i < 8; ++i) { S.cap[st * 16 + i] = cap0; S.cap[st * 16 + 8 + i] = cap1; }
+    for (int h = 0; h < SUB; ++h) {
+      const int cap = std::max(0, std::min(GL, ls - GL * h));
+      for (int i = 0; i < 8; ++i) S.cap[st * GPS + h * 8 + i] = cap;
+    }
   }
   for (int r = 0; r < 16; ++r) S.bucket[r].clear();
   for (int e = 0; e < k; ++e) S.bucket[(cols[idx[e]] - wbase) & 15].push_back(idx[e]);
@@ -369,7 +375,7 @@ static void win_fill_segment(const int* cols, const double* vals, const int* idx
         const int g = (cursor + t) % G;
         const int free_slots = S.cap[g] - S.load[g];
         if (free_slots <= 0) continue;
-        if (!((S.used[g] >> r) & 1)) { if (free_slots > best_free) { best = g; best_free = free_slots; if (free_slots == 16) break; } }
+        if (!((S.used[g] >> r) & 1)) { if (free_slots > best_free) { best = g; best_free = free_slots; if (free_slots == GL) break; } }
         else if (free_slots > fb_free) { fallback = g; fb_free = free_slots; }
       }
       const int g = best >= 0 ? best : fallback;
@@ -380,10 +386,10 @@ static void win_fill_segment(const int* cols, const double* vals, const int* idx
     }
   }
   for (int g = 0; g < G; ++g) {
-    const int st = g / 16, h = (g % 16) / 8, i = g % 8;
+    const int st = g / GPS, h = (g % GPS) / 8, i = g % 8;
     const int nl = S.cap[g];
     for (int t = 0; t < nl; ++t) {
-      const long long pos = start + (long long)st * 256 + (long long)(16 * h + t) * 8 + i;
+      const long long pos = start + (long long)st * 256 + (long long)(GL * h + t) * 8 + i;
       if (t < S.load[g]) {
         const int e = S.members[g][t];
         wc[pos] = (unsigned short)(cols[e] - wbase);
@@ -459,7 +465,7 @@ void Engine<T>::build_windows(DevCsr<T>& dst, const HostCsr& h) {
       for (int k = h.rowptr[r]; k < h.rowptr[r + 1]; ++k) seg[h.col[k] / W].push_back(k);
       for (int w = 0; w < nwin; ++w)
         win_fill_segment<T>(h.col.data(), h.val.data(), seg[w].data(), (int)seg[w].size(), w * W,
-                            rp[(size_t)w * (nr + 1) + r], wc.data(), wv.data(), S);
+                            rp[(size_t)w * (nr + 1) + r], wc.data(), wv.data(), S, win_group_);
     }
   });
   // contiguous row chunks per CTA, balanced by padded nnz (+ per-row overhead)
@@ -548,6 +554,8 @@ Engine<T>::Engine(const cosmo_b200_problem& p, const cosmo_b200_settings& st) : 
   {
     const char* e = getenv("COSMO_B200_NO_WINDOWS");
     use_windows_ = !(e && e[0] == '1');
+    const char* g = getenv("COSMO_B200_WIN_GROUP");
+    if (g && atoi(g) == 8) win_group_ = 8;
   }
   CUDA_TRY(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&ev0_));
