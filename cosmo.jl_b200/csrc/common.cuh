@@ -46,14 +46,18 @@ __device__ __forceinline__ void load4_stream(const float* p, float (&v)[4]) {
 __device__ __forceinline__ int4 load4_stream(const int* p) {
   return __ldcs(reinterpret_cast<const int4*>(p));
 }
-__device__ __forceinline__ void load8_stream(const double* p, double (&v)[8]) {
-  const double2* q = reinterpret_cast<const double2*>(p);
-  double2 a = __ldcs(q), b = __ldcs(q + 1), c = __ldcs(q + 2), d = __ldcs(q + 3);
+// One lane's 8 values of a windowed row-segment step.  Values are stored "instruction-coalesced":
+// the k-th 16-byte load of lane l sits at base + k * (EPL * L) + l * EPL  (EPL = elements per 16 B,
+// L = active lanes of the step), so every load instruction of the warp covers one contiguous run of
+// L * 16 bytes -- each 32-byte sector is requested exactly once.
+__device__ __forceinline__ void load8_coalesced(const double* base, int L, int lane, double (&v)[8]) {
+  const double2* q = reinterpret_cast<const double2*>(base) + lane;
+  const double2 a = __ldcs(q), b = __ldcs(q + L), c = __ldcs(q + 2 * L), d = __ldcs(q + 3 * L);
   v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
 }
-__device__ __forceinline__ void load8_stream(const float* p, float (&v)[8]) {
-  const float4* q = reinterpret_cast<const float4*>(p);
-  float4 a = __ldcs(q), b = __ldcs(q + 1);
+__device__ __forceinline__ void load8_coalesced(const float* base, int L, int lane, float (&v)[8]) {
+  const float4* q = reinterpret_cast<const float4*>(base) + lane;
+  const float4 a = __ldcs(q), b = __ldcs(q + L);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 

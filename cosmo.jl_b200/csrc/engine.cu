@@ -389,17 +389,23 @@ static void win_fill_segment(const int* cols, const double* vals, const int* idx
     const int st = g / GPS, h = (g % GPS) / 8, i = g % 8;
     const int nl = S.cap[g];
     for (int t = 0; t < nl; ++t) {
-      const long long pos = start + (long long)st * 256 + (long long)(GL * h + t) * 8 + i;
+      // column index: lane-contiguous (one 16-byte load per lane); value: instruction-coalesced
+      // (load k of lane l at k * EPL * L + l * EPL, see load8_coalesced)
+      const int lane = GL * h + t;
+      const int ls = std::min(32, lanes_total - 32 * st);
+      constexpr int EPL = 16 / (int)sizeof(T);
+      const long long pos_c = start + (long long)st * 256 + (long long)lane * 8 + i;
+      const long long pos_v = start + (long long)st * 256 + (long long)(i / EPL) * (EPL * ls) + (long long)lane * EPL + (i % EPL);
       if (t < S.load[g]) {
         const int e = S.members[g][t];
-        wc[pos] = (unsigned short)(cols[e] - wbase);
-        wv[pos] = (T)vals[e];
+        wc[pos_c] = (unsigned short)(cols[e] - wbase);
+        wv[pos_v] = (T)vals[e];
       } else {   // padding: zero value on a bank this group does not use yet
         int r0 = 0;
         while (r0 < 15 && ((S.used[g] >> r0) & 1)) ++r0;
         S.used[g] |= (unsigned short)(1u << r0);
-        wc[pos] = (unsigned short)r0;
-        wv[pos] = T(0);
+        wc[pos_c] = (unsigned short)r0;
+        wv[pos_v] = T(0);
       }
     }
   }
