@@ -8,3 +8,4 @@ from .model import (Box, Constraint, Model, Nonnegatives, PsdCone, PsdConeTriang
                     SecondOrderCone, Settings, ZeroSet, assemble, optimize, ruiz_equilibrate)
 from . import problems  # noqa: F401
 from . import sharding  # noqa: F401,E402
+from . import chordal  # noqa: F401,E402

@@ -1,0 +1,311 @@
+"""Host-side chordal decomposition -- the producer of the clique batch.
+
+Stays on the host like the reference's `src/chordal_decomposition/` (north-star);
+what the GPU consumes is only the augmented `(P', q', A', b')`, the cone list with
+one `PsdConeTriangle` per clique, and the row map used to sum the blocks back.
+
+Restated (not ported) from the reference:
+  * aggregate sparsity pattern of a PSD cone   chordal_decomposition.jl:100-115
+  * chordal extension + elimination tree        trees.jl:634-642 (the reference calls QDLDL with an AMD
+    ordering; neither is available here, so a minimum-degree elimination with explicit fill is used --
+    any perfect elimination ordering gives a valid decomposition, only the clique set differs)
+  * supernodes / cliques / clique tree          trees.jl:390-513 (Pothen-Sun rule: v joins a child's
+    supernode iff |hadj(child)| = |hadj(v)| + 1)
+  * merge strategy                              NoMerge, or ParentChildMerge(t_fill, t_size)
+    (clique_merging.jl:278-285, 641-648); the default CliqueGraphMerge is not restated
+  * compact ("clique tree based") augmentation  transformations.jl:152-374: every clique becomes a
+    PsdConeTriangle block; an entry (i,j) inside the separator of a clique gets a new variable with +1 in
+    the clique's row and -1 in the parent's row of the same (i,j)
+  * reverse_decomposition!                       chordal_decomposition.jl:129-213 (x truncated, s = sum of
+    blocks, mu = block value)
+"""
+from __future__ import annotations
+
+import heapq
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import model as M
+
+
+def svec_index(i: int, j: int) -> int:
+    """position of (i,j), i<=j (0-based), in the column-major upper triangle (convexset.jl:432-442)"""
+    return j * (j + 1) // 2 + i
+
+
+def svec_to_ij(k: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """inverse of svec_index (svec_to_mat, trees.jl:697-719)"""
+    k = np.asarray(k, dtype=np.int64)
+    j = ((np.sqrt(8.0 * k + 1.0) - 1.0) / 2.0).astype(np.int64)
+    j = np.where((j + 1) * (j + 2) // 2 <= k, j + 1, j)
+    j = np.where(j * (j + 1) // 2 > k, j - 1, j)
+    return k - j * (j + 1) // 2, j
+
+
+@dataclass
+class CliqueTree:
+    cliques: List[np.ndarray]          # sorted vertex lists
+    parent: List[int]                  # -1 for roots
+    sep: List[np.ndarray]              # clique ∩ parent clique (sorted)
+    order: np.ndarray                  # elimination order used
+
+
+def chordal_cliques(nv: int, rows: np.ndarray, cols: np.ndarray) -> CliqueTree:
+    """Minimum-degree elimination with explicit fill -> maximal cliques and their tree."""
+    adj: List[set] = [set() for _ in range(nv)]
+    for a, b in zip(rows.tolist(), cols.tolist()):
+        if a != b:
+            adj[a].add(b)
+            adj[b].add(a)
+    heap = [(len(adj[v]), v) for v in range(nv)]
+    heapq.heapify(heap)
+    done = np.zeros(nv, dtype=bool)
+    pos = np.empty(nv, dtype=np.int64)
+    order: List[int] = []
+    hadj: List[Optional[List[int]]] = [None] * nv
+    while heap:
+        d, v = heapq.heappop(heap)
+        if done[v] or d != len(adj[v]):
+            continue
+        done[v] = True
+        pos[v] = len(order)
+        order.append(v)
+        nb = list(adj[v])
+        hadj[v] = nb
+        for a in nb:
+            adj[a].discard(v)
+        for ia in range(len(nb)):      # fill: the higher neighbourhood becomes a clique
+            a = nb[ia]
+            sa = adj[a]
+            for ib in range(ia + 1, len(nb)):
+                b = nb[ib]
+                if b not in sa:
+                    sa.add(b)
+                    adj[b].add(a)
+        for a in nb:
+            heapq.heappush(heap, (len(adj[a]), a))
+        adj[v] = set()
+    # elimination tree: parent = earliest-eliminated higher neighbour
+    par = np.full(nv, -1, dtype=np.int64)
+    for v in range(nv):
+        if hadj[v]:
+            par[v] = min(hadj[v], key=lambda u: pos[u])
+    # Pothen-Sun supernodes
+    absorbing_child = np.full(nv, -1, dtype=np.int64)
+    for u in order:
+        p = par[u]
+        if p >= 0 and absorbing_child[p] < 0 and len(hadj[u]) == len(hadj[p]) + 1:
+            absorbing_child[p] = u
+    snode = np.full(nv, -1, dtype=np.int64)
+    lowest: List[int] = []
+    top: List[int] = []
+    for v in order:
+        c = absorbing_child[v]
+        if c >= 0:
+            snode[v] = snode[c]
+            top[snode[v]] = v
+        else:
+            snode[v] = len(lowest)
+            lowest.append(v)
+            top.append(v)
+    cliques, parent, seps = [], [], []
+    for k, v in enumerate(lowest):
+        cl = np.array(sorted([v] + list(hadj[v])), dtype=np.int64)
+        cliques.append(cl)
+        t = top[k]
+        p = par[t]
+        parent.append(int(snode[p]) if p >= 0 else -1)
+    for k, cl in enumerate(cliques):
+        if parent[k] < 0:
+            seps.append(np.zeros(0, dtype=np.int64))
+        else:
+            seps.append(np.intersect1d(cl, cliques[parent[k]]))
+    return CliqueTree(cliques, parent, seps, np.array(order, dtype=np.int64))
+
+
+def parent_child_merge(tree: CliqueTree, t_fill: int = 8, t_size: int = 8) -> CliqueTree:
+    """ParentChildMerge (clique_merging.jl:278-285, 641-648): children are merged into their parent
+    when the fill-in (|C_par|-|sep|)(|C|-|sep|) <= t_fill or both supernodes are small."""
+    n = len(tree.cliques)
+    cl = [set(c.tolist()) for c in tree.cliques]
+    parent = list(tree.parent)
+    alive = [True] * n
+    children: List[List[int]] = [[] for _ in range(n)]
+    for k, p in enumerate(parent):
+        if p >= 0:
+            children[p].append(k)
+    # visit children before parents
+    depth = [0] * n
+    for k in range(n):
+        d, p = 0, parent[k]
+        while p >= 0:
+            d += 1
+            p = parent[p]
+        depth[k] = d
+    for k in sorted(range(n), key=lambda i: -depth[i]):
+        p = parent[k]
+        if p < 0 or not alive[k]:
+            continue
+        while not alive[p]:
+            p = parent[p]
+        sep = len(cl[k] & cl[p])
+        fill = (len(cl[p]) - sep) * (len(cl[k]) - sep)
+        if fill <= t_fill or max(len(cl[k]) - sep, len(cl[p]) - sep) <= t_size:
+            cl[p] |= cl[k]
+            alive[k] = False
+            for ch in children[k]:
+                parent[ch] = p
+                children[p].append(ch)
+    idx = {k: i for i, k in enumerate([k for k in range(n) if alive[k]])}
+    cliques, par2, seps = [], [], []
+    for k in range(n):
+        if not alive[k]:
+            continue
+        p = parent[k]
+        while p >= 0 and not alive[p]:
+            p = parent[p]
+        c = np.array(sorted(cl[k]), dtype=np.int64)
+        cliques.append(c)
+        par2.append(idx[p] if p >= 0 else -1)
+    for k, c in enumerate(cliques):
+        seps.append(np.intersect1d(c, cliques[par2[k]]) if par2[k] >= 0 else np.zeros(0, dtype=np.int64))
+    return CliqueTree(cliques, par2, seps, tree.order)
+
+
+@dataclass
+class DecompositionInfo:
+    n_orig: int
+    m_orig: int
+    sets_orig: list
+    # for every decomposed cone: list of (new_row_start, clique vertices)
+    blocks: Dict[int, List[Tuple[int, np.ndarray]]] = field(default_factory=dict)
+    row_map_plain: List[Tuple[int, int, int]] = field(default_factory=list)   # (old_start, new_start, dim)
+    cone_offsets: Dict[int, int] = field(default_factory=dict)
+    num_overlaps: int = 0
+    clique_sizes: List[int] = field(default_factory=list)
+
+
+def decompose(P, q, A, b, sets, merge: str = "parent_child", min_dim: int = 3):
+    """chordal_decomposition!(ws) for PsdConeTriangle cones (compact transformation).
+    Returns (P', q', A', b', sets', info)."""
+    A = sp.csr_matrix(A)
+    b = np.asarray(b, dtype=np.float64)
+    m, n = A.shape
+    info = DecompositionInfo(n, m, list(sets))
+    rows_new: List[np.ndarray] = []
+    cols_new: List[np.ndarray] = []
+    vals_new: List[np.ndarray] = []
+    b_new: List[np.ndarray] = []
+    sets_new = []
+    row_ptr = 0
+    n_new = n
+    off = 0
+    Acoo_by_row = A  # csr
+    for k, S in enumerate(sets):
+        dim = S.dim
+        decomposable = isinstance(S, M.PsdConeTriangle) and S.sqrt_dim >= min_dim
+        if decomposable:
+            N = S.sqrt_dim
+            sub = Acoo_by_row[off:off + dim]
+            nz_rows = np.unique(np.concatenate([np.nonzero(np.diff(sub.indptr))[0], np.nonzero(b[off:off + dim])[0]]))
+            ii, jj = svec_to_ij(nz_rows)
+            diag_rows = np.arange(N, dtype=np.int64) * (np.arange(N, dtype=np.int64) + 1) // 2 + np.arange(N)
+            if len(np.union1d(nz_rows, diag_rows)) >= dim:   # dense pattern: keep the cone (chordal_decomposition.jl:53-60)
+                decomposable = False
+        if not decomposable:
+            sub = Acoo_by_row[off:off + dim].tocoo()
+            rows_new.append(sub.row + row_ptr)
+            cols_new.append(sub.col)
+            vals_new.append(sub.data)
+            b_new.append(b[off:off + dim])
+            sets_new.append(S)
+            info.row_map_plain.append((off, row_ptr, dim))
+            row_ptr += dim
+            off += dim
+            continue
+        tree = chordal_cliques(N, ii, jj)
+        if merge == "parent_child":
+            tree = parent_child_merge(tree)
+        # row offsets of the clique blocks
+        starts = []
+        for c in tree.cliques:
+            starts.append(row_ptr)
+            nc = len(c)
+            row_ptr += nc * (nc + 1) // 2
+        info.cone_offsets[k] = off
+        info.blocks[k] = [(starts[t], tree.cliques[t]) for t in range(len(tree.cliques))]
+        info.clique_sizes += [len(c) for c in tree.cliques]
+        # owner (clique, local row) of every pattern entry; overlaps get +1/-1 columns
+        owner: Dict[int, int] = {}
+        for t, c in enumerate(tree.cliques):
+            nc = len(c)
+            in_sep = np.isin(c, tree.sep[t])
+            loc = {int(v): a for a, v in enumerate(c)}
+            par_t = tree.parent[t]
+            par_loc = {int(v): a for a, v in enumerate(tree.cliques[par_t])} if par_t >= 0 else None
+            ov_rows, ov_cols, ov_vals = [], [], []
+            for bj in range(nc):
+                for ai in range(bj + 1):
+                    gi, gj = int(c[ai]), int(c[bj])
+                    new_row = starts[t] + svec_index(ai, bj)
+                    if in_sep[ai] and in_sep[bj]:
+                        pa, pb = par_loc[gi], par_loc[gj]
+                        if pa > pb:
+                            pa, pb = pb, pa
+                        ov_rows += [new_row, starts[par_t] + svec_index(pa, pb)]
+                        ov_cols += [n_new, n_new]
+                        ov_vals += [1.0, -1.0]
+                        n_new += 1
+                    else:
+                        owner[svec_index(gi, gj)] = new_row
+            if ov_rows:
+                rows_new.append(np.array(ov_rows, dtype=np.int64))
+                cols_new.append(np.array(ov_cols, dtype=np.int64))
+                vals_new.append(np.array(ov_vals))
+            sets_new.append(M.PsdConeTriangle(nc * (nc + 1) // 2))
+        sub = Acoo_by_row[off:off + dim].tocoo()
+        mapped = np.array([owner[int(r)] for r in sub.row], dtype=np.int64) if sub.nnz else np.zeros(0, dtype=np.int64)
+        rows_new.append(mapped)
+        cols_new.append(sub.col)
+        vals_new.append(sub.data)
+        bseg = np.zeros(row_ptr - starts[0])
+        nzb = np.nonzero(b[off:off + dim])[0]
+        for r in nzb:
+            bseg[owner[int(r)] - starts[0]] = b[off + r]
+        b_new.append(bseg)
+        off += dim
+    info.num_overlaps = n_new - n
+    rows_c = np.concatenate(rows_new) if rows_new else np.zeros(0, dtype=np.int64)
+    cols_c = np.concatenate(cols_new) if cols_new else np.zeros(0, dtype=np.int64)
+    vals_c = np.concatenate(vals_new) if vals_new else np.zeros(0)
+    A2 = sp.csc_matrix((vals_c, (rows_c, cols_c)), shape=(row_ptr, n_new))
+    b2 = np.concatenate(b_new) if b_new else np.zeros(0)
+    P2 = sp.block_diag([sp.csc_matrix(P), sp.csc_matrix((n_new - n, n_new - n))], format="csc")
+    q2 = np.concatenate([np.asarray(q, dtype=np.float64), np.zeros(n_new - n)])
+    return P2, q2, A2, b2, sets_new, info
+
+
+def reverse(info: DecompositionInfo, x2, s2, mu2):
+    """reverse_decomposition! (chordal_decomposition.jl:129-213): x = x'[1:n]; s = sum of clique blocks;
+    mu = the clique block's value (overlaps carry equal values at optimality)."""
+    x = np.asarray(x2)[:info.n_orig].copy()
+    s = np.zeros(info.m_orig)
+    mu = np.zeros(info.m_orig)
+    for old, new, dim in info.row_map_plain:
+        s[old:old + dim] = s2[new:new + dim]
+        mu[old:old + dim] = mu2[new:new + dim]
+    for k, blocks in info.blocks.items():
+        off = info.cone_offsets[k]
+        for start, c in blocks:
+            nc = len(c)
+            for bj in range(nc):
+                gj = int(c[bj])
+                gi = c[:bj + 1]
+                orig = off + gj * (gj + 1) // 2 + gi
+                seg = slice(start + svec_index(0, bj), start + svec_index(bj, bj) + 1)
+                s[orig] += s2[seg]
+                mu[orig] = mu2[seg]
+    return x, s, mu

@@ -134,3 +134,39 @@ def to_oracle_cones(sets):
         else:
             raise TypeError(S)
     return out
+
+
+def banded_random_graph(nv=10_000, mean_degree=3.0, bandwidth=20, seed=1):
+    """BASELINE config C5 graph: random sparse graph with mean degree ~3 whose edges join vertices at
+    index distance <= `bandwidth` (bounded treewidth => the chordal extension has small cliques, the
+    regime chordal decomposition targets: many small PSD blocks instead of one huge one).
+    Integer weights U{1..10}.  Returns (rows, cols, weights) with rows < cols, duplicate-free."""
+    rng = np.random.default_rng(seed)
+    ne = int(round(nv * mean_degree / 2.0 * 1.15))
+    i = rng.integers(0, nv, size=ne)
+    j = i + rng.integers(1, bandwidth + 1, size=ne)
+    keep = j < nv
+    i, j = i[keep], j[keep]
+    key = np.unique(i.astype(np.int64) * nv + j)
+    key = key[: int(round(nv * mean_degree / 2.0))] if len(key) > nv * mean_degree / 2.0 else key
+    i, j = key // nv, key % nv
+    w = rng.integers(1, 11, size=len(i)).astype(np.float64)
+    return i, j, w
+
+
+def maxcut_dual_sdp(nv, rows, cols, weights):
+    """Dual MAXCUT SDP (examples/maxcut.jl:73-77): min sum(gamma) s.t. diag(gamma) - L/4 = S, S PSD,
+    as a PsdConeTriangle constraint on svec(S).  Model form A x + s = b with x = gamma."""
+    W = sp.coo_matrix((weights, (rows, cols)), shape=(nv, nv))
+    deg = np.asarray((W + W.T).sum(axis=1)).ravel()
+    d = nv * (nv + 1) // 2
+    diag_pos = np.arange(nv, dtype=np.int64) * (np.arange(nv, dtype=np.int64) + 1) // 2 + np.arange(nv)
+    # constraint A_c x + b_c in K with A_c = selector of the diagonal, b_c = svec(-L/4)
+    A_c = sp.csr_matrix((np.ones(nv), (diag_pos, np.arange(nv))), shape=(d, nv))
+    b_c = np.zeros(d)
+    b_c[diag_pos] = -deg / 4.0
+    lo, hi = np.minimum(rows, cols).astype(np.int64), np.maximum(rows, cols).astype(np.int64)
+    b_c[hi * (hi + 1) // 2 + lo] = np.sqrt(2.0) * weights / 4.0      # -(-w_ij)/4, off-diagonals scaled by sqrt 2
+    P = sp.csc_matrix((nv, nv))
+    q = np.ones(nv)
+    return P, q, (-A_c).tocsc(), b_c, [M.PsdConeTriangle(d)]

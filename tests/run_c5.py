@@ -1,0 +1,68 @@
+"""BASELINE config C5: dual MAXCUT SDP on a random sparse graph |V| = 10k, host-side chordal
+decomposition, clique PSD cones sharded over the available GPUs.  Prints one JSON line (rank 0)."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import cosmo_b200
+from cosmo_b200 import chordal, sharding
+
+
+def main():
+    nv = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000
+    iters = int(sys.argv[2]) if len(sys.argv) > 2 else 200
+    merge = sys.argv[3] if len(sys.argv) > 3 else "parent_child"
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    t0 = time.time()
+    rows, cols, w = cosmo_b200.problems.banded_random_graph(nv, 3.0, 20, seed=1)
+    P, q, A, b, sets = cosmo_b200.problems.maxcut_dual_sdp(nv, rows, cols, w)
+    P2, q2, A2, b2, sets2, info = chordal.decompose(P, q, A, b, sets, merge=merge)
+    graph_time = time.time() - t0
+    cs = np.array(info.clique_sizes)
+    st = cosmo_b200.Settings(scaling=0, adaptive_rho=False, max_iter=iters, eps_abs=0.0, eps_rel=0.0)
+    sh = sharding.make_shard(P2, q2, A2, b2, sets2, rank, world)
+    eng = sharding.create_engine(sh, st, device=local_rank, dist=dist)
+    eng.solve()          # warm-up (same number of iterations)
+    eng.reset()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    out = eng.solve()
+    dev = out.times["iter_time_device"]
+    if dist is not None:
+        t = torch.tensor([dev], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev = float(t.item())
+    line = {"workload": "C5 MAXCUT dual SDP |V|=%d |E|=%d, chordal decomposition (%s): %d cliques, sizes min/median/max %d/%d/%d, "
+                        "sum|c|^3=%.3g, n'=%d m'=%d" % (nv, len(rows), merge, len(cs), cs.min(), int(np.median(cs)), cs.max(),
+                                                       float((cs.astype(float) ** 3).sum()), A2.shape[1], A2.shape[0]),
+            "n_gpus": world, "iters": iters, "iter_per_s": iters / dev, "ms_per_iter": 1e3 * dev / iters,
+            "cg_iters_per_admm_iter": out.kkt_inner_iterations / max(out.iter, 1), "graph_time_s": graph_time,
+            "kernel_launches": int(out.kernel_launches)}
+    if rank == 0 and world == 1 and "--cpu" in sys.argv:
+        from oracle import cosmo_oracle as O
+        cones = cosmo_b200.problems.to_oracle_cones(sets2)
+        k = min(iters, 20)
+        t0 = time.time()
+        O.solve(P2, q2, A2, b2, cones, O.Settings(kkt_solver="cg", scaling=0, adaptive_rho=False, max_iter=k, eps_abs=0.0, eps_rel=0.0))
+        line["cpu_oracle_iter_per_s"] = k / (time.time() - t0)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
