@@ -171,7 +171,10 @@ class Engine : public EngineBase {
  public:
   Engine(const cosmo_b200_problem& p, const cosmo_b200_settings& st);
   ~Engine() override;
-  void update_settings(const cosmo_b200_settings& st) override { st_ = st; }
+  void update_settings(const cosmo_b200_settings& st) override {
+    if (st.sigma != st_.sigma) destroy_cg_graphs();   // sigma is baked into the captured kernel arguments
+    st_ = st;
+  }
   void warm_start(const void* x, const void* s, const void* mu) override;
   void update_qb(const void* q, const void* b) override;
   void update_rho(const void* rho_vec, double rho) override;
@@ -218,6 +221,12 @@ class Engine : public EngineBase {
   DevBuf<T> ls_, t0_, tm_, xsol_, rhsb_, cb_, r_, u_, nu_;
   DevBuf<T> mr_[6], mr_x_, mr_c_, mr_b_;   // MINRES Lanczos / direction vectors, solution, operator output, rhs
   int cur_maxit_ = -1;
+  // CUDA graphs of 1, 2, 4, 8 CG iterations (the inner loop is launch-bound for small problems)
+  cudaGraphExec_t cg_graph_[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool use_graphs_ = true;
+  void cg_iteration_launches(const int* done);
+  void build_cg_graphs(const int* done);
+  void destroy_cg_graphs();
   long long kkt_counter_ = 1;   // S.iteration_counter
   int last_cg_iters_ = 1;
   long long total_inner_ = 0, total_mults_ = 0;
@@ -560,6 +569,8 @@ Engine<T>::Engine(const cosmo_b200_problem& p, const cosmo_b200_settings& st) : 
   {
     const char* e = getenv("COSMO_B200_NO_WINDOWS");
     use_windows_ = !(e && e[0] == '1');
+    const char* ng = getenv("COSMO_B200_NO_GRAPH");
+    use_graphs_ = !(ng && ng[0] == '1');
     const char* g = getenv("COSMO_B200_WIN_GROUP");
     if (g && atoi(g) == 8) win_group_ = 8;
   }
@@ -702,7 +713,16 @@ Engine<T>::Engine(const cosmo_b200_problem& p, const cosmo_b200_settings& st) : 
 }
 
 template <typename T>
+void Engine<T>::destroy_cg_graphs() {
+  for (auto& g : cg_graph_) {
+    if (g) cudaGraphExecDestroy(g);
+    g = nullptr;
+  }
+}
+
+template <typename T>
 Engine<T>::~Engine() {
+  destroy_cg_graphs();
   if (comm_ && g_nccl.CommDestroy) g_nccl.CommDestroy(comm_);
   if (h_sc_) cudaFreeHost(h_sc_);
   if (h_isc_) cudaFreeHost(h_isc_);
@@ -946,18 +966,20 @@ void Engine<T>::kkt_cg(const int* done) {
   cg_init_kernel<T><<<vgrid(n_), kBlock, 0, stream_>>>(n_, rhsb_.p, cb_.p, r_.p, u_.p, red(SC_RES2),
                                                       CgInitFin<T>{sc_.p, isc_.p, (T)tol_num});
   check_launch("cg_init");
+  const bool graphs = use_graphs_ && nranks_ == 1;
+  if (graphs && !cg_graph_[0]) build_cg_graphs(done);
   int chunk = std::max(last_cg_iters_, 0);
   for (;;) {
-    for (int i = 0; i < chunk; ++i) {
-      cg_update_u_kernel<T><<<vgrid(n_), kBlock, 0, stream_>>>(n_, r_.p, u_.p, sc_.p, isc_.p);
-      check_launch("cg_update_u");
-      launch_spmv(A_, u_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, m_, EpiScale<T>{done, tm_.p, rho_vec_.p},
-                  red(SC_TMP0), "spmv_A_scale");
-      kkt_op_stage2(done, u_.p, tm_.p, cb_.p);
-      allreduce_sum(cb_.p, n_ + 1);
-      cg_update_xr_kernel<T><<<vgrid(n_), kBlock, 0, stream_>>>(n_, u_.p, cb_.p, cb_.p + n_, xsol_.p, r_.p, sc_.p, isc_.p,
-                                                             red(SC_RES2), CgStepFin<T>{sc_.p, isc_.p});
-      check_launch("cg_update_xr");
+    if (graphs) {
+      int left = chunk;
+      for (int b = 3; b >= 0; --b)
+        while (left >= (1 << b)) {
+          CUDA_TRY(cudaGraphLaunch(cg_graph_[b], stream_));
+          launches_ += (long long)(1 << b) * (At_.windowed && P_.nnz > 0 ? 5 : 4);
+          left -= (1 << b);
+        }
+    } else {
+      for (int i = 0; i < chunk; ++i) cg_iteration_launches(done);
     }
     CUDA_TRY(cudaMemcpyAsync(h_isc_, isc_.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream_));
     sync();
@@ -968,6 +990,40 @@ void Engine<T>::kkt_cg(const int* done) {
   last_cg_iters_ = iters;
   total_inner_ += iters;
   total_mults_ += 1 + iters;
+}
+
+// one CG iteration: u = r + beta u ; c = L u ; alpha = res^2/u'c ; x += alpha u ; r -= alpha c
+template <typename T>
+void Engine<T>::cg_iteration_launches(const int* done) {
+  cg_update_u_kernel<T><<<vgrid(n_), kBlock, 0, stream_>>>(n_, r_.p, u_.p, sc_.p, isc_.p);
+  check_launch("cg_update_u");
+  launch_spmv(A_, u_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, m_, EpiScale<T>{done, tm_.p, rho_vec_.p}, red(SC_TMP0),
+              "spmv_A_scale");
+  kkt_op_stage2(done, u_.p, tm_.p, cb_.p);
+  allreduce_sum(cb_.p, n_ + 1);
+  cg_update_xr_kernel<T><<<vgrid(n_), kBlock, 0, stream_>>>(n_, u_.p, cb_.p, cb_.p + n_, xsol_.p, r_.p, sc_.p, isc_.p, red(SC_RES2),
+                                                         CgStepFin<T>{sc_.p, isc_.p});
+  check_launch("cg_update_xr");
+}
+
+// Stream-capture 1, 2, 4 and 8 CG iterations into executable graphs.  All kernel arguments are
+// fixed device pointers (the scalars alpha, beta, tolerance, done flag live on the device), so the
+// graphs stay valid for the lifetime of the handle.
+template <typename T>
+void Engine<T>::build_cg_graphs(const int* done) {
+  // make sure one-time function attributes are set outside of the capture
+  cg_iteration_launches(done);
+  sync();
+  const long long saved = launches_;
+  for (int b = 0; b < 4; ++b) {
+    cudaGraph_t graph = nullptr;
+    CUDA_TRY(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+    for (int i = 0; i < (1 << b); ++i) cg_iteration_launches(done);
+    CUDA_TRY(cudaStreamEndCapture(stream_, &graph));
+    CUDA_TRY(cudaGraphInstantiate(&cg_graph_[b], graph, 0));
+    CUDA_TRY(cudaGraphDestroy(graph));
+  }
+  launches_ = saved;
 }
 
 // minres!(previous_solution, L, b; abstol = tol_k/|L x0 - b|, reltol = 0) on the reduced system
