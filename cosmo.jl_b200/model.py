@@ -381,6 +381,9 @@ class Model:
 
     # warm starts in unscaled coordinates, interface.jl:117-179
     def warm_start_primal(self, x0):
+        x0 = np.asarray(x0, dtype=np.float64)
+        if x0.shape != (self.n,):
+            raise ValueError("Dimension of warm starting vector doesn't match the length of index range ind.")
         self.x[:] = x0
         self.s[:] = self.b0 - self.A0 @ self.x   # s0 = b - A x0 (interface.jl:131-147)
 
@@ -388,7 +391,10 @@ class Model:
         self.s[:] = s0
 
     def warm_start_dual(self, y0):
-        self.mu[:] = -np.asarray(y0, dtype=np.float64)
+        y0 = np.asarray(y0, dtype=np.float64)
+        if y0.shape != (self.m,):
+            raise ValueError("Dimension of warm starting vector doesn't match the length of index range ind.")
+        self.mu[:] = -y0
 
     # update!(model; q, b), interface.jl:187-211
     def update(self, q=None, b=None):

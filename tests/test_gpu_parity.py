@@ -463,3 +463,31 @@ def test_c5_maxcut_chordal_clique_batch():
     assert abs(full.obj_val - res.obj_val) <= 1e-3 * max(1.0, abs(full.obj_val))
     x, s, mu = chordal.reverse(info, res.x, res.s, -res.y)
     assert np.max(np.abs(A @ x + s - b)) < 1e-3
+
+
+def test_simple_statuses_and_warm_start():
+    """test/UnitTests/simple.jl:58-124: Max_iter_reached (max_iter / huge check_termination),
+    Time_limit_reached, warm start gives fewer iterations."""
+    P, q, cons = G.g1_qp_nonneg()
+
+    def run(**kw):
+        model = cosmo_b200.Model()
+        cosmo_b200.assemble(model, P, q, _to_mine(cons), cosmo_b200.Settings(**kw))
+        return model, model.optimize()
+
+    assert run(max_iter=20)[1].status == "Max_iter_reached"                     # :58-66
+    assert run(check_termination=100000)[1].status == "Max_iter_reached"        # :70-80
+    assert run(time_limit=0.2, check_termination=100000000, max_iter=10000000)[1].status == "Time_limit_reached"  # :82-90
+    m1, r1 = run(check_termination=1)
+    m2 = cosmo_b200.Model()
+    cosmo_b200.assemble(m2, P, q, _to_mine(cons), cosmo_b200.Settings(check_termination=1))
+    m2.warm_start_primal(r1.x)
+    m2.warm_start_dual(r1.y)
+    assert np.array_equal(m2.x, r1.x) and np.array_equal(m2.mu, -r1.y) and np.linalg.norm(m2.s - r1.s) < 1e-4   # :107-110
+    rng = np.random.default_rng(0)
+    m2.warm_start_primal(r1.x + 0.01 * rng.random(2))
+    m2.warm_start_dual(r1.y + 0.01 * rng.random(6))
+    r2 = m2.optimize()
+    assert r1.status == "Solved" and r2.status == "Solved" and r2.iter < r1.iter                                  # :118
+    with pytest.raises(ValueError):
+        m2.warm_start_primal(rng.random(4))
