@@ -224,6 +224,7 @@ class Engine : public EngineBase {
   // CUDA graphs of 1, 2, 4, 8 CG iterations (the inner loop is launch-bound for small problems)
   cudaGraphExec_t cg_graph_[4] = {nullptr, nullptr, nullptr, nullptr};
   bool use_graphs_ = true;
+  bool graph_multi_ = true;
   void cg_iteration_launches(const int* done);
   void build_cg_graphs(const int* done);
   void destroy_cg_graphs();
@@ -571,6 +572,8 @@ Engine<T>::Engine(const cosmo_b200_problem& p, const cosmo_b200_settings& st) : 
     use_windows_ = !(e && e[0] == '1');
     const char* ng = getenv("COSMO_B200_NO_GRAPH");
     use_graphs_ = !(ng && ng[0] == '1');
+    const char* gm = getenv("COSMO_B200_GRAPH_MULTI");
+    graph_multi_ = !(gm && gm[0] == '0');
     const char* g = getenv("COSMO_B200_WIN_GROUP");
     if (g && atoi(g) == 8) win_group_ = 8;
   }
@@ -966,7 +969,8 @@ void Engine<T>::kkt_cg(const int* done) {
   cg_init_kernel<T><<<vgrid(n_), kBlock, 0, stream_>>>(n_, rhsb_.p, cb_.p, r_.p, u_.p, red(SC_RES2),
                                                       CgInitFin<T>{sc_.p, isc_.p, (T)tol_num});
   check_launch("cg_init");
-  const bool graphs = use_graphs_ && nranks_ == 1;
+  // NCCL collectives are capturable too; COSMO_B200_GRAPH_MULTI=0 restores eager launches when sharded
+  const bool graphs = use_graphs_ && (nranks_ == 1 || graph_multi_);
   if (graphs && !cg_graph_[0]) build_cg_graphs(done);
   int chunk = std::max(last_cg_iters_, 0);
   for (;;) {
