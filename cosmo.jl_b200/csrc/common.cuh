@@ -92,6 +92,53 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
       : "memory");
 }
 
+// ---- peer-memory exchange (NVLink / NVSwitch) -------------------------------
+// One exchange buffer per rank, mapped into every peer through CUDA IPC:
+//   data : 2 slots x stride elements (the rank's partial n-vector + its partial dot at [n])
+//   flags: 2 slots x kMaxRanks sequence numbers, written REMOTELY by the producers
+// A producer writes its partial into its own slot (seq & 1) and publishes seq+1 into every peer's
+// flag array; a consumer waits until all ranks have published seq+1, then sums the peers' slots in
+// rank order while it does its own work (one-shot allreduce fused into the consumer kernel; the
+// result is bitwise identical on every rank).  Two slots suffice: a rank can only overwrite slot s
+// after all peers have published the NEXT sequence number, i.e. finished reading slot s.
+constexpr int kMaxRanks = 8;
+template <typename T>
+struct P2pView {
+  const T* peer_data[kMaxRanks];   // peer_data[r] = base of rank r's exchange buffer (own buffer at r = rank)
+  unsigned* peer_flags[kMaxRanks]; // peer_flags[r] = base of rank r's flag array (remote writes)
+  const unsigned* local_flags;     // this rank's flag array
+  unsigned* seq;                   // device-resident sequence counter (identical on every rank)
+  size_t stride;                   // elements per slot
+  int nranks, rank;
+};
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ T ld_peer(const T* p) {   // coherent load of peer / own exchange data
+  return *reinterpret_cast<const volatile T*>(p);
+}
+// consumer side: block-wide wait until every rank has published sequence number `want` for `slot`
+template <typename T>
+__device__ __forceinline__ void p2p_wait_all(const P2pView<T>& v, unsigned slot, unsigned want) {
+  if ((int)threadIdx.x < v.nranks) {
+    const unsigned* f = v.local_flags + slot * kMaxRanks + threadIdx.x;
+    while (ld_acquire_sys(f) != want) { __nanosleep(40); }
+  }
+  __syncthreads();
+}
+// producer side (one thread, after the kernel's data is globally visible): publish to all peers
+template <typename T>
+__device__ __forceinline__ void p2p_publish(const P2pView<T>& v, unsigned slot, unsigned val) {
+  __threadfence_system();
+  for (int r = 0; r < v.nranks; ++r) st_release_sys(v.peer_flags[r] + slot * kMaxRanks + v.rank, val);
+}
+
 // NaN-propagating max of non-negative magnitudes (Julia's norm(x, Inf) returns NaN
 // when an entry is NaN; fmax would silently drop it).
 template <typename T>

@@ -164,6 +164,8 @@ class EngineBase {
   virtual void get_rho_vec(void* out) = 0;
   virtual void get_w(void* out) = 0;
   virtual void comm_init(int nranks, int rank, const void* id128) = 0;
+  virtual void p2p_export(void* blob128) = 0;
+  virtual void p2p_attach(const void* blobs, int nranks) = 0;
 };
 
 template <typename T>
@@ -188,6 +190,8 @@ class Engine : public EngineBase {
   void get_rho_vec(void* out) override;
   void get_w(void* out) override;
   void comm_init(int nranks, int rank, const void* id128) override;
+  void p2p_export(void* blob128) override;
+  void p2p_attach(const void* blobs, int nranks) override;
 
  private:
   // ---- problem ----
@@ -249,6 +253,12 @@ class Engine : public EngineBase {
   // multi-GPU
   int nranks_ = 1, rank_ = 0;
   NcclComm comm_ = nullptr;
+  // peer-memory exchange of the reduced-KKT operator partials (replaces the per-application allreduce)
+  bool p2p_ = false;
+  P2pView<T> xv_;
+  DevBuf<T> xchg_data_;
+  DevBuf<unsigned> xchg_flags_, xchg_seq_;
+  std::vector<void*> ipc_opened_;
 
   // ---- helpers ----
   RedBuf<T> red(int out_slot) { return RedBuf<T>{partials_.p, sc_.p + out_slot, ticket_.p}; }
@@ -278,7 +288,7 @@ class Engine : public EngineBase {
   void project_device(const T* w, bool with_rhs, const T* ws_rhs);
   void soc_norms(const T* ws, T* norm_out);
   void kkt_core(bool fused_tail, const T* w_src, T* w_dst);
-  void kkt_op_stage2(const int* done, const T* u, const T* t_in, T* c_out);
+  void kkt_op_stage2(const int* done, const T* u, const T* t_in, T* c_out, bool exchange = false);
   void kkt_cg(const int* done);
   void kkt_minres(bool full);
   void set_maxit(int v);
@@ -710,6 +720,7 @@ Engine<T>::Engine(const cosmo_b200_problem& p, const cosmo_b200_settings& st) : 
     CUDA_TRY(cudaMemcpyAsync(isc_.p, h, sizeof(h), cudaMemcpyHostToDevice, stream_));
     sync();
   }
+  memset(&xv_, 0, sizeof(xv_));
   rho_ = st_.rho;
   classify_and_set_rho(true);
   sync();
@@ -726,6 +737,7 @@ void Engine<T>::destroy_cg_graphs() {
 template <typename T>
 Engine<T>::~Engine() {
   destroy_cg_graphs();
+  for (void* p : ipc_opened_) cudaIpcCloseMemHandle(p);
   if (comm_ && g_nccl.CommDestroy) g_nccl.CommDestroy(comm_);
   if (h_sc_) cudaFreeHost(h_sc_);
   if (h_isc_) cudaFreeHost(h_isc_);
@@ -837,6 +849,54 @@ void Engine<T>::comm_init(int nranks, int rank, const void* id128) {
   if (rc != 0) throw EngineError{COSMO_B200_ERR_NCCL, std::string("ncclCommInitRank failed: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?")};
 }
 
+// Peer-memory exchange set-up: every rank exports its exchange buffer + flag array as two CUDA IPC
+// handles (64 B each); the host plumbing all-gathers the blobs; attach() maps the peers' buffers.
+template <typename T>
+void Engine<T>::p2p_export(void* blob128) {
+  CUDA_TRY(cudaSetDevice(device_));
+  const size_t stride = ((size_t)n_ + 8 + 15) & ~(size_t)15;
+  xchg_data_.alloc(2 * stride);
+  xchg_flags_.alloc(2 * kMaxRanks);
+  xchg_seq_.alloc(1);
+  xv_.stride = stride;
+  cudaIpcMemHandle_t hd, hf;
+  CUDA_TRY(cudaIpcGetMemHandle(&hd, xchg_data_.p));
+  CUDA_TRY(cudaIpcGetMemHandle(&hf, xchg_flags_.p));
+  memcpy(blob128, &hd, 64);
+  memcpy(static_cast<char*>(blob128) + 64, &hf, 64);
+}
+
+template <typename T>
+void Engine<T>::p2p_attach(const void* blobs, int nranks) {
+  if (nranks != nranks_ || nranks > kMaxRanks) throw EngineError{COSMO_B200_ERR_INVALID, "p2p_attach: rank count mismatch (max 8)"};
+  if (!xchg_data_.p) throw EngineError{COSMO_B200_ERR_INVALID, "p2p_attach before p2p_export"};
+  CUDA_TRY(cudaSetDevice(device_));
+  for (int r = 0; r < nranks; ++r) {
+    if (r == rank_) {
+      xv_.peer_data[r] = xchg_data_.p;
+      xv_.peer_flags[r] = xchg_flags_.p;
+      continue;
+    }
+    cudaIpcMemHandle_t hd, hf;
+    memcpy(&hd, static_cast<const char*>(blobs) + (size_t)r * 128, 64);
+    memcpy(&hf, static_cast<const char*>(blobs) + (size_t)r * 128 + 64, 64);
+    void *pd = nullptr, *pf = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&pd, hd, cudaIpcMemLazyEnablePeerAccess));
+    CUDA_TRY(cudaIpcOpenMemHandle(&pf, hf, cudaIpcMemLazyEnablePeerAccess));
+    ipc_opened_.push_back(pd);
+    ipc_opened_.push_back(pf);
+    xv_.peer_data[r] = static_cast<const T*>(pd);
+    xv_.peer_flags[r] = static_cast<unsigned*>(pf);
+  }
+  for (int r = nranks; r < kMaxRanks; ++r) { xv_.peer_data[r] = nullptr; xv_.peer_flags[r] = nullptr; }
+  xv_.local_flags = xchg_flags_.p;
+  xv_.seq = xchg_seq_.p;
+  xv_.nranks = nranks;
+  xv_.rank = rank_;
+  destroy_cg_graphs();
+  p2p_ = true;
+}
+
 // ---------------------------------------------------------------------------
 template <typename T>
 template <typename Epi>
@@ -893,8 +953,9 @@ void Engine<T>::project_device(const T* w, bool with_rhs, const T* ws_rhs) {
 // c = A' tm + P u + sigma u ; cb[n] = u'c   (second half of reduced_mul!, kktsolver_indirect.jl:61-65)
 // Rank 0 alone adds the replicated P / sigma terms of a row-sharded run.
 template <typename T>
-void Engine<T>::kkt_op_stage2(const int* done, const T* u, const T* t_in, T* c_out) {
+void Engine<T>::kkt_op_stage2(const int* done, const T* u, const T* t_in, T* c_out, bool exchange) {
   const bool lead = (rank_ == 0);
+  const bool px = exchange && p2p_;
   if (At_.windowed) {
     // the slab kernel cannot walk P's rows without unbalancing its window-0 CTAs: P u goes first
     const T* pu = nullptr;
@@ -903,10 +964,10 @@ void Engine<T>::kkt_op_stage2(const int* done, const T* u, const T* t_in, T* c_o
       pu = vec_n2_.p;
     }
     launch_spmv(At_, t_in, (const DevCsr<T>*)nullptr, (const T*)nullptr, n_,
-                EpiKktOp<T>{done, c_out, u, lead ? (T)st_.sigma : (T)0, pu}, red_ptr(cb_.p + n_), "spmv_kkt_op");
+                EpiKktOp<T>{done, c_out, u, lead ? (T)st_.sigma : (T)0, pu, px, xv_, n_}, red_ptr(cb_.p + n_), "spmv_kkt_op");
   } else {
     launch_spmv(At_, t_in, lead ? &P_ : nullptr, u, n_,
-                EpiKktOp<T>{done, c_out, u, lead ? (T)st_.sigma : (T)0, nullptr}, red_ptr(cb_.p + n_), "spmv_kkt_op");
+                EpiKktOp<T>{done, c_out, u, lead ? (T)st_.sigma : (T)0, nullptr, px, xv_, n_}, red_ptr(cb_.p + n_), "spmv_kkt_op");
   }
 }
 
@@ -963,11 +1024,11 @@ void Engine<T>::kkt_cg(const int* done) {
   // c = L x0 (warm start => one product for the initial residual)
   launch_spmv(A_, xsol_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, m_, EpiScale<T>{nullptr, tm_.p, rho_vec_.p},
               red(SC_TMP0), "spmv_A_scale");
-  kkt_op_stage2(nullptr, xsol_.p, tm_.p, cb_.p);
-  allreduce_sum(cb_.p, n_ + 1);
+  kkt_op_stage2(nullptr, xsol_.p, tm_.p, cb_.p, true);
+  if (!p2p_) allreduce_sum(cb_.p, n_ + 1);
   const double tol_num = st_.tol_constant / pow((double)kkt_counter_, st_.tol_exponent);
   cg_init_kernel<T><<<vgrid(n_), kBlock, 0, stream_>>>(n_, rhsb_.p, cb_.p, r_.p, u_.p, red(SC_RES2),
-                                                      CgInitFin<T>{sc_.p, isc_.p, (T)tol_num});
+                                                      CgInitFin<T>{sc_.p, isc_.p, (T)tol_num, p2p_ ? xchg_seq_.p : nullptr}, p2p_, xv_);
   check_launch("cg_init");
   // NCCL collectives are capturable too; COSMO_B200_GRAPH_MULTI=0 restores eager launches when sharded
   const bool graphs = use_graphs_ && (nranks_ == 1 || graph_multi_);
@@ -1003,10 +1064,10 @@ void Engine<T>::cg_iteration_launches(const int* done) {
   check_launch("cg_update_u");
   launch_spmv(A_, u_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, m_, EpiScale<T>{done, tm_.p, rho_vec_.p}, red(SC_TMP0),
               "spmv_A_scale");
-  kkt_op_stage2(done, u_.p, tm_.p, cb_.p);
-  allreduce_sum(cb_.p, n_ + 1);
+  kkt_op_stage2(done, u_.p, tm_.p, cb_.p, true);
+  if (!p2p_) allreduce_sum(cb_.p, n_ + 1);
   cg_update_xr_kernel<T><<<vgrid(n_), kBlock, 0, stream_>>>(n_, u_.p, cb_.p, cb_.p + n_, xsol_.p, r_.p, sc_.p, isc_.p, red(SC_RES2),
-                                                         CgStepFin<T>{sc_.p, isc_.p});
+                                                         CgStepFin<T>{sc_.p, isc_.p, p2p_ ? xchg_seq_.p : nullptr}, p2p_, xv_);
   check_launch("cg_update_xr");
 }
 
@@ -1592,6 +1653,14 @@ int cosmo_b200_comm_unique_id(void* id128) {
 int cosmo_b200_comm_init(cosmo_b200_handle* h, int32_t nranks, int32_t rank, const void* id128) {
   if (nranks > 1 && !id128) return COSMO_B200_ERR_INVALID;
   ABI_GUARD(h, h->impl->comm_init(nranks, rank, id128));
+}
+int cosmo_b200_comm_p2p_export(cosmo_b200_handle* h, void* blob128) {
+  if (!blob128) return COSMO_B200_ERR_INVALID;
+  ABI_GUARD(h, h->impl->p2p_export(blob128));
+}
+int cosmo_b200_comm_p2p_attach(cosmo_b200_handle* h, const void* blobs, int32_t nranks) {
+  if (!blobs) return COSMO_B200_ERR_INVALID;
+  ABI_GUARD(h, h->impl->p2p_attach(blobs, nranks));
 }
 
 }  // extern "C"

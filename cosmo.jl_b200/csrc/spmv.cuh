@@ -309,13 +309,24 @@ struct EpiKktOp {
   const T* u;
   T sigma;
   const T* add;   // optional precomputed P u (nullptr: P rows are traversed by the same kernel)
+  // row-sharded runs: write the partial into this rank's exchange slot and publish it to the peers
+  // (the consumer kernels sum the slots; no separate allreduce launch)
+  bool p2p;
+  P2pView<T> x;
+  int n;
+  __device__ T* target() const { return p2p ? const_cast<T*>(x.peer_data[x.rank]) + (size_t)(*x.seq & 1u) * x.stride : c; }
   __device__ void row(int r, T s, T* accS, T*) const {
     const T ur = u[r];
     const T v = (add ? s + add[r] : s) + sigma * ur;
-    c[r] = v;
+    target()[r] = v;
     accS[0] += ur * v;
   }
-  __device__ void operator()(T*) const {}
+  __device__ void operator()(T* out) const {   // last block, one thread: out[0] = partial u'c
+    if (!p2p) return;
+    const unsigned sq = *x.seq;
+    target()[n] = out[0];
+    p2p_publish(x, sq & 1u, sq + 1u);
+  }
 };
 
 // rhs = x1 + A'(rho .* x2)                  (kktsolver_indirect.jl:52-54)

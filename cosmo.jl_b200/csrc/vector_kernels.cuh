@@ -197,9 +197,18 @@ __global__ void __launch_bounds__(kBlock) sub_kernel(int n, const T* __restrict_
 // kktsolver_indirect.jl:70).  Scalars live on the device; every kernel is a
 // no-op once isc[ISC_DONE] is set so the host can enqueue iterations ahead.
 // ---------------------------------------------------------------------------
+// sum of the ranks' partial vectors at index i, in rank order (one-shot allreduce on the fly)
+template <typename T>
+__device__ __forceinline__ T p2p_gather(const P2pView<T>& v, unsigned slot, int i) {
+  T acc = ld_peer(v.peer_data[0] + (size_t)slot * v.stride + i);
+  for (int r = 1; r < v.nranks; ++r) acc += ld_peer(v.peer_data[r] + (size_t)slot * v.stride + i);
+  return acc;
+}
+
 template <typename T>
 struct CgInitFin {
   T* sc; int* isc; T tol_num;
+  unsigned* seq;   // non-null in peer-exchange mode: this consumer retires the sequence number
   __device__ void operator()(T* out) const {   // out[0] = |r|^2, out[1] = |rhs|^2
     const T res = sqrt(out[0]);
     const T rhsn = sqrt(out[1]);
@@ -209,6 +218,7 @@ struct CgInitFin {
     sc[SC_TOL] = tol;
     isc[ISC_IT] = 0;
     isc[ISC_DONE] = (res <= tol || isc[ISC_MAXIT] <= 0) ? 1 : 0;
+    if (seq) *seq = *seq + 1u;
   }
 };
 
@@ -216,12 +226,19 @@ struct CgInitFin {
 template <typename T>
 __global__ void __launch_bounds__(kBlock) cg_init_kernel(int n, const T* __restrict__ rhs, const T* __restrict__ c,
                                                          T* __restrict__ r, T* __restrict__ u, RedBuf<T> rb,
-                                                         CgInitFin<T> fin) {
+                                                         CgInitFin<T> fin, bool p2p, P2pView<T> xv) {
   T accS[2] = {0, 0};
   T accM[1] = {0};
+  unsigned slot = 0;
+  if (p2p) {
+    const unsigned sq = *xv.seq;
+    slot = sq & 1u;
+    p2p_wait_all(xv, slot, sq + 1u);
+  }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const T b = rhs[i];
-    const T ri = b - c[i];
+    const T ci = p2p ? p2p_gather(xv, slot, i) : c[i];
+    const T ri = b - ci;
     r[i] = ri;
     u[i] = T(0);
     accS[0] += ri * ri;
@@ -243,6 +260,7 @@ __global__ void __launch_bounds__(kBlock) cg_update_u_kernel(int n, const T* __r
 template <typename T>
 struct CgStepFin {
   T* sc; int* isc;
+  unsigned* seq;
   __device__ void operator()(T* out) const {   // out[0] = |r|^2
     const T res = sqrt(out[0]);
     sc[SC_PREV] = sc[SC_RES];
@@ -250,6 +268,7 @@ struct CgStepFin {
     const int it = isc[ISC_IT] + 1;
     isc[ISC_IT] = it;
     isc[ISC_DONE] = (res <= sc[SC_TOL] || it >= isc[ISC_MAXIT]) ? 1 : 0;
+    if (seq) *seq = *seq + 1u;
   }
 };
 
@@ -259,15 +278,26 @@ __global__ void __launch_bounds__(kBlock) cg_update_xr_kernel(int n, const T* __
                                                               const T* __restrict__ dot_uc, T* __restrict__ x,
                                                               T* __restrict__ r, const T* __restrict__ sc,
                                                               const int* __restrict__ isc, RedBuf<T> rb,
-                                                              CgStepFin<T> fin) {
+                                                              CgStepFin<T> fin, bool p2p, P2pView<T> xv) {
   if (isc[ISC_DONE]) return;
   const T res = sc[SC_RES];
-  const T alpha = (res * res) / dot_uc[0];
+  unsigned slot = 0;
+  T dot;
+  if (p2p) {
+    const unsigned sq = *xv.seq;
+    slot = sq & 1u;
+    p2p_wait_all(xv, slot, sq + 1u);
+    dot = p2p_gather(xv, slot, n);
+  } else {
+    dot = dot_uc[0];
+  }
+  const T alpha = (res * res) / dot;
   T accS[1] = {0};
   T accM[1] = {0};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     x[i] += alpha * u[i];
-    const T ri = r[i] - alpha * c[i];
+    const T ci = p2p ? p2p_gather(xv, slot, i) : c[i];
+    const T ri = r[i] - alpha * ci;
     r[i] = ri;
     accS[0] += ri * ri;
   }

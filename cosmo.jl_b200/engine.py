@@ -79,7 +79,7 @@ EXPORTS = [
     "cosmo_b200_last_error", "cosmo_b200_update_settings", "cosmo_b200_warm_start", "cosmo_b200_update_qb",
     "cosmo_b200_update_rho", "cosmo_b200_reset", "cosmo_b200_solve", "cosmo_b200_project", "cosmo_b200_kkt_solve",
     "cosmo_b200_residuals", "cosmo_b200_spmv", "cosmo_b200_spmv_bench", "cosmo_b200_get_rho_vec", "cosmo_b200_get_w",
-    "cosmo_b200_comm_unique_id", "cosmo_b200_comm_init",
+    "cosmo_b200_comm_unique_id", "cosmo_b200_comm_init", "cosmo_b200_comm_p2p_export", "cosmo_b200_comm_p2p_attach",
 ]
 
 _lib = None
@@ -123,6 +123,8 @@ def load_library(rebuild_if_stale=True):
     lib.cosmo_b200_get_w.argtypes = [vp, vp]
     lib.cosmo_b200_comm_unique_id.argtypes = [vp]
     lib.cosmo_b200_comm_init.argtypes = [vp, C.c_int32, C.c_int32, vp]
+    lib.cosmo_b200_comm_p2p_export.argtypes = [vp, vp]
+    lib.cosmo_b200_comm_p2p_attach.argtypes = [vp, vp, C.c_int32]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("cosmo_b200_destroy", "cosmo_b200_last_error"):
@@ -272,6 +274,15 @@ class Engine:
     def comm_init(self, nranks, rank, unique_id: Optional[bytes]):
         buf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
         self._check(self._lib.cosmo_b200_comm_init(self._h, nranks, rank, C.cast(buf, C.c_void_p) if buf else None))
+
+    def p2p_export(self) -> bytes:
+        buf = (C.c_char * 128)()
+        self._check(self._lib.cosmo_b200_comm_p2p_export(self._h, C.cast(buf, C.c_void_p)))
+        return bytes(buf)
+
+    def p2p_attach(self, blobs: bytes, nranks: int):
+        buf = C.create_string_buffer(blobs, len(blobs))
+        self._check(self._lib.cosmo_b200_comm_p2p_attach(self._h, C.cast(buf, C.c_void_p), nranks))
 
     # ---- the hot loop ----------------------------------------------------------
     def solve(self, out_x=None, out_s=None, out_mu=None) -> SolveOutput:

@@ -11,6 +11,7 @@ the reference's own check points) -- issued inside libcosmo_b200.so.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -115,4 +116,9 @@ def create_engine(shard: Shard, settings: M.Settings, device: int = 0, dist=None
         obj = [_eng.nccl_unique_id() if shard.rank == 0 else None]
         dist.broadcast_object_list(obj, src=0)
         eng.comm_init(shard.world, shard.rank, obj[0])
+        if os.environ.get("COSMO_B200_P2P", "1") != "0" and shard.world <= 8:
+            # peer-memory exchange (CUDA IPC over NVLink): all-gather the 128-byte handle blobs
+            blobs = [None] * shard.world
+            dist.all_gather_object(blobs, eng.p2p_export())
+            eng.p2p_attach(b"".join(blobs), shard.world)
     return eng

@@ -215,6 +215,12 @@ int cosmo_b200_get_w(cosmo_b200_handle* h, void* w);
 /* 128-byte ncclUniqueId created on rank 0 and broadcast by the host plumbing */
 int cosmo_b200_comm_unique_id(void* id128);
 int cosmo_b200_comm_init(cosmo_b200_handle* h, int32_t nranks, int32_t rank, const void* id128);
+/* Peer-memory exchange over NVLink/NVSwitch for the reduced-KKT operator partials (optional; replaces
+   the per-application NCCL allreduce by a one-shot sum fused into the consumer kernels).
+   export: 128 bytes (two CUDA IPC handles) per rank; the host all-gathers them in rank order;
+   attach: maps the peers' buffers.  All ranks must be on one NVLink-connected node. */
+int cosmo_b200_comm_p2p_export(cosmo_b200_handle* h, void* blob128);
+int cosmo_b200_comm_p2p_attach(cosmo_b200_handle* h, const void* blobs, int32_t nranks);
 
 #ifdef __cplusplus
 }
