@@ -116,8 +116,10 @@ def create_engine(shard: Shard, settings: M.Settings, device: int = 0, dist=None
         obj = [_eng.nccl_unique_id() if shard.rank == 0 else None]
         dist.broadcast_object_list(obj, src=0)
         eng.comm_init(shard.world, shard.rank, obj[0])
-        if os.environ.get("COSMO_B200_P2P", "1") != "0" and shard.world <= 8:
-            # peer-memory exchange (CUDA IPC over NVLink): all-gather the 128-byte handle blobs
+        if os.environ.get("COSMO_B200_P2P", "0") == "1" and shard.world <= 8:
+            # peer-memory exchange (CUDA IPC over NVLink), opt-in: measured SLOWER than the graph-captured
+            # NVLS allreduce of NCCL on 4 x B200 (168.6 vs 181.3 iter/s on C2, profiles/bench_r1_4gpu*.json).
+            # all-gather the 128-byte handle blobs
             blobs = [None] * shard.world
             dist.all_gather_object(blobs, eng.p2p_export())
             eng.p2p_attach(b"".join(blobs), shard.world)
