@@ -352,7 +352,7 @@ constexpr int kBjP = 2 * kBjB;    // pivot size
 __device__ __forceinline__ int bj_col(int I, int J, int k) { return (k < kBjB) ? I * kBjB + k : J * kBjB + (k - kBjB); }
 
 template <typename T>
-__global__ void __launch_bounds__(kBlock) bj_pivot_kernel(int N, int Nb, int r, const T* __restrict__ A, const T* __restrict__ thr_p,
+__global__ void __launch_bounds__(512) bj_pivot_kernel(int N, int Nb, int r, const T* __restrict__ A, const T* __restrict__ thr_p,
                                                           T* __restrict__ Rbuf, int* __restrict__ active, int* __restrict__ rotated,
                                                           int inner_sweeps) {
   extern __shared__ unsigned char smem_raw[];
@@ -450,103 +450,126 @@ __global__ void __launch_bounds__(kBlock) bj_pivot_kernel(int N, int Nb, int r, 
   if (threadIdx.x == 0) { active[k] = 1; *rotated = 1; }
 }
 
-// C_tile(64 x 64) = S_tile(64 x 64) * R, in place; S = 64 rows x the 64 columns [I|J] of X (A or V)
+// ---- GEMM-shaped block updates -------------------------------------------------------------
+// 64 threads own one 64x64 output tile with an 8x8 register micro-tile each (64 FP64 accumulators,
+// 8 LDS.128 per 64 DFMA => FP64-pipe bound instead of shared-memory bound); a 256-thread CTA handles
+// four tiles that share the same 64x64 rotation R (stored transposed in shared memory).
+constexpr int kBjLd = kBjP + 2;        // even leading dimension: 16-byte aligned columns for LDS.128
+constexpr int kBjTilesPerCta = 4;
+
 template <typename T>
-__global__ void __launch_bounds__(kBlock) bj_cols_kernel(int N, int Nb, int r, T* __restrict__ A, T* __restrict__ V,
-                                                         const T* __restrict__ Rbuf, const int* __restrict__ active) {
+__device__ __forceinline__ void bj_load8(const T* p, T (&v)[8]) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = p[k];
+}
+
+// X[:, I|J] <- X[:, I|J] * R  for X = A (blockIdx.z = 0) and V (blockIdx.z = 1), 4 row tiles per CTA
+template <typename T>
+__global__ void __launch_bounds__(kBlock, 1) bj_cols_kernel(int N, int Nb, int r, T* __restrict__ A, T* __restrict__ V,
+                                                            const T* __restrict__ Rbuf, const int* __restrict__ active) {
   const int k = blockIdx.y;
   if (!active[k]) return;
-  extern __shared__ unsigned char smem_raw[];
-  constexpr int P = kBjP, ld = P + 1;
-  T* S = reinterpret_cast<T*>(smem_raw);     // S[row + col*ld]
-  T* Rs = S + ld * P;                        // Rs[kk + j*P]
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int P = kBjP, ld = kBjLd;
+  T* Rt = reinterpret_cast<T*>(smem_raw);            // Rt[kk * P + j] = R[kk][j]
+  T* S = Rt + P * P;                                 // 4 tiles: S[g][i + kk * ld]
   T* X = (blockIdx.z == 0) ? A : V;
   int I, J;
   rr_pair(Nb, r, k, I, J);
-  const int row0 = blockIdx.x * P;
-  const T* R = Rbuf + (size_t)k * P * P;
+  const T* R = Rbuf + (size_t)k * P * P;             // column-major R[i + j * P]
   for (int e = threadIdx.x; e < P * P; e += blockDim.x) {
     const int i = e % P, j = e / P;
-    const int gi = row0 + i, gj = bj_col(I, J, j);
-    S[i + j * ld] = (gi < N && gj < N) ? X[gi + (long long)gj * N] : T(0);
-    Rs[e] = R[e];
+    Rt[i * P + j] = R[e];
+  }
+  const int row_base = blockIdx.x * (P * kBjTilesPerCta);
+  for (int e = threadIdx.x; e < kBjTilesPerCta * P * P; e += blockDim.x) {
+    const int g = e / (P * P), rem = e % (P * P);
+    const int i = rem % P, j = rem / P;
+    const int gi = row_base + g * P + i, gj = bj_col(I, J, j);
+    S[g * (ld * P) + i + j * ld] = (gi < N && gj < N) ? X[gi + (long long)gj * N] : T(0);
   }
   __syncthreads();
-  const int ti = (threadIdx.x % 16) * 4, tj = (threadIdx.x / 16) * 4;   // 4x4 micro-tile
-  T acc[4][4];
+  const int g = threadIdx.x / 64, t = threadIdx.x % 64;
+  const int ti = (t % 8) * 8, tj = (t / 8) * 8;
+  const T* Sg = S + g * (ld * P);
+  T acc[8][8];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < 8; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = T(0);
-#pragma unroll 4
+    for (int b = 0; b < 8; ++b) acc[a][b] = T(0);
+#pragma unroll 2
   for (int kk = 0; kk < P; ++kk) {
-    T sv[4], rv[4];
+    T sv[8], rv[8];
+    bj_load8(Sg + ti + kk * ld, sv);
+    bj_load8(Rt + kk * P + tj, rv);
 #pragma unroll
-    for (int a = 0; a < 4; ++a) sv[a] = S[ti + a + kk * ld];
+    for (int a = 0; a < 8; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) rv[b] = Rs[kk + (tj + b) * P];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b] += sv[a] * rv[b];
+      for (int b = 0; b < 8; ++b) acc[a][b] += sv[a] * rv[b];
   }
 #pragma unroll
-  for (int b = 0; b < 4; ++b) {
+  for (int b = 0; b < 8; ++b) {
     const int gj = bj_col(I, J, tj + b);
+    if (gj >= N) continue;
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int gi = row0 + ti + a;
-      if (gi < N && gj < N) X[gi + (long long)gj * N] = acc[a][b];
+    for (int a = 0; a < 8; ++a) {
+      const int gi = row_base + g * P + ti + a;
+      if (gi < N) X[gi + (long long)gj * N] = acc[a][b];
     }
   }
 }
 
-// T_tile(64 x 64) = R' * T_tile, in place; T = the 64 rows [I|J] of A x 64 columns
+// A[I|J, :] <- R' * A[I|J, :], 4 column tiles per CTA
 template <typename T>
-__global__ void __launch_bounds__(kBlock) bj_rows_kernel(int N, int Nb, int r, T* __restrict__ A, const T* __restrict__ Rbuf,
-                                                         const int* __restrict__ active) {
+__global__ void __launch_bounds__(kBlock, 1) bj_rows_kernel(int N, int Nb, int r, T* __restrict__ A, const T* __restrict__ Rbuf,
+                                                            const int* __restrict__ active) {
   const int k = blockIdx.y;
   if (!active[k]) return;
-  extern __shared__ unsigned char smem_raw[];
-  constexpr int P = kBjP, ld = P + 1;
-  T* S = reinterpret_cast<T*>(smem_raw);     // S[i + j*ld], i: pivot row, j: column in tile
-  T* Rs = S + ld * P;                        // Rs[kk + i*P] = R[kk][i]
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int P = kBjP, ld = kBjLd;
+  T* Rc = reinterpret_cast<T*>(smem_raw);            // Rc[kk * P + i] = R[kk][i]  (row kk of R: contiguous in i)
+  T* Tt = Rc + P * P;                                // 4 tiles: Tt[g][kk * ld + j] = A[pivot row kk][col j]
   int I, J;
   rr_pair(Nb, r, k, I, J);
-  const int col0 = blockIdx.x * P;
   const T* R = Rbuf + (size_t)k * P * P;
   for (int e = threadIdx.x; e < P * P; e += blockDim.x) {
-    const int i = e % P, j = e / P;
-    const int gi = bj_col(I, J, i), gj = col0 + j;
-    S[i + j * ld] = (gi < N && gj < N) ? A[gi + (long long)gj * N] : T(0);
-    Rs[e] = R[e];
+    const int i = e % P, j = e / P;                  // R[i + j*P] = R[i][j]
+    Rc[i * P + j] = R[e];
+  }
+  const int col_base = blockIdx.x * (P * kBjTilesPerCta);
+  for (int e = threadIdx.x; e < kBjTilesPerCta * P * P; e += blockDim.x) {
+    const int g = e / (P * P), rem = e % (P * P);
+    const int i = rem % P, j = rem / P;              // i: pivot row (contiguous in memory), j: column in tile
+    const int gi = bj_col(I, J, i), gj = col_base + g * P + j;
+    Tt[g * (ld * P) + i * ld + j] = (gi < N && gj < N) ? A[gi + (long long)gj * N] : T(0);
   }
   __syncthreads();
-  const int ti = (threadIdx.x % 16) * 4, tj = (threadIdx.x / 16) * 4;
-  T acc[4][4];
+  const int g = threadIdx.x / 64, t = threadIdx.x % 64;
+  const int ti = (t % 8) * 8, tj = (t / 8) * 8;       // out[ti..ti+7][tj..tj+7] = sum_kk R[kk][ti+a] * T[kk][tj+b]
+  const T* Tg = Tt + g * (ld * P);
+  T acc[8][8];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < 8; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = T(0);
-#pragma unroll 4
+    for (int b = 0; b < 8; ++b) acc[a][b] = T(0);
+#pragma unroll 2
   for (int kk = 0; kk < P; ++kk) {
-    T rv[4], sv[4];
+    T rv[8], tv[8];
+    bj_load8(Rc + kk * P + ti, rv);
+    bj_load8(Tg + kk * ld + tj, tv);
 #pragma unroll
-    for (int a = 0; a < 4; ++a) rv[a] = Rs[kk + (ti + a) * P];   // R[kk][ti+a] = (R')[ti+a][kk]
+    for (int a = 0; a < 8; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) sv[b] = S[kk + (tj + b) * ld];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b] += rv[a] * sv[b];
+      for (int b = 0; b < 8; ++b) acc[a][b] += rv[a] * tv[b];
   }
 #pragma unroll
-  for (int b = 0; b < 4; ++b) {
-    const int gj = col0 + tj + b;
+  for (int b = 0; b < 8; ++b) {
+    const int gj = col_base + g * P + tj + b;
+    if (gj >= N) continue;
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
+    for (int a = 0; a < 8; ++a) {
       const int gi = bj_col(I, J, ti + a);
-      if (gi < N && gj < N) A[gi + (long long)gj * N] = acc[a][b];
+      if (gi < N) A[gi + (long long)gj * N] = acc[a][b];
     }
   }
 }
@@ -673,7 +696,7 @@ struct PsdBatch {
       ck(cudaMalloc(&R_d, (size_t)(Nb / 2) * kBjP * kBjP * sizeof(T)), "cudaMalloc R");
       ck(cudaMalloc(&act_d, (size_t)(Nb / 2) * sizeof(int)), "cudaMalloc act");
       const int smem_pivot = (int)((2 * (size_t)(kBjP + 1) * kBjP + kBjP + 2) * sizeof(T));
-      const int smem_upd = (int)(((size_t)(kBjP + 1) * kBjP + (size_t)kBjP * kBjP) * sizeof(T));
+      const int smem_upd = (int)(((size_t)kBjP * kBjP + (size_t)kBjTilesPerCta * kBjLd * kBjP) * sizeof(T));
       ck(cudaFuncSetAttribute(bj_pivot_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pivot), "smem attr pivot");
       ck(cudaFuncSetAttribute(bj_cols_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_upd), "smem attr cols");
       ck(cudaFuncSetAttribute(bj_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_upd), "smem attr rows");
@@ -697,12 +720,12 @@ struct PsdBatch {
     psd_large_thr_kernel<T><<<1, 32, 0, st>>>(fro_d, g, thr_d, rot_d);
     launches += 2;
     const size_t smem_pivot = (2 * (size_t)(kBjP + 1) * kBjP + kBjP + 2) * sizeof(T);
-    const size_t smem_upd = ((size_t)(kBjP + 1) * kBjP + (size_t)kBjP * kBjP) * sizeof(T);
-    const int tiles = (N + kBjP - 1) / kBjP;
+    const size_t smem_upd = ((size_t)kBjP * kBjP + (size_t)kBjTilesPerCta * kBjLd * kBjP) * sizeof(T);
+    const int tiles = (N + kBjP * kBjTilesPerCta - 1) / (kBjP * kBjTilesPerCta);
     bool converged = false;
     for (int sweep = 0; sweep < max_sweeps && !converged; ++sweep) {
       for (int r = 0; r < Nb - 1; ++r) {
-        bj_pivot_kernel<T><<<npairs, kBlock, smem_pivot, st>>>(N, Nb, r, A_d, thr_d, R_d, act_d, rot_d, 1);
+        bj_pivot_kernel<T><<<npairs, 512, smem_pivot, st>>>(N, Nb, r, A_d, thr_d, R_d, act_d, rot_d, 1);
         bj_cols_kernel<T><<<dim3(tiles, npairs, 2), kBlock, smem_upd, st>>>(N, Nb, r, A_d, V_d, R_d, act_d);
         bj_rows_kernel<T><<<dim3(tiles, npairs, 1), kBlock, smem_upd, st>>>(N, Nb, r, A_d, R_d, act_d);
         launches += 3;
