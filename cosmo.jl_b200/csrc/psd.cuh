@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(kBlock) psd_small_kernel(const PsdConeDesc* __
   T* A = reinterpret_cast<T*>(smem_raw);
   T* V = A + (size_t)ld * N;
   T* cs = V + (size_t)ld * N;   // 2 * (N/2 + 1): rotation cosines / sines of the round
+  __shared__ int pq[kPsdSmallMax + 2];
   __shared__ T red[kWarpsPerBlock];
   __shared__ int rotated;
   __shared__ T thr_sh;
@@ -140,16 +141,17 @@ __global__ void __launch_bounds__(kBlock) psd_small_kernel(const PsdConeDesc* __
         }
         cs[2 * k] = c;
         cs[2 * k + 1] = sn;
+        pq[2 * k] = p;          // the pairing is computed once per round (integer modulo is expensive)
+        pq[2 * k + 1] = q;
       }
       __syncthreads();
       // columns p,q of A and V:  [ap aq] <- [ap aq] * [c s; -s c]
       for (int e = threadIdx.x; e < npairs * N; e += blockDim.x) {
-        const int k = e / N, i = e % N;
+        const int k = e / N, i = e - k * N;
         const T sn = cs[2 * k + 1];
         if (sn == T(0)) continue;
         const T c = cs[2 * k];
-        int p, q;
-        rr_pair(Ne, r, k, p, q);
+        const int p = pq[2 * k], q = pq[2 * k + 1];
         const T aip = A[i + p * ld], aiq = A[i + q * ld];
         A[i + p * ld] = c * aip - sn * aiq;
         A[i + q * ld] = sn * aip + c * aiq;
@@ -160,12 +162,11 @@ __global__ void __launch_bounds__(kBlock) psd_small_kernel(const PsdConeDesc* __
       __syncthreads();
       // rows p,q of A
       for (int e = threadIdx.x; e < npairs * N; e += blockDim.x) {
-        const int k = e / N, j = e % N;
+        const int k = e / N, j = e - k * N;
         const T sn = cs[2 * k + 1];
         if (sn == T(0)) continue;
         const T c = cs[2 * k];
-        int p, q;
-        rr_pair(Ne, r, k, p, q);
+        const int p = pq[2 * k], q = pq[2 * k + 1];
         const T apj = A[p + j * ld], aqj = A[q + j * ld];
         A[p + j * ld] = c * apj - sn * aqj;
         A[q + j * ld] = sn * apj + c * aqj;
@@ -361,6 +362,7 @@ __global__ void __launch_bounds__(512) bj_pivot_kernel(int N, int Nb, int r, con
   T* Sv = Sa + ld * P;
   T* cs = Sv + ld * P;
   __shared__ int any_big, rot_flag, round_rot[2];
+  __shared__ int pq[kBjP];
   const int k = blockIdx.x;
   int I, J;
   rr_pair(Nb, r, k, I, J);
@@ -411,6 +413,8 @@ __global__ void __launch_bounds__(512) bj_pivot_kernel(int N, int Nb, int r, con
         }
         cs[2 * kk] = c;
         cs[2 * kk + 1] = sn;
+        pq[2 * kk] = p;
+        pq[2 * kk + 1] = q;
       }
       __syncthreads();
       if (!round_rot[f]) continue;   // nothing to rotate in this round (block-uniform)
@@ -419,8 +423,7 @@ __global__ void __launch_bounds__(512) bj_pivot_kernel(int N, int Nb, int r, con
         const T sn = cs[2 * kk + 1];
         if (sn == T(0)) continue;
         const T c = cs[2 * kk];
-        int p, q;
-        rr_pair(P, rr, kk, p, q);
+        const int p = pq[2 * kk], q = pq[2 * kk + 1];
         const T aip = Sa[i + p * ld], aiq = Sa[i + q * ld];
         Sa[i + p * ld] = c * aip - sn * aiq;
         Sa[i + q * ld] = sn * aip + c * aiq;
@@ -434,8 +437,7 @@ __global__ void __launch_bounds__(512) bj_pivot_kernel(int N, int Nb, int r, con
         const T sn = cs[2 * kk + 1];
         if (sn == T(0)) continue;
         const T c = cs[2 * kk];
-        int p, q;
-        rr_pair(P, rr, kk, p, q);
+        const int p = pq[2 * kk], q = pq[2 * kk + 1];
         const T apj = Sa[p + j * ld], aqj = Sa[q + j * ld];
         Sa[p + j * ld] = c * apj - sn * aqj;
         Sa[q + j * ld] = sn * apj + c * aqj;
