@@ -20,6 +20,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include <string>
 #include <vector>
@@ -576,6 +578,60 @@ __global__ void __launch_bounds__(kBlock, 1) bj_rows_kernel(int N, int Nb, int r
   }
 }
 
+// C (N x N) = op(A) * B, column-major, op(A) = A or A'; 128x128 CTA tile, 8x8 register micro-tiles,
+// K in chunks of 16 through shared memory.  Used for the warm start  A <- V0' (X V0).
+template <typename T, bool TRANSA>
+__global__ void __launch_bounds__(kBlock, 1) bj_gemm_kernel(int N, const T* __restrict__ A, const T* __restrict__ B,
+                                                            T* __restrict__ C) {
+  constexpr int TM = 128, TK = 16, LDS_ = TM + 2;
+  __shared__ __align__(16) T As[TK][LDS_];   // As[kk][i] = op(A)[row0 + i][k0 + kk]
+  __shared__ __align__(16) T Bs[TK][LDS_];   // Bs[kk][j] = B[k0 + kk][col0 + j]
+  const int row0 = blockIdx.x * TM, col0 = blockIdx.y * TM;
+  const int ti = (threadIdx.x % 16) * 8, tj = (threadIdx.x / 16) * 8;
+  T acc[8][8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[a][b] = T(0);
+  for (int k0 = 0; k0 < N; k0 += TK) {
+    for (int e = threadIdx.x; e < TK * TM; e += blockDim.x) {
+      int kk, i;
+      if (TRANSA) { kk = e % TK; i = e / TK; } else { i = e % TM; kk = e / TM; }
+      const int gi = row0 + i, gk = k0 + kk;
+      T v = T(0);
+      if (gi < N && gk < N) v = TRANSA ? A[gk + (long long)gi * N] : A[gi + (long long)gk * N];
+      As[kk][i] = v;
+    }
+    for (int e = threadIdx.x; e < TK * TM; e += blockDim.x) {
+      const int kk = e % TK, j = e / TK;
+      const int gk = k0 + kk, gj = col0 + j;
+      Bs[kk][j] = (gk < N && gj < N) ? B[gk + (long long)gj * N] : T(0);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int kk = 0; kk < TK; ++kk) {
+      T av[8], bv[8];
+      bj_load8(&As[kk][ti], av);
+      bj_load8(&Bs[kk][tj], bv);
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc[a][b] += av[a] * bv[b];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const int gj = col0 + tj + b;
+    if (gj >= N) continue;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      const int gi = row0 + ti + a;
+      if (gi < N) C[gi + (long long)gj * N] = acc[a][b];
+    }
+  }
+}
+
 // V[:,k] *= sqrt(max(lambda_k, 0))
 template <typename T>
 __global__ void __launch_bounds__(kBlock) psd_large_scale_kernel(int N, const T* __restrict__ A, T* __restrict__ V) {
@@ -655,13 +711,20 @@ struct PsdBatch {
   T *A_d = nullptr, *V_d = nullptr, *cs_d = nullptr, *fro_d = nullptr, *thr_d = nullptr, *lam_large_d = nullptr;
   int* rot_d = nullptr;
   int* rot_h = nullptr;  // pinned
+  // warm start across ADMM iterations (single large cone): eigenvectors of the previous projection
+  T *Vw_d = nullptr, *T_d = nullptr;
+  bool warm_valid = false;
+  int warm_N = 0;
+  long long warm_count = 0;
+  bool warm_enabled = true;
+  int last_sweeps = 0;
   T* R_d = nullptr;      // npairs * 64 * 64 pivot rotations
   int* act_d = nullptr;  // per pair: pivot needed work this round
   std::vector<T> lam_host;
 
   ~PsdBatch() {
     cudaFree(small_d); cudaFree(lam_small_d); cudaFree(fail_d); cudaFree(A_d); cudaFree(V_d); cudaFree(cs_d);
-    cudaFree(fro_d); cudaFree(thr_d); cudaFree(lam_large_d); cudaFree(rot_d); cudaFree(R_d); cudaFree(act_d);
+    cudaFree(fro_d); cudaFree(thr_d); cudaFree(lam_large_d); cudaFree(rot_d); cudaFree(R_d); cudaFree(act_d); cudaFree(Vw_d); cudaFree(T_d);
     if (rot_h) cudaFreeHost(rot_h);
   }
   bool empty() const { return small_h.empty() && large_h.empty(); }
@@ -692,6 +755,14 @@ struct PsdBatch {
       ck(cudaMalloc(&thr_d, sizeof(T)), "cudaMalloc thr");
       ck(cudaMalloc(&lam_large_d, large_h.size() * sizeof(T)), "cudaMalloc lam");
       ck(cudaMalloc(&rot_d, sizeof(int)), "cudaMalloc rot");
+      {
+        const char* e = getenv("COSMO_B200_PSD_WARM");
+        warm_enabled = !(e && e[0] == '0');
+      }
+      if (large_h.size() == 1 && warm_enabled) {
+        ck(cudaMalloc(&Vw_d, nn * sizeof(T)), "cudaMalloc psd Vw");
+        ck(cudaMalloc(&T_d, nn * sizeof(T)), "cudaMalloc psd T");
+      }
       ck(cudaMallocHost(&rot_h, sizeof(int)), "cudaMallocHost rot");
       int Nb = (large_maxN + kBjB - 1) / kBjB;
       if (Nb & 1) ++Nb;
@@ -709,10 +780,11 @@ struct PsdBatch {
     const size_t ld = (size_t)(small_maxN | 1);
     return (2 * ld * small_maxN + 2 * (size_t)(small_maxN / 2 + 2)) * sizeof(T);
   }
-  void reset_warm_start() {}
+  void reset_warm_start() { warm_valid = false; warm_count = 0; }
 
   // eigen-decompose one large cone into A_d (diagonal = eigenvalues) and V_d (block Jacobi)
-  void large_eig(const PsdConeDesc& d, const T* ws, cudaStream_t st, int max_sweeps, long long& launches) {
+  void large_eig(const PsdConeDesc& d, const T* ws, cudaStream_t st, int max_sweeps, long long& launches,
+                 bool allow_warm = false) {
     const int N = d.N;
     int Nb = (N + kBjB - 1) / kBjB;
     if (Nb & 1) ++Nb;                                 // even number of blocks (zero padding decouples)
@@ -721,11 +793,23 @@ struct PsdBatch {
     psd_large_load_kernel<T><<<g, kBlock, 0, st>>>(d, ws, A_d, V_d, fro_d);
     psd_large_thr_kernel<T><<<1, 32, 0, st>>>(fro_d, g, thr_d, rot_d);
     launches += 2;
+    // Warm start (ADMM iterates move slowly): rotate X into the eigenbasis of the previous projection,
+    // A <- V0' X V0 is then nearly diagonal and a couple of sweeps finish the job; V starts at V0.
+    // A cold start every 16th call bounds the drift of V's orthogonality.
+    const bool warm = allow_warm && Vw_d && warm_valid && warm_N == N && (warm_count % 16 != 0);
+    if (warm) {
+      dim3 gg((N + 127) / 128, (N + 127) / 128);
+      bj_gemm_kernel<T, false><<<gg, kBlock, 0, st>>>(N, A_d, Vw_d, T_d);     // T = X V0
+      bj_gemm_kernel<T, true><<<gg, kBlock, 0, st>>>(N, Vw_d, T_d, A_d);      // A = V0' T
+      ck(cudaMemcpyAsync(V_d, Vw_d, (size_t)N * N * sizeof(T), cudaMemcpyDeviceToDevice, st), "copy V0");
+      launches += 2;
+    }
     const size_t smem_pivot = (2 * (size_t)(kBjP + 1) * kBjP + kBjP + 2) * sizeof(T);
     const size_t smem_upd = ((size_t)kBjP * kBjP + (size_t)kBjTilesPerCta * kBjLd * kBjP) * sizeof(T);
     const int tiles = (N + kBjP * kBjTilesPerCta - 1) / (kBjP * kBjTilesPerCta);
     bool converged = false;
-    for (int sweep = 0; sweep < max_sweeps && !converged; ++sweep) {
+    int sweep = 0;
+    for (; sweep < max_sweeps && !converged; ++sweep) {
       for (int r = 0; r < Nb - 1; ++r) {
         bj_pivot_kernel<T><<<npairs, 512, smem_pivot, st>>>(N, Nb, r, A_d, thr_d, R_d, act_d, rot_d, 1);
         bj_cols_kernel<T><<<dim3(tiles, npairs, 2), kBlock, smem_upd, st>>>(N, Nb, r, A_d, V_d, R_d, act_d);
@@ -737,8 +821,16 @@ struct PsdBatch {
       ck(cudaStreamSynchronize(st), "sync");
       if (*rot_h == 0) converged = true;
     }
+    last_sweeps = sweep;
+    if (getenv("COSMO_B200_PSD_DEBUG")) fprintf(stderr, "[psd] N=%d warm=%d sweeps=%d\n", N, (int)warm, sweep);
     ck(cudaGetLastError(), "psd block-Jacobi kernels");
     if (!converged) throw PsdError{"block Jacobi eigensolver did not converge within psd_max_sweeps"};
+    if (allow_warm && Vw_d) {
+      ck(cudaMemcpyAsync(Vw_d, V_d, (size_t)N * N * sizeof(T), cudaMemcpyDeviceToDevice, st), "save V0");
+      warm_valid = true;
+      warm_N = N;
+      ++warm_count;
+    }
   }
 
   // s[cone rows] = Pi_PSD(ws[cone rows]) for every PSD cone
@@ -751,7 +843,7 @@ struct PsdBatch {
       ++launches;
     }
     for (const auto& d : large_h) {
-      large_eig(d, ws, st, max_sweeps, launches);
+      large_eig(d, ws, st, max_sweeps, launches, /*allow_warm=*/true);
       const int N = d.N;
       const int g = (int)std::min<long long>(((long long)N * N + kBlock - 1) / kBlock, kMaxGrid);
       psd_large_scale_kernel<T><<<g, kBlock, 0, st>>>(N, A_d, V_d);

@@ -17,5 +17,10 @@ for N in [int(a) for a in sys.argv[1:]] or [200, 500, 1000, 2000]:
     # a nearby matrix (ADMM-like small change)
     ws2 = got + 1e-3 * rng.standard_normal(d)
     t0 = time.time(); got2 = eng.project(ws2); tgpu2 = time.time() - t0
+    ref2 = ws2.copy(); O.project(ref2, cosmo_b200.problems.to_oracle_cones(sets))
+    err2 = np.linalg.norm(got2 - ref2) / np.linalg.norm(ws2)
+    ws3 = got2 + 1e-5 * rng.standard_normal(d)
+    t0 = time.time(); got3 = eng.project(ws3); tgpu3 = time.time() - t0
+    print("   nearby relerr %.2e, third (1e-5 away) %.3fs" % (err2, tgpu3))
     print("N=%d  cpu dsyevr+syrk %.3fs  gpu %.3fs (nearby %.3fs)  relerr %.2e" % (
         N, tcpu, tgpu, tgpu2, np.linalg.norm(got - ref) / np.linalg.norm(ws)), flush=True)
