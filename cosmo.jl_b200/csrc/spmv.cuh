@@ -140,30 +140,12 @@ __device__ __forceinline__ T win_fma8(const T (&v)[8], const uint4& c, const T* 
   return s0 + s1;
 }
 
-// steps beyond the first 256 entries of a row segment (long rows, e.g. dense factor rows of a
-// portfolio model): two 256-entry steps are kept in flight per warp so that a handful of long rows
-// per SM still pull enough bytes to cover the HBM latency.
+// steps beyond the first 256 entries of a row segment (long rows)
 template <typename T>
 __device__ __forceinline__ T win_row_rest(const unsigned short* __restrict__ col, const T* __restrict__ val, const T* xs,
                                           int start, int end, int lane) {
   T s = 0;
-  int j0 = start + 256;
-  for (; j0 + 256 < end; j0 += 512) {          // two steps per trip (the first one is always full)
-    const int L1 = min(32, (end - (j0 + 256)) >> 3);
-    const uint4 c0 = __ldcs(reinterpret_cast<const uint4*>(col + j0 + lane * 8));
-    T v0[8], v1[8];
-    load8_coalesced(val + j0, 32, lane, v0);
-    uint4 c1 = make_uint4(0, 0, 0, 0);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v1[i] = T(0);
-    if (lane < L1) {
-      c1 = __ldcs(reinterpret_cast<const uint4*>(col + j0 + 256 + lane * 8));
-      load8_coalesced(val + j0 + 256, L1, lane, v1);
-    }
-    s += win_fma8<T>(v0, c0, xs);
-    if (lane < L1) s += win_fma8<T>(v1, c1, xs);
-  }
-  if (j0 < end) {                               // one trailing step
+  for (int j0 = start + 256; j0 < end; j0 += 256) {
     const int L = min(32, (end - j0) >> 3);
     if (lane < L) {
       const uint4 c = __ldcs(reinterpret_cast<const uint4*>(col + j0 + lane * 8));
