@@ -956,19 +956,22 @@ template <typename T>
 void Engine<T>::kkt_op_stage2(const int* done, const T* u, const T* t_in, T* c_out, bool exchange) {
   const bool lead = (rank_ == 0);
   const bool px = exchange && p2p_;
+  const T sig = lead ? (T)st_.sigma : (T)0;
+  const DevCsr<T>* M2 = nullptr;
+  const T* pu = nullptr;
   if (At_.windowed) {
     // the slab kernel cannot walk P's rows without unbalancing its window-0 CTAs: P u goes first
-    const T* pu = nullptr;
     if (lead && P_.nnz > 0) {
       launch_spmv(P_, u, (const DevCsr<T>*)nullptr, (const T*)nullptr, n_, EpiStore<T>{done, vec_n2_.p}, red(SC_TMP0), "spmv_P");
       pu = vec_n2_.p;
     }
-    launch_spmv(At_, t_in, (const DevCsr<T>*)nullptr, (const T*)nullptr, n_,
-                EpiKktOp<T>{done, c_out, u, lead ? (T)st_.sigma : (T)0, pu, px, xv_, n_}, red_ptr(cb_.p + n_), "spmv_kkt_op");
-  } else {
-    launch_spmv(At_, t_in, lead ? &P_ : nullptr, u, n_,
-                EpiKktOp<T>{done, c_out, u, lead ? (T)st_.sigma : (T)0, nullptr, px, xv_, n_}, red_ptr(cb_.p + n_), "spmv_kkt_op");
+  } else if (lead) {
+    M2 = &P_;
   }
+  if (px)
+    launch_spmv(At_, t_in, M2, u, n_, EpiKktOpX<T>{done, u, sig, pu, xv_, n_}, red_ptr(cb_.p + n_), "spmv_kkt_op");
+  else
+    launch_spmv(At_, t_in, M2, u, n_, EpiKktOp<T>{done, c_out, u, sig, pu}, red_ptr(cb_.p + n_), "spmv_kkt_op");
 }
 
 template <typename T>

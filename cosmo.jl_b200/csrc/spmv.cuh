@@ -309,12 +309,28 @@ struct EpiKktOp {
   const T* u;
   T sigma;
   const T* add;   // optional precomputed P u (nullptr: P rows are traversed by the same kernel)
-  // row-sharded runs: write the partial into this rank's exchange slot and publish it to the peers
-  // (the consumer kernels sum the slots; no separate allreduce launch)
-  bool p2p;
+  __device__ void row(int r, T s, T* accS, T*) const {
+    const T ur = u[r];
+    const T v = (add ? s + add[r] : s) + sigma * ur;
+    c[r] = v;
+    accS[0] += ur * v;
+  }
+  __device__ void operator()(T*) const {}
+};
+
+// Same operator, row-sharded peer-exchange variant: the partial goes into this rank's exchange slot
+// and is published to the peers from the kernel's scalar epilogue (the consumer kernels sum the slots;
+// no separate allreduce launch).
+template <typename T>
+struct EpiKktOpX {
+  static constexpr int NS = 1, NM = 0;
+  const int* done;
+  const T* u;
+  T sigma;
+  const T* add;
   P2pView<T> x;
   int n;
-  __device__ T* target() const { return p2p ? const_cast<T*>(x.peer_data[x.rank]) + (size_t)(*x.seq & 1u) * x.stride : c; }
+  __device__ T* target() const { return const_cast<T*>(x.peer_data[x.rank]) + (size_t)(*x.seq & 1u) * x.stride; }
   __device__ void row(int r, T s, T* accS, T*) const {
     const T ur = u[r];
     const T v = (add ? s + add[r] : s) + sigma * ur;
@@ -322,7 +338,6 @@ struct EpiKktOp {
     accS[0] += ur * v;
   }
   __device__ void operator()(T* out) const {   // last block, one thread: out[0] = partial u'c
-    if (!p2p) return;
     const unsigned sq = *x.seq;
     target()[n] = out[0];
     p2p_publish(x, sq & 1u, sq + 1u);
