@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcosmo_b200.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["common.cuh", "spmv.cuh", "vector_kernels.cuh", "psd.cuh", "../../include/cosmo_b200.h"]
+HEADERS = ["common.cuh", "spmv.cuh", "vector_kernels.cuh", "psd.cuh", "cg_persistent.cuh", "../../include/cosmo_b200.h"]
 
 
 def _stale():

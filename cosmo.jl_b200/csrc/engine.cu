@@ -27,6 +27,7 @@
 #include "psd.cuh"
 #include "spmv.cuh"
 #include "vector_kernels.cuh"
+#include "cg_persistent.cuh"
 
 namespace cosmo {
 
@@ -229,6 +230,13 @@ class Engine : public EngineBase {
   cudaGraphExec_t cg_graph_[4] = {nullptr, nullptr, nullptr, nullptr};
   bool use_graphs_ = true;
   bool graph_multi_ = true;
+  // persistent cooperative CG kernel for launch-latency-bound (small / medium, non-windowed) problems
+  bool use_persistent_ = true;
+  int persist_grid_ = 0, persist_lanes_ = 0;
+  DevBuf<T> persist_part_;
+  long long persist_solves_ = 0;
+  bool persistent_cg_ok();
+  void launch_persistent_cg(double tol_num);
   void cg_iteration_launches(const int* done);
   void build_cg_graphs(const int* done);
   void destroy_cg_graphs();
@@ -582,6 +590,8 @@ Engine<T>::Engine(const cosmo_b200_problem& p, const cosmo_b200_settings& st) : 
     use_windows_ = !(e && e[0] == '1');
     const char* ng = getenv("COSMO_B200_NO_GRAPH");
     use_graphs_ = !(ng && ng[0] == '1');
+    const char* np_ = getenv("COSMO_B200_NO_PERSISTENT");
+    use_persistent_ = !(np_ && np_[0] == '1');
     const char* gm = getenv("COSMO_B200_GRAPH_MULTI");
     graph_multi_ = !(gm && gm[0] == '0');
     const char* g = getenv("COSMO_B200_WIN_GROUP");
@@ -1024,6 +1034,10 @@ void Engine<T>::kkt_core(bool fused_tail, const T* w_src, T* w_dst) {
 template <typename T>
 void Engine<T>::kkt_cg(const int* done) {
   set_maxit(n_);   // IterativeSolvers default maxiter = size(A, 2)
+  if (persistent_cg_ok()) {
+    launch_persistent_cg(st_.tol_constant / pow((double)kkt_counter_, st_.tol_exponent));
+    return;
+  }
   // c = L x0 (warm start => one product for the initial residual)
   launch_spmv(A_, xsol_.p, (const DevCsr<T>*)nullptr, (const T*)nullptr, m_, EpiScale<T>{nullptr, tm_.p, rho_vec_.p},
               red(SC_TMP0), "spmv_A_scale");
@@ -1058,6 +1072,46 @@ void Engine<T>::kkt_cg(const int* done) {
   last_cg_iters_ = iters;
   total_inner_ += iters;
   total_mults_ += 1 + iters;
+}
+
+template <typename T>
+bool Engine<T>::persistent_cg_ok() {
+  if (!use_persistent_ || nranks_ != 1 || A_.windowed || At_.windowed) return false;
+  const long long work = A_.nnz + At_.nnz + P_.nnz + 4LL * ((long long)n_ + m_);
+  if (work > 6000000LL) return false;           // bigger problems are bandwidth-bound: separate kernels win
+  if (persist_grid_ == 0) {
+    int coop = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device_));
+    if (!coop) { persist_grid_ = -1; return false; }
+    const int la = std::max(A_.lanes, At_.lanes);
+    persist_lanes_ = la;
+    int nb = 0;
+    if (la == 32) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cg_persistent_kernel<T, 32>, kBlock, 0));
+    else if (la == 8) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cg_persistent_kernel<T, 8>, kBlock, 0));
+    else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cg_persistent_kernel<T, 2>, kBlock, 0));
+    const long long per = kBlock / la;
+    const long long need = std::max<long long>(1, (std::max(n_, m_) + per - 1) / per);
+    persist_grid_ = (int)std::max<long long>(1, std::min<long long>((long long)nb * num_sms_, need));
+    if (nb <= 0) { persist_grid_ = -1; return false; }
+    persist_part_.alloc((size_t)persist_grid_ * 4);
+  }
+  return persist_grid_ > 0;
+}
+
+template <typename T>
+void Engine<T>::launch_persistent_cg(double tol_num) {
+  CgPersistArgs<T> a;
+  a.A = A_.view(); a.At = At_.view(); a.P = P_.view();
+  a.n = n_; a.m = m_;
+  a.rhs = rhsb_.p; a.rho = rho_vec_.p; a.x = xsol_.p; a.r = r_.p; a.u = u_.p; a.tm = tm_.p; a.c = cb_.p;
+  a.partA = persist_part_.p; a.partB = persist_part_.p + (size_t)persist_grid_ * 2;
+  a.sc = sc_.p; a.isc = isc_.p; a.sigma = (T)st_.sigma; a.tol_num = (T)tol_num;
+  void* args[] = {&a};
+  const void* fn = persist_lanes_ == 32 ? (const void*)cg_persistent_kernel<T, 32>
+                 : persist_lanes_ == 8 ? (const void*)cg_persistent_kernel<T, 8> : (const void*)cg_persistent_kernel<T, 2>;
+  CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(persist_grid_), dim3(kBlock), args, 0, stream_));
+  check_launch("cg_persistent");
+  ++persist_solves_;
 }
 
 // one CG iteration: u = r + beta u ; c = L u ; alpha = res^2/u'c ; x += alpha u ; r -= alpha c
@@ -1305,6 +1359,8 @@ void Engine<T>::solve(cosmo_b200_result* out) {
   const int n = n_, m = m_;
   const long long launches0 = launches_;
   total_inner_ = 0; total_mults_ = 0;
+  persist_solves_ = 0;
+  CUDA_TRY(cudaMemsetAsync(isc_.p + ISC_TOTAL, 0, sizeof(int), stream_));
   int status = COSMO_B200_UNDETERMINED;
   double cost = INFINITY;
   double info[5] = {INFINITY, INFINITY, 0.0, 0.0, INFINITY};
@@ -1424,6 +1480,12 @@ void Engine<T>::solve(cosmo_b200_result* out) {
     compute_residuals(W_[prev_].p, s_.p, mu_.p, false, info);
     status = COSMO_B200_MAX_ITER_REACHED;
   }
+  if (persist_solves_ > 0) {   // inner-iteration statistics of the persistent CG kernel live on the device
+    CUDA_TRY(cudaMemcpyAsync(h_isc_ + ISC_TOTAL, isc_.p + ISC_TOTAL, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    sync();
+    total_inner_ += h_isc_[ISC_TOTAL];
+    total_mults_ += h_isc_[ISC_TOTAL] + persist_solves_;
+  }
   // x = view(w_prev, 1:n): keep it for the next warm start and hand it out
   CUDA_TRY(cudaMemcpyAsync(xs_.p, W_[prev_].p, n * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
   if (out) {
@@ -1476,7 +1538,11 @@ void Engine<T>::kkt_solve(const void* rhs, void* sol, int64_t* inner) {
   download_vec(sol, xsol_.p, n_);
   download_vec(static_cast<T*>(sol) + n_, nu_.p, m_);
   sync();
-  if (inner) *inner = last_cg_iters_;
+  if (inner) {
+    CUDA_TRY(cudaMemcpyAsync(h_isc_, isc_.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    sync();
+    *inner = h_isc_[ISC_IT];
+  }
 }
 
 template <typename T>

@@ -19,9 +19,18 @@
 
 namespace cosmo {
 
+// Gather of the dense operand: through the read-only (non-coherent) path when the vector is constant
+// for the lifetime of the kernel, through L2 (ld.global.cg) when the same kernel also writes it
+// (the persistent CG kernel re-reads vectors across grid barriers).
+template <typename T, bool NC>
+__device__ __forceinline__ T gather_ld(const T* p) {
+  if (NC) return __ldg(p);
+  return __ldcg(p);
+}
+
 // Partial dot product of one CSR row with a dense vector, LANES cooperating
 // lanes (32 => vectorised stream path).  Returns this lane's partial sum.
-template <typename T, int LANES>
+template <typename T, int LANES, bool NC = true>
 __device__ __forceinline__ T row_partial(const CsrView<T>& M, const T* __restrict__ x, int row, int lane) {
   const int start = __ldg(M.rowptr + row);
   const int end = __ldg(M.rowptr + row + 1);
@@ -31,7 +40,7 @@ __device__ __forceinline__ T row_partial(const CsrView<T>& M, const T* __restric
     if (a0 > end) a0 = end;
     {  // head: < 4 unaligned elements
       const int i = start + lane;
-      if (i < a0) s0 += __ldcs(M.val + i) * __ldg(x + __ldcs(M.col + i));
+      if (i < a0) s0 += __ldcs(M.val + i) * gather_ld<T, NC>(x + __ldcs(M.col + i));
     }
     const int body_end = a0 + ((end - a0) & ~3);
 #pragma unroll 2
@@ -39,17 +48,17 @@ __device__ __forceinline__ T row_partial(const CsrView<T>& M, const T* __restric
       const int4 c = load4_stream(M.col + j);
       T v[4];
       load4_stream(M.val + j, v);
-      s0 += v[0] * __ldg(x + c.x);
-      s1 += v[1] * __ldg(x + c.y);
-      s0 += v[2] * __ldg(x + c.z);
-      s1 += v[3] * __ldg(x + c.w);
+      s0 += v[0] * gather_ld<T, NC>(x + c.x);
+      s1 += v[1] * gather_ld<T, NC>(x + c.y);
+      s0 += v[2] * gather_ld<T, NC>(x + c.z);
+      s1 += v[3] * gather_ld<T, NC>(x + c.w);
     }
     {  // tail: < 4 elements
       const int i = body_end + lane;
-      if (i < end) s1 += __ldcs(M.val + i) * __ldg(x + __ldcs(M.col + i));
+      if (i < end) s1 += __ldcs(M.val + i) * gather_ld<T, NC>(x + __ldcs(M.col + i));
     }
   } else {
-    for (int j = start + lane; j < end; j += LANES) s0 += __ldcs(M.val + j) * __ldg(x + __ldcs(M.col + j));
+    for (int j = start + lane; j < end; j += LANES) s0 += __ldcs(M.val + j) * gather_ld<T, NC>(x + __ldcs(M.col + j));
   }
   return s0 + s1;
 }
