@@ -232,7 +232,7 @@ class Engine : public EngineBase {
   bool graph_multi_ = true;
   // persistent cooperative CG kernel for launch-latency-bound (small / medium, non-windowed) problems
   bool use_persistent_ = true;
-  int persist_grid_ = 0, persist_lanes_ = 0;
+  int persist_grid_ = 0, persist_lanes_ = 0, persist_ctas_per_sm_ = 2;
   DevBuf<T> persist_part_;
   long long persist_solves_ = 0;
   bool persistent_cg_ok();
@@ -592,6 +592,8 @@ Engine<T>::Engine(const cosmo_b200_problem& p, const cosmo_b200_settings& st) : 
     use_graphs_ = !(ng && ng[0] == '1');
     const char* np_ = getenv("COSMO_B200_NO_PERSISTENT");
     use_persistent_ = !(np_ && np_[0] == '1');
+    const char* pc = getenv("COSMO_B200_PERSIST_CTAS");
+    if (pc && atoi(pc) > 0) persist_ctas_per_sm_ = atoi(pc);
     const char* gm = getenv("COSMO_B200_GRAPH_MULTI");
     graph_multi_ = !(gm && gm[0] == '0');
     const char* g = getenv("COSMO_B200_WIN_GROUP");
@@ -1091,7 +1093,8 @@ bool Engine<T>::persistent_cg_ok() {
     else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cg_persistent_kernel<T, 2>, kBlock, 0));
     const long long per = kBlock / la;
     const long long need = std::max<long long>(1, (std::max(n_, m_) + per - 1) / per);
-    persist_grid_ = (int)std::max<long long>(1, std::min<long long>((long long)nb * num_sms_, need));
+    // a grid barrier costs more the more CTAs take part: at most two CTAs per SM
+    persist_grid_ = (int)std::max<long long>(1, std::min<long long>(std::min<long long>((long long)nb, persist_ctas_per_sm_) * num_sms_, need));
     if (nb <= 0) { persist_grid_ = -1; return false; }
     persist_part_.alloc((size_t)persist_grid_ * 4);
   }
