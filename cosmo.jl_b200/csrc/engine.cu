@@ -1302,14 +1302,18 @@ bool Engine<T>::primal_infeasible() {
   }
   const bool psd_ok = psd_.certificate(dy_.p, /*negate=*/true, (double)eps, stream_, st_.psd_max_sweeps, launches_);
   (void)flag;
+  // the PSD verdict is a host bool of THIS rank: put it next to the device flags so that the
+  // max-allreduce makes every rank take the same decision
+  h_sc_[SC_TMP4] = psd_ok ? T(0) : T(1);
+  CUDA_TRY(cudaMemcpyAsync(sc_.p + SC_TMP4, h_sc_ + SC_TMP4, sizeof(T), cudaMemcpyHostToDevice, stream_));
   if (nranks_ > 1) {
     allreduce_sum(sc_.p + SC_TMP0, 2);   // dy'b, box support sum
-    allreduce_max(sc_.p + SC_TMP2, 2);   // flags
+    allreduce_max(sc_.p + SC_TMP2, 3);   // flags: rows, SOC, PSD
   }
-  read_scalars(SC_TMP0, 4);
+  read_scalars(SC_TMP0, 5);
   const double dyt_b = (double)h_sc_[SC_TMP0];
   const double box_sum = (double)h_sc_[SC_TMP1];
-  const bool cone_bad = (h_sc_[SC_TMP2] != 0) || (h_sc_[SC_TMP3] != 0) || !psd_ok;
+  const bool cone_bad = (h_sc_[SC_TMP2] != 0) || (h_sc_[SC_TMP3] != 0) || (h_sc_[SC_TMP4] != 0);
   const double sF = (cone_bad ? INFINITY : 0.0) + box_sum - dyt_b;
   return sF <= st_.eps_prim_inf;
 }
@@ -1347,9 +1351,11 @@ bool Engine<T>::dual_infeasible() {
     CUDA_TRY(cudaMemsetAsync(sc_.p + SC_TMP3, 0, sizeof(T), stream_));
   }
   const bool psd_ok = psd_.certificate(vec_m_.p, /*negate=*/true, (double)eps, stream_, st_.psd_max_sweeps, launches_);
-  if (nranks_ > 1) allreduce_max(sc_.p + SC_TMP2, 2);
-  read_scalars(SC_TMP2, 2);
-  return (h_sc_[SC_TMP2] == 0) && (h_sc_[SC_TMP3] == 0) && psd_ok;
+  h_sc_[SC_TMP4] = psd_ok ? T(0) : T(1);
+  CUDA_TRY(cudaMemcpyAsync(sc_.p + SC_TMP4, h_sc_ + SC_TMP4, sizeof(T), cudaMemcpyHostToDevice, stream_));
+  if (nranks_ > 1) allreduce_max(sc_.p + SC_TMP2, 3);
+  read_scalars(SC_TMP2, 3);
+  return (h_sc_[SC_TMP2] == 0) && (h_sc_[SC_TMP3] == 0) && (h_sc_[SC_TMP4] == 0);
 }
 
 // ---------------------------------------------------------------------------
