@@ -96,6 +96,48 @@ class PsdConeTriangle:  # convexset.jl:362-377 (svec upper triangle)
         return (math.isqrt(1 + 8 * self.dim) - 1) // 2
 
 
+@dataclass
+class ExponentialCone:  # convexset.jl:497-507  K_exp = cl{(x,y,z) | y > 0, y e^(x/y) <= z}
+    dim: int = 3
+    MAX_ITER: int = 100
+    EXP_TOL: float = 1e-8
+
+
+@dataclass
+class DualExponentialCone:  # convexset.jl:749-758
+    dim: int = 3
+    MAX_ITER: int = 100
+    EXP_TOL: float = 1e-8
+
+
+@dataclass
+class PowerCone:  # convexset.jl:625-636  K_pow = {(x,y,z) | x^a y^(1-a) >= |z|, x,y >= 0}
+    alpha: float
+    MAX_ITER: int = 20
+    POW_TOL: float = 1e-8
+    dim: int = 3
+
+    def __post_init__(self):
+        if self.alpha <= 0 or self.alpha >= 1:
+            raise ValueError("The exponent alpha of the power cone has to be in (0, 1).")
+
+
+@dataclass
+class DualPowerCone:  # convexset.jl:765-775
+    alpha: float
+    MAX_ITER: int = 20
+    POW_TOL: float = 1e-8
+    dim: int = 3
+
+    def __post_init__(self):
+        if self.alpha <= 0 or self.alpha >= 1:
+            raise ValueError("The exponent alpha of the dual power cone has to be in (0, 1).")
+
+
+SCALAR_SCALED_CONES = (SecondOrderCone, PsdCone, PsdConeTriangle, ExponentialCone, DualExponentialCone, PowerCone,
+                       DualPowerCone)  # rectify_scaling!, convexset.jl:955-957
+
+
 def row_ranges(cones) -> List[slice]:
     """get_set_indices, convexset.jl:985-993."""
     out, s = [], 0
@@ -153,6 +195,139 @@ def _psd_project_upper(X: np.ndarray) -> np.ndarray:
     return out
 
 
+# ---- 3-d exponential / power cones (convexset.jl:510-747) -------------------
+def _exp_in_cone(v, tol):  # convexset.jl:600-605
+    x, y, z = v
+    with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+        return bool((y > 0 and y * np.exp(x / y) <= z + tol) or (x <= tol and y == 0.0 and z >= -tol))
+
+
+def _exp_in_dual(v, tol):  # convexset.jl:607-612
+    x, y, z = v
+    with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+        return bool((x < 0 and -x * np.exp(y / x) - math.e * z <= tol) or (abs(x) <= tol and y >= -tol and z >= -tol))
+
+
+def _exp_find_min_t(lam, s0, t0, tol):  # find_min_t, convexset.jl:578-597 (Newton on dt = t - t0)
+    dt = max(-t0, tol)
+    for _ in range(150):
+        f = dt * (dt + t0) / lam ** 2 - s0 / lam + math.log(dt / lam) + 1.0
+        grad_f = (2.0 * dt + t0) / lam ** 2 + 1.0 / dt
+        dt = dt - f / grad_f
+        if dt <= -t0:
+            dt = -t0
+            break
+        elif dt <= 0:
+            dt = 0.0
+            break
+        elif abs(f) < tol:
+            break
+    return dt + t0
+
+
+def _exp_grad_dual(lam, v, v0, tol):  # grad_dual! + find_minimizers!, convexset.jl:559-573
+    v[2] = _exp_find_min_t(lam, v0[1], v0[2], tol)
+    v[1] = (1.0 / lam) * (v[2] - v0[2]) * v[2]
+    v[0] = v0[0] - lam
+    if v[1] == 0:
+        return v[0]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return v[0] + v[1] * np.log(v[1] / v[2])
+
+
+def _project_exp(v, cone):  # project!, convexset.jl:510-532
+    if _exp_in_cone(v, 0.0):
+        return
+    if _exp_in_dual(-v, 0.0):
+        v[:] = 0.0
+        return
+    if v[0] < 0 and v[1] < 0:
+        v[1] = 0.0
+        v[2] = max(v[2], 0.0)
+        return
+    # project_exp!, convexset.jl:537-557: bisection on the dual variable lambda
+    v0 = v.copy()
+    tol = cone.EXP_TOL
+    l, lam = 0.0, 0.125
+    g = _exp_grad_dual(lam, v, v0, tol)
+    while g > 0:
+        l = lam
+        lam *= 2
+        g = _exp_grad_dual(lam, v, v0, tol)
+    u = lam
+    for _ in range(cone.MAX_ITER):
+        lam = (u + l) / 2
+        g = _exp_grad_dual(lam, v, v0, tol)
+        if g > 0:
+            l = lam
+        else:
+            u = lam
+        if u - l < tol:
+            break
+
+
+def _pow_in_cone(v, alpha, tol):  # convexset.jl:719-725
+    x, y, z = v
+    return bool(x >= 0 and y >= 0 and x ** alpha * y ** (1 - alpha) >= abs(z) - tol)
+
+
+def _pow_in_dual(v, alpha, tol):  # convexset.jl:728-734  (NaN powers of negative s, t compare false)
+    s_, t_, w_ = v
+    if not (s_ >= -tol and t_ >= -tol):
+        return False
+    if s_ < 0 or t_ < 0:
+        return False  # Julia raises a DomainError here; unreachable for tol = 0
+    return bool(s_ ** alpha * t_ ** (1 - alpha) >= abs(w_) * alpha ** alpha * (1 - alpha) ** (1 - alpha) - tol)
+
+
+def _project_pow(v, cone):  # project!, convexset.jl:646-712
+    a = cone.alpha
+    if _pow_in_cone(v, a, 0.0):
+        return
+    if _pow_in_dual(-v, a, 0.0):
+        v[:] = 0.0
+        return
+    if abs(v[2]) <= cone.POW_TOL:
+        v[0] = max(v[0], 0.0)
+        v[1] = max(v[1], 0.0)
+        return
+    x0, y0, z0 = float(v[0]), float(v[1]), float(v[2])
+    az = abs(z0)
+
+    def phic(c0, r, al):  # convexset.jl:698-700
+        return max(0.5 * (c0 + math.sqrt(c0 * c0 + 4.0 * al * r * (az - r))), 1e-10)
+
+    r = az / 2.0
+    px = py = 0.0
+    for _ in range(cone.MAX_ITER):
+        px = phic(x0, r, a)
+        py = phic(y0, r, 1.0 - a)
+        pw = px ** a * py ** (1.0 - a)
+        phi = pw - r
+        if abs(phi) < cone.POW_TOL:
+            break
+        dpx = a / (2.0 * px - x0) * (az - 2.0 * r)           # convexset.jl:702-704
+        dpy = (1.0 - a) / (2.0 * py - y0) * (az - 2.0 * r)
+        dphi = pw * (a * dpx / px + (1.0 - a) * dpy / py) - 1.0   # convexset.jl:711-713
+        r = r - phi / dphi
+        r = min(max(r, 0.0), az)
+    v[0] = px
+    v[1] = py
+    v[2] = z0 * r / az
+
+
+def in_cone(x, cone, tol) -> bool:
+    if isinstance(cone, ExponentialCone):
+        return _exp_in_cone(x, tol)
+    if isinstance(cone, DualExponentialCone):  # convexset.jl:779
+        return _exp_in_dual(x, tol)
+    if isinstance(cone, PowerCone):
+        return _pow_in_cone(x, cone.alpha, tol)
+    if isinstance(cone, DualPowerCone):
+        return _pow_in_dual(x, cone.alpha, tol)
+    raise TypeError(cone)
+
+
 def project_cone(x: np.ndarray, cone) -> None:
     """project!(x, cone) in place on a contiguous view."""
     if isinstance(cone, ZeroSet):  # convexset.jl:25-28
@@ -191,6 +366,19 @@ def project_cone(x: np.ndarray, cone) -> None:
             X = populate_upper_triangle(x, N, 1.0 / math.sqrt(2.0))
             Xp = _psd_project_upper(X)
             x[:] = extract_upper_triangle(Xp, math.sqrt(2.0))
+    elif isinstance(cone, ExponentialCone):
+        _project_exp(x, cone)
+    elif isinstance(cone, PowerCone):
+        _project_pow(x, cone)
+    elif isinstance(cone, (DualExponentialCone, DualPowerCone)):
+        # Moreau: Proj_K*(v) = v + Proj_K(-v), convexset.jl:784-789
+        v0 = x.copy()
+        x *= -1.0
+        if isinstance(cone, DualExponentialCone):
+            _project_exp(x, ExponentialCone(3, cone.MAX_ITER, cone.EXP_TOL))
+        else:
+            _project_pow(x, PowerCone(cone.alpha, cone.MAX_ITER, cone.POW_TOL))
+        x += v0
     else:
         raise TypeError("unsupported cone %r" % (cone,))
 
@@ -225,6 +413,14 @@ def in_dual(x, cone, tol) -> bool:
         return np.linalg.norm(x[1:]) <= (tol + x[0])
     if isinstance(cone, (PsdCone, PsdConeTriangle)):  # convexset.jl:324-329,415-419
         return _is_pos_def(_cone_matrix(x, cone), tol)
+    if isinstance(cone, ExponentialCone):
+        return _exp_in_dual(x, tol)
+    if isinstance(cone, PowerCone):
+        return _pow_in_dual(x, cone.alpha, tol)
+    if isinstance(cone, DualExponentialCone):  # convexset.jl:780: dual of the dual = primal
+        return _exp_in_cone(x, tol)
+    if isinstance(cone, DualPowerCone):
+        return _pow_in_cone(x, cone.alpha, tol)
     raise TypeError(cone)
 
 
@@ -239,6 +435,8 @@ def in_pol_recc(x, cone, tol) -> bool:
         return (not np.any((cone.u == np.inf) & (x > tol))) and (not np.any((cone.l == -np.inf) & (x < -tol)))
     if isinstance(cone, (PsdCone, PsdConeTriangle)):  # convexset.jl:331-336,421-425 + algebra.jl:235-238
         return _is_pos_def(-_cone_matrix(x, cone), tol)
+    if isinstance(cone, (ExponentialCone, PowerCone, DualExponentialCone, DualPowerCone)):
+        return in_dual(-x, cone, tol)  # convexset.jl:616-618, 740-742, 781
     raise TypeError(cone)
 
 
@@ -632,7 +830,7 @@ def scale_ruiz(P, q, A, b, cones, st: Settings):
     Ew = np.ones(m)
     changed = False
     for rng, cone in zip(row_ranges(cones), cones):
-        if isinstance(cone, (SecondOrderCone, PsdCone, PsdConeTriangle)):
+        if isinstance(cone, SCALAR_SCALED_CONES):
             tmp = np.mean(E[rng])
             Ew[rng] = tmp / E[rng]
             changed = True

@@ -141,3 +141,91 @@ G3_OBJ = -99.96 + 100.0  # the constant r = -100 is carried outside the solver
 def g14_update_qp():
     """test/UnitTests/model_modifications.jl:33-47: G1 then update!(q=[2,3]) -> obj 3.5? (x=[0.5,0.5])."""
     return g1_qp_nonneg()
+
+
+# ---------------------------------------------------------------------------
+# G15 / G16: exponential and power cone problems (test/UnitTests/exp_cone.jl, pow_cone.jl)
+# Each entry: (name, builder, expected status, expected objective or None, atol, settings)
+# ---------------------------------------------------------------------------
+_I3 = np.eye(3)
+_Z3 = np.zeros((3, 3))
+_E5 = float(np.exp(5.0))
+
+
+def g15_exp_feasible():
+    """exp_cone.jl:19-43 — max x s.t. y e^(x/y) <= z, y = 1, z = e^5: Solved, obj = -5 (atol 1e-2)."""
+    return _Z3, np.array([-1.0, 0, 0]), [O.Constraint(_I3, np.zeros(3), O.ExponentialCone()),
+                                         O.Constraint([[0, 1.0, 0], [0, 0, 1.0]], [-1.0, -_E5], O.ZeroSet(2))]
+
+
+def g15_exp_primal_infeasible_1():
+    """exp_cone.jl:47-77 — y = 1, z = -1: Primal_infeasible."""
+    return _Z3, np.array([1.0, 0, 0]), [O.Constraint(_I3, np.zeros(3), O.ExponentialCone()),
+                                        O.Constraint([[0, -1.0, 0]], [-1.0], O.ZeroSet(1)),
+                                        O.Constraint([[0, 0, -1.0]], [1.0], O.ZeroSet(1))]
+
+
+def g15_exp_primal_infeasible_2():
+    """exp_cone.jl:79-104 — two shifted cones that cannot intersect: Primal_infeasible."""
+    return _Z3, np.array([1.0, 0, 0]), [O.Constraint(_I3, [0, 0, -0.2], O.ExponentialCone()),
+                                        O.Constraint(-_I3, [0, 0, -0.3], O.ExponentialCone())]
+
+
+def g15_exp_dual_infeasible():
+    """exp_cone.jl:106-124 — max z over the cone: Dual_infeasible."""
+    return _Z3, np.array([0, 0, -1.0]), [O.Constraint(_I3, np.zeros(3), O.ExponentialCone())]
+
+
+def g15_dualexp_feasible():
+    """exp_cone.jl:130-156 — min y s.t. -x e^(y/x) <= e z, x = -1, z = e^5: Solved, obj = -6 (atol 1e-3)."""
+    return _Z3, np.array([0, 1.0, 0]), [O.Constraint(_I3, np.zeros(3), O.DualExponentialCone()),
+                                        O.Constraint([[1.0, 0, 0], [0, 0, 1.0]], [1.0, -_E5], O.ZeroSet(2))]
+
+
+def g15_dualexp_primal_infeasible():
+    """exp_cone.jl:160-185 — u = 1 violates u <= 0 of the dual cone: Primal_infeasible."""
+    return _Z3, np.ones(3), [O.Constraint(_I3, np.zeros(3), O.DualExponentialCone()),
+                             O.Constraint([[1.0, 0, 0], [0, 1.0, 0]], [-1.0, -2.0], O.ZeroSet(2))]
+
+
+def g16_pow_feasible():
+    """pow_cone.jl:16-56 — max x1^0.6 y^0.4 + x2^0.1: Solved, obj = -1.8458 (atol 1e-3), max_iter = 5000."""
+    q = np.zeros(6)
+    q[2] = q[5] = -1.0
+    A1 = np.zeros((3, 6)); A1[:, 0:3] = _I3
+    A2 = np.zeros((3, 6)); A2[:, 3:6] = _I3
+    return np.zeros((6, 6)), q, [O.Constraint(A1, np.zeros(3), O.PowerCone(0.6)),
+                                 O.Constraint(A2, np.zeros(3), O.PowerCone(0.1)),
+                                 O.Constraint([[1.0, 2.0, 0, 3.0, 0, 0]], [-3.0], O.ZeroSet(1)),
+                                 O.Constraint([[0, 0, 0, 0, 1.0, 0]], [-1.0], O.ZeroSet(1))]
+
+
+def g16_pow_primal_infeasible():
+    """pow_cone.jl:77-95 — x = y = 1, z = 2: Primal_infeasible."""
+    return _Z3, np.array([0, 0, -1.0]), [O.Constraint(_I3, np.zeros(3), O.PowerCone(0.8)),
+                                         O.Constraint(_I3, [-1.0, -1.0, -2.0], O.ZeroSet(3))]
+
+
+def g16_pow_dual_infeasible():
+    """pow_cone.jl:97-111 — min z over the cone: Dual_infeasible."""
+    return _Z3, np.array([0, 0, 1.0]), [O.Constraint(_I3, np.zeros(3), O.PowerCone(0.8))]
+
+
+def g16_dualpow_feasible():
+    """pow_cone.jl:116-137 — max z s.t. (x/.8)^.8 (y/.2)^.2 >= z, x = .8, y = .2: Solved, obj = -1 (atol 1e-3)."""
+    return _Z3, np.array([0, 0, -1.0]), [O.Constraint(_I3, np.zeros(3), O.DualPowerCone(0.8)),
+                                         O.Constraint([[1.0, 0, 0], [0, 1.0, 0]], [-0.8, -0.2], O.ZeroSet(2))]
+
+
+G15_G16 = [
+    ("exp_feasible", g15_exp_feasible, "Solved", -5.0, 1e-2, dict(eps_abs=1e-4, eps_rel=1e-4)),
+    ("exp_primal_infeasible_1", g15_exp_primal_infeasible_1, "Primal_infeasible", None, None, {}),
+    ("exp_primal_infeasible_2", g15_exp_primal_infeasible_2, "Primal_infeasible", None, None, {}),
+    ("exp_dual_infeasible", g15_exp_dual_infeasible, "Dual_infeasible", None, None, {}),
+    ("dualexp_feasible", g15_dualexp_feasible, "Solved", -6.0, 1e-3, {}),
+    ("dualexp_primal_infeasible", g15_dualexp_primal_infeasible, "Primal_infeasible", None, None, {}),
+    ("pow_feasible", g16_pow_feasible, "Solved", -1.8458, 1e-3, dict(max_iter=5000)),
+    ("pow_primal_infeasible", g16_pow_primal_infeasible, "Primal_infeasible", None, None, {}),
+    ("pow_dual_infeasible", g16_pow_dual_infeasible, "Dual_infeasible", None, None, {}),
+    ("dualpow_feasible", g16_dualpow_feasible, "Solved", -1.0, 1e-3, {}),
+]

@@ -172,3 +172,31 @@ def test_kkt_indirect_matches_direct():
             S.iteration_counter = 10 ** 6
             sol = S.solve(rhs)
         assert np.allclose(sol, D.solve(rhs), atol=1e-5), name
+
+
+@pytest.mark.parametrize("name,builder,status,obj,atol,kw", G.G15_G16, ids=[g[0] for g in G.G15_G16])
+def test_g15_g16_exp_pow_cone_problems(name, builder, status, obj, atol, kw):
+    # test/UnitTests/exp_cone.jl, pow_cone.jl: statuses and objective values with the reference's tolerances
+    res, _ = _solve(builder, **kw)
+    assert res.status == status
+    if obj is not None:
+        assert abs(res.obj_val - obj) < atol
+
+
+def test_exp_pow_projections_land_in_cone():
+    # test/UnitTests/sets.jl:84-110: 100 random points in [-25, 25]^3, projection in the cone (tol 1e-4);
+    # plus the projection's optimality conditions (v - Pi v in the polar cone, orthogonal to Pi v)
+    rng = np.random.default_rng(7)
+    for i in range(100):
+        alpha = 0.1 + 0.85 * rng.random()
+        for cone in (O.ExponentialCone(), O.PowerCone(alpha), O.DualExponentialCone(), O.DualPowerCone(alpha)):
+            v0 = -25.0 + 50.0 * rng.random(3)
+            v = v0.copy()
+            O.project_cone(v, cone)
+            assert O.in_cone(v, cone, 1e-4)
+            d = v - v0                       # must lie in the dual cone, orthogonal to v
+            assert O.in_dual(d, cone, 1e-3)
+            assert abs(v @ d) < 1e-5 * (1.0 + v0 @ v0)
+            w = v.copy()
+            O.project_cone(w, cone)          # idempotence (up to the iteration tolerances)
+            assert np.max(np.abs(w - v)) < 1e-3 * (1.0 + np.max(np.abs(v)))
