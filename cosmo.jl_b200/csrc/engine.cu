@@ -25,6 +25,7 @@
 #include "../../include/cosmo_b200.h"
 #include "common.cuh"
 #include "psd.cuh"
+#include "cone3.cuh"
 #include "spmv.cuh"
 #include "vector_kernels.cuh"
 #include "cg_persistent.cuh"
@@ -214,6 +215,13 @@ class Engine : public EngineBase {
   DevBuf<int> soc_off_, soc_dim_, soc_chunk_start_, soc_chunk_len_, soc_cone_chunk_ptr_;
   DevBuf<T> soc_norm_, soc_chunk_sum_, soc_norm2_;
   PsdBatch<T> psd_;
+  int n_c3_ = 0;             // exponential / power cones and their duals (cone3.cuh)
+  DevBuf<int> c3_off_, c3_maxit_;
+  DevBuf<unsigned char> c3_kind_;
+  DevBuf<T> c3_alpha_, c3_tol_;
+  Cone3Table<T> c3_table() const {
+    return Cone3Table<T>{n_c3_, c3_off_.p, c3_kind_.p, c3_alpha_.p, c3_maxit_.p, c3_tol_.p};
+  }
   // ---- state ----
   DevBuf<T> W_[2];           // operator variable, ping-pong (w / w_prev)
   int cur_ = 0, prev_ = 1;
@@ -613,6 +621,9 @@ Engine<T>::Engine(const cosmo_b200_problem& p, const cosmo_b200_settings& st) : 
   hu_.assign(m_, INFINITY);
   std::vector<int> soc_off, soc_dim;
   std::vector<PsdConeDesc> psd_descs;
+  std::vector<int> c3_off, c3_maxit;
+  std::vector<unsigned char> c3_kind;
+  std::vector<T> c3_alpha, c3_tol;
   for (long long k = 0; k < p.n_sets; ++k) {
     const cosmo_b200_set& sdesc = p.sets[k];
     if (sdesc.dim < 0 || off + sdesc.dim > m_) throw EngineError{COSMO_B200_ERR_INVALID, "set dimensions exceed m"};
@@ -655,8 +666,25 @@ Engine<T>::Engine(const cosmo_b200_problem& p, const cosmo_b200_settings& st) : 
         if (sdesc.dim > 0) psd_descs.push_back(PsdConeDesc{(int)off, (int)N, sdesc.type == COSMO_B200_PSD_TRIANGLE ? 1 : 0});
         break;
       }
+      case COSMO_B200_EXP:
+      case COSMO_B200_DUAL_EXP:
+      case COSMO_B200_POW:
+      case COSMO_B200_DUAL_POW: {
+        cls = ROW_CONE3;
+        if (sdesc.dim != 3) throw EngineError{COSMO_B200_ERR_INVALID, "exponential / power cones have dimension 3"};
+        const bool is_pow = (sdesc.type == COSMO_B200_POW || sdesc.type == COSMO_B200_DUAL_POW);
+        if (is_pow && !(sdesc.alpha > 0.0 && sdesc.alpha < 1.0))
+          throw EngineError{COSMO_B200_ERR_INVALID, "The exponent alpha of the power cone has to be in (0, 1)."};
+        for (int i = 0; i < 3; ++i) row_cone[off + i] = (int)c3_off.size();
+        c3_off.push_back((int)off);
+        c3_kind.push_back((unsigned char)(sdesc.type - COSMO_B200_EXP));
+        c3_alpha.push_back(is_pow ? (T)sdesc.alpha : T(0.5));
+        c3_maxit.push_back(sdesc.max_iter > 0 ? sdesc.max_iter : (is_pow ? 20 : 100));   // convexset.jl:503, 631
+        c3_tol.push_back(sdesc.tol > 0.0 ? (T)sdesc.tol : (T)1e-8);
+        break;
+      }
       default:
-        throw EngineError{COSMO_B200_ERR_UNSUPPORTED, "unsupported cone type (Exp/Pow/dual/complex PSD): fall back to the host loop"};
+        throw EngineError{COSMO_B200_ERR_UNSUPPORTED, "unsupported cone type (complex PSD): fall back to the host loop"};
     }
     for (long long i = 0; i < sdesc.dim; ++i) row_class[off + i] = cls;
     off += sdesc.dim;
@@ -715,6 +743,12 @@ Engine<T>::Engine(const cosmo_b200_problem& p, const cosmo_b200_settings& st) : 
     sync();
   }
   psd_.init(psd_descs, stream_);
+  n_c3_ = (int)c3_off.size();
+  if (n_c3_) {
+    c3_off_.upload(c3_off, stream_); c3_kind_.upload(c3_kind, stream_); c3_alpha_.upload(c3_alpha, stream_);
+    c3_maxit_.upload(c3_maxit, stream_); c3_tol_.upload(c3_tol, stream_);
+    sync();
+  }
 
   // ---- state / scratch ------------------------------------------------------
   W_[0].alloc(n_ + m_); W_[1].alloc(n_ + m_);
@@ -951,6 +985,10 @@ template <typename T>
 void Engine<T>::project_device(const T* w, bool with_rhs, const T* ws_rhs) {
   soc_norms(w + n_, soc_norm_.p);
   psd_.project(w + n_, s_.p, stream_, st_.psd_max_sweeps, launches_);
+  if (n_c3_) {
+    cone3_project_kernel<T><<<(n_c3_ + 127) / 128, 128, 0, stream_>>>(c3_table(), w + n_, s_.p);
+    check_launch("cone3_project");
+  }
   ProjRhsArgs<T> a;
   a.n = n_; a.m = m_; a.w = w; a.ws_rhs = ws_rhs ? ws_rhs : w + n_;
   a.q = q_.p; a.b = b_.p; a.rho = rho_vec_.p; a.box_l = box_l_.p; a.box_u = box_u_.p;
@@ -1300,6 +1338,12 @@ bool Engine<T>::primal_infeasible() {
   } else {
     CUDA_TRY(cudaMemsetAsync(sc_.p + SC_TMP3, 0, sizeof(T), stream_));
   }
+  if (n_c3_) {
+    cone3_cert_kernel<T><<<1, kBlock, 0, stream_>>>(c3_table(), dy_.p, eps, sc_.p + SC_TMP5);
+    check_launch("cone3_cert");
+  } else {
+    CUDA_TRY(cudaMemsetAsync(sc_.p + SC_TMP5, 0, sizeof(T), stream_));
+  }
   const bool psd_ok = psd_.certificate(dy_.p, /*negate=*/true, (double)eps, stream_, st_.psd_max_sweeps, launches_);
   (void)flag;
   // the PSD verdict is a host bool of THIS rank: put it next to the device flags so that the
@@ -1308,12 +1352,12 @@ bool Engine<T>::primal_infeasible() {
   CUDA_TRY(cudaMemcpyAsync(sc_.p + SC_TMP4, h_sc_ + SC_TMP4, sizeof(T), cudaMemcpyHostToDevice, stream_));
   if (nranks_ > 1) {
     allreduce_sum(sc_.p + SC_TMP0, 2);   // dy'b, box support sum
-    allreduce_max(sc_.p + SC_TMP2, 3);   // flags: rows, SOC, PSD
+    allreduce_max(sc_.p + SC_TMP2, 4);   // flags: rows, SOC, PSD, Exp/Pow
   }
-  read_scalars(SC_TMP0, 5);
+  read_scalars(SC_TMP0, 6);
   const double dyt_b = (double)h_sc_[SC_TMP0];
   const double box_sum = (double)h_sc_[SC_TMP1];
-  const bool cone_bad = (h_sc_[SC_TMP2] != 0) || (h_sc_[SC_TMP3] != 0) || (h_sc_[SC_TMP4] != 0);
+  const bool cone_bad = (h_sc_[SC_TMP2] != 0) || (h_sc_[SC_TMP3] != 0) || (h_sc_[SC_TMP4] != 0) || (h_sc_[SC_TMP5] != 0);
   const double sF = (cone_bad ? INFINITY : 0.0) + box_sum - dyt_b;
   return sF <= st_.eps_prim_inf;
 }
@@ -1350,12 +1394,18 @@ bool Engine<T>::dual_infeasible() {
   } else {
     CUDA_TRY(cudaMemsetAsync(sc_.p + SC_TMP3, 0, sizeof(T), stream_));
   }
+  if (n_c3_) {
+    cone3_cert_kernel<T><<<1, kBlock, 0, stream_>>>(c3_table(), vec_m_.p, eps, sc_.p + SC_TMP5);
+    check_launch("cone3_cert");
+  } else {
+    CUDA_TRY(cudaMemsetAsync(sc_.p + SC_TMP5, 0, sizeof(T), stream_));
+  }
   const bool psd_ok = psd_.certificate(vec_m_.p, /*negate=*/true, (double)eps, stream_, st_.psd_max_sweeps, launches_);
   h_sc_[SC_TMP4] = psd_ok ? T(0) : T(1);
   CUDA_TRY(cudaMemcpyAsync(sc_.p + SC_TMP4, h_sc_ + SC_TMP4, sizeof(T), cudaMemcpyHostToDevice, stream_));
-  if (nranks_ > 1) allreduce_max(sc_.p + SC_TMP2, 3);
-  read_scalars(SC_TMP2, 3);
-  return (h_sc_[SC_TMP2] == 0) && (h_sc_[SC_TMP3] == 0) && (h_sc_[SC_TMP4] == 0);
+  if (nranks_ > 1) allreduce_max(sc_.p + SC_TMP2, 4);
+  read_scalars(SC_TMP2, 4);
+  return (h_sc_[SC_TMP2] == 0) && (h_sc_[SC_TMP3] == 0) && (h_sc_[SC_TMP4] == 0) && (h_sc_[SC_TMP5] == 0);
 }
 
 // ---------------------------------------------------------------------------

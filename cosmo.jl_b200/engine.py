@@ -18,7 +18,7 @@ from . import build as _build
 OK = 0
 ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_ALLOC, ERR_NCCL, ERR_NUMERICAL = -1, -2, -3, -4, -5, -6
 F64, F32 = 0, 1
-ZERO, NONNEG, BOX, SOC, PSD_SQUARE, PSD_TRIANGLE = range(6)
+ZERO, NONNEG, BOX, SOC, PSD_SQUARE, PSD_TRIANGLE, EXP, DUAL_EXP, POW, DUAL_POW = range(10)
 STATUS = {0: "Undetermined", 1: "Solved", 2: "Max_iter_reached", 3: "Time_limit_reached",
           4: "Primal_infeasible", 5: "Dual_infeasible", 6: "Unsolved"}
 KKT_CG, KKT_MINRES_REDUCED, KKT_MINRES = 0, 1, 2
@@ -36,7 +36,8 @@ class CscStruct(C.Structure):
 
 
 class SetStruct(C.Structure):
-    _fields_ = [("type", C.c_int32), ("_pad", C.c_int32), ("dim", C.c_int64), ("l", C.c_void_p), ("u", C.c_void_p)]
+    _fields_ = [("type", C.c_int32), ("max_iter", C.c_int32), ("dim", C.c_int64), ("l", C.c_void_p), ("u", C.c_void_p),
+                ("alpha", C.c_double), ("tol", C.c_double)]
 
 
 class ProblemStruct(C.Structure):
@@ -163,7 +164,8 @@ class Engine:
     """Owns one ``cosmo_b200_handle`` (one problem resident in HBM on one GPU).
 
     ``P`` and ``A`` are SciPy CSC matrices (the same three arrays Julia's
-    SparseMatrixCSC holds); ``sets`` is a list of ``(type, dim, l, u)``.
+    SparseMatrixCSC holds); ``sets`` is a list of ``(type, dim, l, u)`` or, for the
+    exponential / power cones, ``(type, 3, None, None, {"alpha": a, "max_iter": k, "tol": t})``.
     """
 
     def __init__(self, P, q, A, b, sets: Sequence[tuple], settings: Optional[SettingsStruct] = None,
@@ -190,9 +192,13 @@ class Engine:
             return CscStruct(M.shape[0], M.shape[1], _ptr(colptr), _ptr(rowval), _ptr(nz))
 
         set_arr = (SetStruct * max(len(sets), 1))()
-        for i, (typ, dim, l, u) in enumerate(sets):
+        for i, (typ, dim, l, u, *extra) in enumerate(sets):
             set_arr[i].type = int(typ)
             set_arr[i].dim = int(dim)
+            if extra and extra[0]:
+                set_arr[i].alpha = float(extra[0].get("alpha", 0.0))
+                set_arr[i].max_iter = int(extra[0].get("max_iter", 0))
+                set_arr[i].tol = float(extra[0].get("tol", 0.0))
             if l is not None:
                 la = np.ascontiguousarray(l, dtype=T)
                 ua = np.ascontiguousarray(u, dtype=T)

@@ -103,6 +103,49 @@ class PsdConeTriangle(AbstractConvexSet):
             raise ValueError("dimension must be N(N+1)/2")
 
 
+class ExponentialCone(AbstractConvexSet):
+    """COSMO.ExponentialCone(): cl{(x,y,z) | y > 0, y e^(x/y) <= z}, convexset.jl:497-507."""
+    code = _eng.EXP
+    dim = 3
+
+    def __init__(self, dim=3, MAX_ITERS=100, EXP_TOL=1e-8):
+        self.MAX_ITER, self.TOL = int(MAX_ITERS), float(EXP_TOL)
+
+
+class DualExponentialCone(ExponentialCone):
+    """COSMO.DualExponentialCone(), convexset.jl:749-758."""
+    code = _eng.DUAL_EXP
+
+
+class PowerCone(AbstractConvexSet):
+    """COSMO.PowerCone(alpha): {(x,y,z) | x^a y^(1-a) >= |z|, x, y >= 0}, convexset.jl:625-636."""
+    code = _eng.POW
+    dim = 3
+
+    def __init__(self, alpha, MAX_ITERS=20, POW_TOL=1e-8):
+        if alpha <= 0 or alpha >= 1:
+            raise ValueError("The exponent alpha of the power cone has to be in (0, 1).")
+        self.alpha, self.MAX_ITER, self.TOL = float(alpha), int(MAX_ITERS), float(POW_TOL)
+
+
+class DualPowerCone(PowerCone):
+    """COSMO.DualPowerCone(alpha), convexset.jl:765-775."""
+    code = _eng.DUAL_POW
+
+
+# cones whose rows may only be scaled by one common factor (rectify_scaling!, convexset.jl:955-957)
+SCALAR_SCALED_CONES = (SecondOrderCone, PsdCone, PsdConeTriangle, ExponentialCone, PowerCone)
+# cones that cannot be split across ranks
+ATOMIC_CONES = SCALAR_SCALED_CONES
+
+
+def set_tuple(S):
+    """The (type, dim, l, u[, params]) tuple `engine.Engine` marshals into a cosmo_b200_set."""
+    if isinstance(S, (ExponentialCone, PowerCone)):
+        return (S.code, 3, None, None, {"alpha": getattr(S, "alpha", 0.0), "max_iter": S.MAX_ITER, "tol": S.TOL})
+    return (S.code, S.dim, getattr(S, "l", None), getattr(S, "u", None))
+
+
 _SORT = (ZeroSet, Nonnegatives, Box, SecondOrderCone, PsdCone, PsdConeTriangle)
 
 
@@ -294,7 +337,7 @@ def ruiz_equilibrate(P, q, A, b, sets, st: Settings):
     changed = False
     off = 0
     for S in sets:
-        if isinstance(S, (SecondOrderCone, PsdCone, PsdConeTriangle)) and S.dim > 0:
+        if isinstance(S, SCALAR_SCALED_CONES) and S.dim > 0:
             seg = slice(off, off + S.dim)
             Ew[seg] = np.mean(E[seg]) / E[seg]
             changed = True
@@ -426,7 +469,7 @@ class Model:
                 P, q, A, b, sets = self.P0, self.q0, self.A0, self.b0, self.sets0
                 D, E, c = np.ones(self.n), np.ones(self.m), 1.0
             self.D, self.E, self.c = D, E, c
-            set_tuples = [(S.code, S.dim, getattr(S, "l", None), getattr(S, "u", None)) for S in sets]
+            set_tuples = [set_tuple(S) for S in sets]
             self.engine = _eng.Engine(P, q, A, b, set_tuples, st.to_struct(),
                                       D=D if st.scaling != 0 else None, E=E if st.scaling != 0 else None, c=c,
                                       dtype=self.dtype, device=self.device)

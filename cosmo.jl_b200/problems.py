@@ -131,6 +131,14 @@ def to_oracle_cones(sets):
             out.append(O.PsdCone(S.dim))
         elif isinstance(S, M.PsdConeTriangle):
             out.append(O.PsdConeTriangle(S.dim))
+        elif isinstance(S, M.DualExponentialCone):
+            out.append(O.DualExponentialCone(3, S.MAX_ITER, S.TOL))
+        elif isinstance(S, M.ExponentialCone):
+            out.append(O.ExponentialCone(3, S.MAX_ITER, S.TOL))
+        elif isinstance(S, M.DualPowerCone):
+            out.append(O.DualPowerCone(S.alpha, S.MAX_ITER, S.TOL))
+        elif isinstance(S, M.PowerCone):
+            out.append(O.PowerCone(S.alpha, S.MAX_ITER, S.TOL))
         else:
             raise TypeError(S)
     return out

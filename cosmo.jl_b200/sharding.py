@@ -56,7 +56,7 @@ def partition_rows(A: sp.csc_matrix, sets, world: int) -> List[List[Tuple[int, i
     for k, S in enumerate(sets):
         if S.dim == 0:
             continue
-        atomic = isinstance(S, (M.SecondOrderCone, M.PsdCone, M.PsdConeTriangle))
+        atomic = isinstance(S, M.ATOMIC_CONES)
         if atomic:
             mid = 0.5 * (cum[off] + cum[off + S.dim])
             while g < world - 1 and mid > bounds[g]:
@@ -107,7 +107,7 @@ def create_engine(shard: Shard, settings: M.Settings, device: int = 0, dist=None
                   dtype=np.float64) -> _eng.Engine:
     """Build the per-rank engine; with world > 1 rank 0 creates the ncclUniqueId and
     `torch.distributed` (the plumbing) broadcasts its 128 bytes."""
-    tuples = [(S.code, S.dim, getattr(S, "l", None), getattr(S, "u", None)) for S in shard.sets]
+    tuples = [M.set_tuple(S) for S in shard.sets]
     eng = _eng.Engine(shard.P, shard.q, shard.A, shard.b, tuples, settings.to_struct(), D=D,
                       E=None if E is None else np.asarray(E)[shard.rows], c=c, dtype=dtype, device=device)
     if shard.world > 1:

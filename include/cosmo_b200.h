@@ -38,14 +38,14 @@
 extern "C" {
 #endif
 
-#define COSMO_B200_ABI_VERSION 1
+#define COSMO_B200_ABI_VERSION 2
 
 typedef struct cosmo_b200_handle cosmo_b200_handle;
 
 enum {
   COSMO_B200_OK = 0,
   COSMO_B200_ERR_INVALID = -1,     /* bad argument / dimension mismatch (interface.jl:369-392) */
-  COSMO_B200_ERR_UNSUPPORTED = -2, /* Exp/Pow/dual cones, complex PSD, BigFloat: shim falls back to Julia */
+  COSMO_B200_ERR_UNSUPPORTED = -2, /* complex PSD, BigFloat: shim falls back to Julia */
   COSMO_B200_ERR_CUDA = -3,        /* CUDA runtime error or no usable sm_100 device */
   COSMO_B200_ERR_ALLOC = -4,
   COSMO_B200_ERR_NCCL = -5,
@@ -61,7 +61,12 @@ enum {
   COSMO_B200_BOX = 2,          /* Box(l,u),         convexset.jl:803-847 */
   COSMO_B200_SOC = 3,          /* SecondOrderCone,  convexset.jl:92-114  */
   COSMO_B200_PSD_SQUARE = 4,   /* PsdCone / DensePsdCone,                 convexset.jl:271-321 */
-  COSMO_B200_PSD_TRIANGLE = 5  /* PsdConeTriangle / DensePsdConeTriangle, convexset.jl:362-412 */
+  COSMO_B200_PSD_TRIANGLE = 5, /* PsdConeTriangle / DensePsdConeTriangle, convexset.jl:362-412 */
+  /* 3-d cones (sort_sets puts every remaining type in class 6 too, interface.jl:473) */
+  COSMO_B200_EXP = 6,          /* ExponentialCone,      convexset.jl:497-618 */
+  COSMO_B200_DUAL_EXP = 7,     /* DualExponentialCone,  convexset.jl:749-789 */
+  COSMO_B200_POW = 8,          /* PowerCone(alpha),     convexset.jl:625-742 */
+  COSMO_B200_DUAL_POW = 9      /* DualPowerCone(alpha), convexset.jl:765-789 */
 };
 
 /* status (src/solver.jl:113,161,175,311-353) */
@@ -92,11 +97,13 @@ typedef struct {
 
 /* one entry of CompositeConvexSet.sets (src/projections.jl:20-31) */
 typedef struct {
-  int32_t type;  /* COSMO_B200_ZERO ... */
-  int32_t _pad;
-  int64_t dim;   /* rows of this set (for PSD: length of the vector, N^2 or N(N+1)/2) */
-  const void* l; /* Box only: lower/upper bounds, already scaled by E (convexset.jl:863-867) */
+  int32_t type;     /* COSMO_B200_ZERO ... */
+  int32_t max_iter; /* Exp/Pow cones: MAX_ITER of the projection (0 = reference default, 100 / 20) */
+  int64_t dim;      /* rows of this set (for PSD: length of the vector, N^2 or N(N+1)/2; Exp/Pow: 3) */
+  const void* l;    /* Box only: lower/upper bounds, already scaled by E (convexset.jl:863-867) */
   const void* u;
+  double alpha;     /* PowerCone / DualPowerCone exponent in (0,1), convexset.jl:631-634 */
+  double tol;       /* Exp/Pow cones: EXP_TOL / POW_TOL (0 = reference default 1e-8) */
 } cosmo_b200_set;
 
 /* ws.p (ProblemData, types.jl:158-175) + ws.sm (ScaleMatrices, types.jl:130-151) after setup! */

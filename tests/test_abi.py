@@ -26,7 +26,7 @@ def test_header_symbols_exported():
     for name in declared:
         assert hasattr(lib, name), name
     assert sorted(E.EXPORTS) == declared
-    assert lib.cosmo_b200_abi_version() == 1
+    assert lib.cosmo_b200_abi_version() == 2
 
 
 def test_default_settings_match_reference():
@@ -42,7 +42,7 @@ def test_default_settings_match_reference():
 def test_struct_sizes():
     # keep the ctypes mirrors in sync with the C header layout
     assert ctypes.sizeof(E.CscStruct) == 40
-    assert ctypes.sizeof(E.SetStruct) == 32
+    assert ctypes.sizeof(E.SetStruct) == 48
     assert ctypes.sizeof(E.ProblemStruct) == 16 + 16 + 80 + 16 + 16 + 32 + 8
     assert ctypes.sizeof(E.SettingsStruct) == 56 + 8 + 24 + 16 + 48 + 24 + 8
     assert ctypes.sizeof(E.ResultStruct) == 24 + 24 + 8 + 40 + 24 + 56 + 24

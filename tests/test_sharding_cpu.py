@@ -17,8 +17,9 @@ def _mixed_problem(seed=1):
     P, q, A, b, sets = cosmo_b200.problems.random_sparse_qp(120, 401, 0.08, seed=seed)
     box = sets[1]
     sets = [cosmo_b200.ZeroSet(0), sets[0],
-            cosmo_b200.Box(box.l[:100], box.u[:100]), cosmo_b200.SecondOrderCone(60),
-            cosmo_b200.PsdConeTriangle(36), cosmo_b200.Box(box.l[100:105], box.u[100:105])]
+            cosmo_b200.Box(box.l[:99], box.u[:99]), cosmo_b200.SecondOrderCone(60),
+            cosmo_b200.PsdConeTriangle(36), cosmo_b200.ExponentialCone(), cosmo_b200.DualPowerCone(0.4),
+            cosmo_b200.Box(box.l[99:99], box.u[99:99])]
     assert sum(S.dim for S in sets) == A.shape[0]
     return P, q, A, b, sets
 
@@ -37,6 +38,8 @@ def test_partition_covers_rows_and_keeps_cones_whole(world):
                 assert S.dim == 60
             if isinstance(S, cosmo_b200.PsdConeTriangle):
                 assert S.dim == 36
+            if isinstance(S, (cosmo_b200.ExponentialCone, cosmo_b200.PowerCone)):
+                assert S.dim == 3
         rows.append(sh.rows)
     assert np.array_equal(np.concatenate(rows), np.arange(A.shape[0]))  # contiguous, in cone order
 
