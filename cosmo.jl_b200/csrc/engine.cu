@@ -26,6 +26,7 @@
 #include "common.cuh"
 #include "psd.cuh"
 #include "cone3.cuh"
+#include "aa.cuh"
 #include "spmv.cuh"
 #include "vector_kernels.cuh"
 #include "cg_persistent.cuh"
@@ -222,6 +223,17 @@ class Engine : public EngineBase {
   Cone3Table<T> c3_table() const {
     return Cone3Table<T>{n_c3_, c3_off_.p, c3_kind_.p, c3_alpha_.p, c3_maxit_.p, c3_tol_.p};
   }
+  // ---- accelerator (aa.cuh) ----
+  DevBuf<T> aaG_, aaQ_, aaR_, aa_eta_, aa_glast_, aa_f_, aa_flast_, aa_sc_;
+  T* h_aa_ = nullptr;          // pinned mirror of aa_sc_
+  int aa_mem_ = 0;             // allocated history length (min(mem, dim)), 0 = not allocated
+  int aa_iter_ = 0;            // columns filled since the last restart
+  bool aa_init_ = true, aa_success_ = false, aa_active_ = false;
+  long long aa_accelerated_ = 0, aa_declined_ = 0;
+  void aa_prepare();
+  void aa_restart() { aa_iter_ = 0; aa_init_ = true; }
+  void aa_update(const T* g, const T* x);
+  bool aa_accelerate(T* g);
   // ---- state ----
   DevBuf<T> W_[2];           // operator variable, ping-pong (w / w_prev)
   int cur_ = 0, prev_ = 1;
@@ -787,6 +799,7 @@ Engine<T>::~Engine() {
   if (comm_ && g_nccl.CommDestroy) g_nccl.CommDestroy(comm_);
   if (h_sc_) cudaFreeHost(h_sc_);
   if (h_isc_) cudaFreeHost(h_isc_);
+  if (h_aa_) cudaFreeHost(h_aa_);
   if (ev0_) cudaEventDestroy(ev0_);
   if (ev1_) cudaEventDestroy(ev1_);
   if (stream_) cudaStreamDestroy(stream_);
@@ -1409,6 +1422,82 @@ bool Engine<T>::dual_infeasible() {
 }
 
 // ---------------------------------------------------------------------------
+// Accelerator: AndersonAccelerator{T, Type2{QRDecomp}, RestartedMemory, NoRegularizer} (aa.cuh)
+// ---------------------------------------------------------------------------
+template <typename T>
+void Engine<T>::aa_prepare() {   // _make_accelerator!, setup.jl:10-14 (built once per dimension / memory)
+  const long long dim = (long long)n_ + m_;
+  int mem = (int)std::min<long long>(std::max(st_.accelerator_mem, 3), std::min<long long>(dim, 32));
+  if (aa_mem_ != mem) {
+    aaG_.alloc((size_t)dim * mem, false); aaQ_.alloc((size_t)dim * mem, false);
+    aaR_.alloc((size_t)mem * mem); aa_eta_.alloc(32);
+    aa_glast_.alloc(dim); aa_f_.alloc(dim); aa_flast_.alloc(dim); aa_sc_.alloc(AA_SC_COUNT);
+    if (!h_aa_) CUDA_TRY(cudaMallocHost(&h_aa_, AA_SC_COUNT * sizeof(T)));
+    aa_mem_ = mem;
+  }
+  aa_restart();               // setup.jl:47-49
+  aa_active_ = false; aa_success_ = false;
+  aa_accelerated_ = aa_declined_ = 0;
+}
+
+// CA.update!(aa, g = w, x = w_prev): history columns + QR update by modified Gram-Schmidt
+template <typename T>
+void Engine<T>::aa_update(const T* g, const T* x) {
+  const int dim = n_ + m_, lo = (rank_ == 0) ? 0 : n_;
+  const int grid = vgrid(dim);
+  if (aa_init_) {
+    aa_update_kernel<T><<<grid, kBlock, 0, stream_>>>(dim, lo, g, x, aa_f_.p, aa_flast_.p, aa_glast_.p, (T*)nullptr, (T*)nullptr, 1,
+                                                      red_ptr(aa_sc_.p + AA_F2));
+    check_launch("aa_update");
+    allreduce_sum(aa_sc_.p + AA_F2, 1);
+    aa_init_ = false;
+    return;
+  }
+  int j = aa_iter_ % aa_mem_;
+  if (j == 0 && aa_iter_ != 0) aa_iter_ = 0;   // RestartedMemory: the history is full, start again
+  T* Gj = aaG_.p + (size_t)j * dim;
+  T* q = aaQ_.p + (size_t)j * dim;
+  aa_update_kernel<T><<<grid, kBlock, 0, stream_>>>(dim, lo, g, x, aa_f_.p, aa_flast_.p, aa_glast_.p, Gj, q, 0,
+                                                    red_ptr(aa_sc_.p + AA_F2));
+  check_launch("aa_update");
+  allreduce_sum(aa_sc_.p + AA_F2, 1);
+  T* Rj = aaR_.p + (size_t)j * aa_mem_;        // column j of R
+  for (int i = 0; i <= j; ++i) {
+    const T* Qp = i > 0 ? aaQ_.p + (size_t)(i - 1) * dim : nullptr;
+    const T* Qi = i < j ? aaQ_.p + (size_t)i * dim : nullptr;
+    T* out = i < j ? Rj + i : aa_sc_.p + AA_NRM2;
+    aa_mgs_kernel<T><<<grid, kBlock, 0, stream_>>>(dim, lo, q, Qp, i > 0 ? Rj + (i - 1) : nullptr, Qi, red_ptr(out));
+    check_launch("aa_mgs");
+    allreduce_sum(out, 1);
+  }
+  aa_normalize_kernel<T><<<grid, kBlock, 0, stream_>>>(dim, q, aa_sc_.p + AA_NRM2, Rj + j);
+  check_launch("aa_normalize");
+  ++aa_iter_;
+}
+
+// CA.accelerate!(g = w, ...): w -= G eta with R eta = Q'f; returns was_successful(aa)
+template <typename T>
+bool Engine<T>::aa_accelerate(T* g) {
+  const int l = std::min(aa_iter_, aa_mem_);
+  if (l < std::max(st_.accelerator_min_mem, 1)) return false;
+  const int dim = n_ + m_, lo = (rank_ == 0) ? 0 : n_;
+  const int grid = vgrid(dim);
+  for (int c0 = 0; c0 < l; c0 += 8) {
+    aa_qtf_kernel<T><<<grid, kBlock, 0, stream_>>>(dim, lo, aa_f_.p, aaQ_.p, (size_t)dim, c0, std::min(8, l - c0),
+                                                   red_ptr(aa_eta_.p + c0));
+    check_launch("aa_qtf");
+  }
+  allreduce_sum(aa_eta_.p, l);
+  aa_solve_kernel<T><<<1, 32, 0, stream_>>>(aaR_.p, aa_mem_, l, aa_eta_.p, aa_sc_.p + AA_FLAG);
+  check_launch("aa_solve");
+  aa_apply_kernel<T><<<grid, kBlock, 0, stream_>>>(dim, g, aaG_.p, (size_t)dim, l, aa_eta_.p, aa_sc_.p + AA_FLAG);
+  check_launch("aa_apply");
+  CUDA_TRY(cudaMemcpyAsync(h_aa_ + AA_FLAG, aa_sc_.p + AA_FLAG, sizeof(T), cudaMemcpyDeviceToHost, stream_));
+  sync();
+  return h_aa_[AA_FLAG] != T(0);
+}
+
+// ---------------------------------------------------------------------------
 // The hot loop: COSMO.optimize!, src/solver.jl:125-167
 // ---------------------------------------------------------------------------
 template <typename T>
@@ -1462,10 +1551,25 @@ void Engine<T>::solve(cosmo_b200_result* out) {
   xw_step(cur_, 1 - cur_, false, nullptr);
   cur_ = 1 - cur_; prev_ = 1 - cur_;
 
-  while (iter < st_.max_iter) {
+  const bool use_aa = (st_.accelerator == COSMO_B200_ACC_ANDERSON);
+  long long safeguarding_iter = 0;
+  if (use_aa) aa_prepare();
+  // update_suggested (solver.jl:284-292): with an Anderson accelerator, rho updates and the infeasibility
+  // snapshot wait for the next iteration whose candidate was not accelerated
+  auto suggested = [&](bool due) { return due && !(use_aa && aa_success_); };
+
+  while (iter + safeguarding_iter < st_.max_iter) {
     ++iter;
-    // acceleration_pre!: EmptyAccelerator (accelerator_interface.jl:75)
-    if (infeasibility_check_due) {  // solver.jl:145-148
+    // acceleration_pre! (accelerator_interface.jl:58-75), ImmediateActivation (:24-28)
+    if (use_aa) {
+      if (!aa_active_ && iter >= 2) aa_active_ = true;
+      if (aa_active_) {
+        aa_update(W_[cur_].p, W_[prev_].p);
+        aa_success_ = aa_accelerate(W_[cur_].p);   // overwrites w with the candidate
+        if (aa_success_) ++aa_accelerated_;
+      }
+    }
+    if (suggested(infeasibility_check_due)) {  // solver.jl:145-148
       recover_mu(W_[prev_].p);
       CUDA_TRY(cudaMemcpyAsync(dy_.p, mu_.p, m * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
     }
@@ -1475,7 +1579,7 @@ void Engine<T>::solve(cosmo_b200_result* out) {
     if (st_.adaptive_rho && st_.adaptive_rho_interval > 0 && (iter % st_.adaptive_rho_interval) == 0 &&
         (long long)(rho_updates_.size() - 1) < st_.adaptive_rho_max_adaptions)
       rho_update_due = true;
-    if (rho_update_due) {
+    if (suggested(rho_update_due)) {
       rho_update_due = false;
       project_device(W_[src].p, false, nullptr);          // admm_z!
       recover_mu(W_[src].p);                               // w_prev == w here
@@ -1483,6 +1587,7 @@ void Engine<T>::solve(cosmo_b200_result* out) {
       const bool adapted = adapt_rho(W_[src].p);
       res_time += now_s() - t0;
       if (adapted) {
+        if (use_aa) aa_restart();   // the operator changed: CA.restart! (solver.jl:272-275)
         // w[n+1:end] = mu ./ rho + s (solver.jl:278), kept apart from w_prev
         ws_from_mu_kernel<T><<<vgrid(m), kBlock, 0, stream_>>>(m, rho_vec_.p, mu_.p, s_.p, W_[dst].p + n);
         check_launch("ws_from_mu");
@@ -1494,7 +1599,23 @@ void Engine<T>::solve(cosmo_b200_result* out) {
       xw_step(src, dst, true, nullptr);
     }
     prev_ = src; cur_ = dst;
-    // acceleration_post!: EmptyAccelerator
+    // acceleration_post! (accelerator_interface.jl:85-114): safeguard the accelerated candidate
+    if (use_aa && aa_active_ && aa_success_ && st_.safeguard) {
+      const int dim = n + m, lo = (rank_ == 0) ? 0 : n;
+      aa_res_kernel<T><<<vgrid(dim), kBlock, 0, stream_>>>(dim, lo, W_[prev_].p, W_[cur_].p, aa_f_.p, red_ptr(aa_sc_.p + AA_FACC2));
+      check_launch("aa_res");
+      allreduce_sum(aa_sc_.p + AA_FACC2, 1);
+      CUDA_TRY(cudaMemcpyAsync(h_aa_, aa_sc_.p, 2 * sizeof(T), cudaMemcpyDeviceToHost, stream_));
+      sync();
+      const double nrm_f = sqrt((double)h_aa_[AA_F2]), nrm_f_acc = sqrt((double)h_aa_[AA_FACC2]);
+      if (nrm_f_acc > nrm_f * st_.safeguard_tol) {
+        // decline: w_prev = w = g_last, then one plain ADMM step from there (:100-106)
+        CUDA_TRY(cudaMemcpyAsync(W_[prev_].p, aa_glast_.p, (size_t)dim * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+        xw_step(prev_, cur_, true, nullptr);
+        ++safeguarding_iter;
+        ++aa_declined_;
+      }
+    }
 
     // check_termination! (solver.jl:303-356)
     if ((st_.check_termination > 0 && iter % st_.check_termination == 0) || iter == 1) {
@@ -1512,7 +1633,7 @@ void Engine<T>::solve(cosmo_b200_result* out) {
     }
     if (st_.check_infeasibility > 0 && iter % st_.check_infeasibility == 0) {
       infeasibility_check_due = true;
-    } else if (infeasibility_check_due) {
+    } else if (suggested(infeasibility_check_due)) {
       infeasibility_check_due = false;
       recover_mu(W_[prev_].p);
       sub_kernel<T><<<vgrid(m), kBlock, 0, stream_>>>(m, dy_.p, mu_.p, dy_.p);          // dy -= mu
@@ -1535,7 +1656,7 @@ void Engine<T>::solve(cosmo_b200_result* out) {
   const double iter_time = now_s() - iter_start;
   float dev_ms = 0.f;
   CUDA_TRY(cudaEventElapsedTime(&dev_ms, ev0_, ev1_));
-  if (iter == st_.max_iter && status == COSMO_B200_UNDETERMINED) {  // solver.jl:173-176
+  if (iter + safeguarding_iter == st_.max_iter && status == COSMO_B200_UNDETERMINED) {  // solver.jl:173-176
     compute_residuals(W_[prev_].p, s_.p, mu_.p, false, info);
     status = COSMO_B200_MAX_ITER_REACHED;
   }
@@ -1553,8 +1674,8 @@ void Engine<T>::solve(cosmo_b200_result* out) {
     if (out->mu) download_vec(out->mu, mu_.p, m);
     sync();
     out->obj_val = cost;
-    out->iter = iter;
-    out->safeguarding_iter = 0;
+    out->iter = iter + safeguarding_iter;      // total_iter, solver.jl:195
+    out->safeguarding_iter = safeguarding_iter;
     out->status = status;
     out->r_prim = info[0]; out->r_dual = info[1]; out->max_norm_prim = info[2]; out->max_norm_dual = info[3];
     out->rho = rho_;
@@ -1701,6 +1822,8 @@ int cosmo_b200_default_settings(cosmo_b200_settings* s) {
   s->COSMO_INFTY = 1e20; s->MIN_SCALING = 1e-4;
   s->time_limit = 0.0; s->tol_constant = 1.0; s->tol_exponent = 1.5;
   s->verbose = 0; s->psd_max_sweeps = 30;
+  s->accelerator = COSMO_B200_ACC_EMPTY; s->accelerator_mem = 15; s->accelerator_min_mem = 3;
+  s->safeguard = 1; s->safeguard_tol = 2.0;
   return COSMO_B200_OK;
 }
 

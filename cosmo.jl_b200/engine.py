@@ -22,6 +22,7 @@ ZERO, NONNEG, BOX, SOC, PSD_SQUARE, PSD_TRIANGLE, EXP, DUAL_EXP, POW, DUAL_POW =
 STATUS = {0: "Undetermined", 1: "Solved", 2: "Max_iter_reached", 3: "Time_limit_reached",
           4: "Primal_infeasible", 5: "Dual_infeasible", 6: "Unsolved"}
 KKT_CG, KKT_MINRES_REDUCED, KKT_MINRES = 0, 1, 2
+ACC_EMPTY, ACC_ANDERSON = 0, 1
 
 
 class EngineError(RuntimeError):
@@ -58,7 +59,9 @@ class SettingsStruct(C.Structure):
                 ("RHO_MIN", C.c_double), ("RHO_MAX", C.c_double), ("RHO_TOL", C.c_double),
                 ("RHO_EQ_OVER_RHO_INEQ", C.c_double), ("COSMO_INFTY", C.c_double), ("MIN_SCALING", C.c_double),
                 ("time_limit", C.c_double), ("tol_constant", C.c_double), ("tol_exponent", C.c_double),
-                ("verbose", C.c_int32), ("psd_max_sweeps", C.c_int32)]
+                ("verbose", C.c_int32), ("psd_max_sweeps", C.c_int32),
+                ("accelerator", C.c_int32), ("accelerator_mem", C.c_int32), ("accelerator_min_mem", C.c_int32),
+                ("safeguard", C.c_int32), ("safeguard_tol", C.c_double)]
 
 
 class ResultStruct(C.Structure):

@@ -226,7 +226,13 @@ class Settings:
     tol_constant: float = 1.0
     tol_exponent: float = 1.5
     psd_max_sweeps: int = 30
-    accelerator: str = "EmptyAccelerator"     # Anderson acceleration is SURVEY 8f-1 (next)
+    # "EmptyAccelerator" | "AndersonAccelerator" (= AndersonAccelerator{T, Type2{QRDecomp}, RestartedMemory,
+    # NoRegularizer} with ImmediateActivation, the reference's default family, settings.jl:136-138)
+    accelerator: str = "EmptyAccelerator"
+    accelerator_mem: int = 15
+    accelerator_min_mem: int = 3
+    safeguard: bool = True
+    safeguard_tol: float = 2.0
 
     _KKT = {"CGIndirectKKTSolver": _eng.KKT_CG, "MINRESIndirectKKTSolver": _eng.KKT_MINRES,
             "IndirectReducedKKTSolver:MINRES": _eng.KKT_MINRES_REDUCED}
@@ -236,18 +242,22 @@ class Settings:
             raise _eng.EngineError(_eng.ERR_UNSUPPORTED,
                                    "kkt_solver %r is a direct CPU factorisation; the B200 engine implements "
                                    "CGIndirectKKTSolver / MINRESIndirectKKTSolver" % self.kkt_solver)
-        if self.accelerator != "EmptyAccelerator":
-            raise _eng.EngineError(_eng.ERR_UNSUPPORTED, "only accelerator = EmptyAccelerator is implemented")
+        if self.accelerator not in ("EmptyAccelerator", "AndersonAccelerator"):
+            raise _eng.EngineError(_eng.ERR_UNSUPPORTED,
+                                   "accelerator %r: the engine implements EmptyAccelerator and AndersonAccelerator"
+                                   "{T, Type2{QRDecomp}, RestartedMemory, NoRegularizer}" % self.accelerator)
         s = _eng.default_settings()
         for name in ("rho", "sigma", "alpha", "eps_abs", "eps_rel", "eps_prim_inf", "eps_dual_inf", "max_iter",
                      "check_termination", "check_infeasibility", "scaling", "adaptive_rho_interval",
                      "adaptive_rho_tolerance", "adaptive_rho_max_adaptions", "RHO_MIN", "RHO_MAX", "RHO_TOL",
                      "RHO_EQ_OVER_RHO_INEQ", "COSMO_INFTY", "MIN_SCALING", "time_limit", "tol_constant",
-                     "tol_exponent", "psd_max_sweeps"):
+                     "tol_exponent", "psd_max_sweeps", "accelerator_mem", "accelerator_min_mem", "safeguard_tol"):
             setattr(s, name, getattr(self, name))
         s.adaptive_rho = int(self.adaptive_rho)
         s.verbose = int(self.verbose)
         s.kkt_solver = self._KKT[self.kkt_solver]
+        s.accelerator = _eng.ACC_ANDERSON if self.accelerator == "AndersonAccelerator" else _eng.ACC_EMPTY
+        s.safeguard = int(self.safeguard)
         return s
 
 

@@ -80,6 +80,9 @@ enum {
   COSMO_B200_UNSOLVED = 6
 };
 
+/* accelerators (COSMOAccelerators.jl types selectable through settings.accelerator) */
+enum { COSMO_B200_ACC_EMPTY = 0, COSMO_B200_ACC_ANDERSON = 1 };
+
 /* KKT plugins (src/linear_solver/kktsolver_indirect.jl:173-189) */
 enum {
   COSMO_B200_KKT_CG = 0,             /* CGIndirectKKTSolver      (reduced system, CG)      :3-88   */
@@ -144,6 +147,13 @@ typedef struct {
   double tol_constant, tol_exponent; /* kktsolver_indirect.jl:21,168-170 */
   int32_t verbose;
   int32_t psd_max_sweeps;            /* Jacobi eigensolver sweep cap (engine-specific) */
+  /* accelerator (settings.jl:96-98,136-138; accelerator_interface.jl:58-114) */
+  int32_t accelerator;         /* COSMO_B200_ACC_EMPTY | COSMO_B200_ACC_ANDERSON (Type2{QRDecomp}, RestartedMemory,
+                                  NoRegularizer, ImmediateActivation) */
+  int32_t accelerator_mem;     /* history length `mem` (reference default 15) */
+  int32_t accelerator_min_mem; /* columns needed before a candidate is formed (package default 3) */
+  int32_t safeguard;           /* settings.safeguard */
+  double safeguard_tol;        /* settings.safeguard_tol (2.0) */
 } cosmo_b200_settings;
 
 /* COSMO.Result / ResultInfo / ResultTimes (types.jl:26-41, 65-71, 93-112) */

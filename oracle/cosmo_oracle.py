@@ -526,6 +526,106 @@ class Settings:
     kkt_solver: str = "direct"  # "direct" (QDLDL stand-in) | "cg" | "minres" | "minres_reduced"
     tol_constant: float = 1.0   # kktsolver_indirect.jl:21
     tol_exponent: float = 1.5
+    # accelerator (settings.jl:136-138).  The reference default is "anderson" (Type-II, QR, restarted memory,
+    # mem = 15, safeguarded); the oracle defaults to "empty" (= EmptyAccelerator, docs/src/acceleration.md:9-12)
+    # because only that configuration is pinned iterate by iterate.
+    accelerator: str = "empty"
+    accelerator_mem: int = 15
+    accelerator_min_mem: int = 3
+    safeguard: bool = True
+    safeguard_tol: float = 2.0
+
+
+# --------------------------------------------------------------------------
+# Accelerator (COSMOAccelerators.jl ^0.1.0 -- NOT under /root/reference).
+# PARITY UNPINNED: restated from the published method (Garstka, Cannon, Goulart,
+# "Safeguarded Anderson acceleration for parametric nonexpansive operators", 2022,
+# Alg. 2: type-II Anderson acceleration, least squares by an updated QR factorisation,
+# memory restarted when full) and from the call sites in the reference
+# (accelerator_interface.jl:58-130, solver.jl:143,157,274-292, setup.jl:10-14,44-50).
+# The constants min_mem = 3 and the |eta|_2 > 1e4 rejection are the package defaults
+# as remembered; the reference's own tests pin this path only behaviourally
+# (AccelerationTests: status :Solved, #restarts == #rho adaptions).
+# --------------------------------------------------------------------------
+class AndersonAccelerator:
+    """AndersonAccelerator{T, Type2{QRDecomp}, RestartedMemory, NoRegularizer}(dim; mem)."""
+
+    def __init__(self, dim, mem=15, min_mem=3):
+        if mem <= 2:
+            raise ValueError("Memory has to be bigger than two.")
+        self.dim = dim
+        self.mem = min(mem, dim)
+        self.min_mem = min_mem
+        self.G = np.zeros((dim, self.mem))   # columns g_k - g_{k-1}
+        self.Q = np.zeros((dim, self.mem))   # F = [f_k - f_{k-1}] = Q R
+        self.R = np.zeros((self.mem, self.mem))
+        self.g_last = np.zeros(dim)
+        self.f = np.zeros(dim)
+        self.f_last = np.zeros(dim)
+        self.eta = np.zeros(self.mem)
+        self.iter = 0
+        self.init_phase = True
+        self.success = False
+        self.num_accelerated_steps = 0
+        self.log = []   # (iteration, event) like CA.log!
+
+    def empty_caches(self):
+        self.G[:] = 0.0
+        self.Q[:] = 0.0
+        self.R[:] = 0.0
+        self.iter = 0
+
+    def restart(self):   # CA.restart!: forget the history; the next update! only stores (x, g, f)
+        self.empty_caches()
+        self.init_phase = True
+
+    def update(self, g, x, num_iter):
+        """CA.update!(aa, g, x, num_iter) with g = w = T(w_prev), x = w_prev."""
+        self.f[:] = x - g
+        if self.init_phase:
+            self.g_last[:] = g
+            self.f_last[:] = self.f
+            self.init_phase = False
+            return
+        j = self.iter % self.mem          # 0-based column that receives the new differences
+        if j == 0 and self.iter != 0:     # RestartedMemory: history full -> start again
+            self.empty_caches()
+            self.log.append((num_iter, "memory_full"))
+        self.G[:, j] = g - self.g_last
+        df = self.f - self.f_last
+        self.g_last[:] = g
+        self.f_last[:] = self.f
+        # qr!: modified Gram-Schmidt update of F = Q R by the new column
+        q = df
+        for i in range(j):
+            self.R[i, j] = self.Q[:, i] @ q
+            q = q - self.R[i, j] * self.Q[:, i]
+        self.R[j, j] = np.linalg.norm(q)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            self.Q[:, j] = q / self.R[j, j]
+        self.iter += 1
+
+    def accelerate(self, g, x, num_iter):
+        """CA.accelerate!(g, x, aa, num_iter): overwrites g with g - G eta, eta = argmin |f - F eta|_2."""
+        l = min(self.iter, self.mem)
+        if l < self.min_mem:
+            self.success = False
+            return
+        eta = self.Q[:, :l].T @ self.f
+        Rl = self.R[:l, :l]
+        ok = bool(np.all(np.diag(Rl) != 0.0) and np.all(np.isfinite(Rl)))
+        if ok:
+            for i in range(l - 1, -1, -1):       # back substitution (LAPACK trtrs 'U','N','N')
+                eta[i] = (eta[i] - Rl[i, i + 1:] @ eta[i + 1:]) / Rl[i, i]
+            ok = bool(np.all(np.isfinite(eta)) and np.linalg.norm(eta) <= 1e4)
+        if not ok:
+            self.success = False
+            self.log.append((num_iter, "acc_failed"))
+            return
+        self.eta[:l] = eta
+        g -= self.G[:, :l] @ eta
+        self.num_accelerated_steps += 1
+        self.success = True
 
 
 # --------------------------------------------------------------------------
@@ -907,6 +1007,7 @@ class Result:
     rho_vec: Optional[np.ndarray] = None
     kkt: object = None
     history: Optional[list] = None
+    safeguarding_iter: int = 0   # iter = ADMM iterations + safeguarding_iter (solver.jl:195-199)
 
 
 class Workspace:
@@ -927,6 +1028,8 @@ class Workspace:
         self.is_scaled = False
         self.is_optimized = False
         self.kkt = None
+        self.accelerator = None
+        self.accelerator_active = False
         self.rho_updates: List[float] = []
 
     # warm starts in *unscaled* coordinates, interface.jl:117-179
@@ -960,6 +1063,13 @@ class Workspace:
             self.rho_vec = self.rho * np.ones(self.m)
             apply_constraint_rho_scaling(self.rho_vec, self.cones, st)
             self.rho_updates.append(self.rho)
+        # setup.jl:44-50: build the accelerator with the KKT solver, restart it on a re-solve
+        if self.kkt is None:
+            self.accelerator = (AndersonAccelerator(self.n + self.m, st.accelerator_mem, st.accelerator_min_mem)
+                                if st.accelerator == "anderson" else None)
+        elif self.accelerator is not None:
+            self.accelerator.restart()
+        self.accelerator_active = False
         if self.kkt is None:
             self.kkt = make_kkt_solver(st.kkt_solver, self.P, self.A, st.sigma, self.rho_vec, st)
 
@@ -1094,27 +1204,60 @@ class Workspace:
         x_tl, s_tl = admm_x()
         admm_w(x_tl, s_tl)
 
-        while it < st.max_iter:
+        aa = self.accelerator
+        safeguarding_iter = 0
+
+        def update_suggested(due):  # solver.jl:284-292: postponed to the next non-accelerated iteration
+            return due and not (aa is not None and aa.success)
+
+        def admm_z():  # admm_z!, :7-21
+            tp = time.perf_counter()
+            self.s[:] = self.w[n:]
+            project(self.s, self.cones)
+            times["proj_time"] += time.perf_counter() - tp
+
+        while it + safeguarding_iter < st.max_iter:
             it += 1
-            if infeasibility_check_due:  # solver.jl:145-148
+            # acceleration_pre!, accelerator_interface.jl:58-75 (ImmediateActivation, :24-28)
+            if aa is not None:
+                if not self.accelerator_active and it >= 2:
+                    self.accelerator_active = True
+                if self.accelerator_active:
+                    aa.update(self.w, self.w_prev, it)
+                    aa.accelerate(self.w, self.w_prev, it)   # overwrites w
+            if update_suggested(infeasibility_check_due):  # solver.jl:145-148
                 self.recover_mu()
                 dy[:] = self.mu
             self.w_prev[:] = self.w  # :151
-            tp = time.perf_counter()
-            self.s[:] = self.w[n:]   # admm_z!, :7-21
-            project(self.s, self.cones)
-            times["proj_time"] += time.perf_counter() - tp
+            admm_z()
             # apply_rho_adaptation_rules!, :242-282 (interval > 0 only: deterministic)
             if st.adaptive_rho and st.adaptive_rho_interval > 0 and it % st.adaptive_rho_interval == 0 \
                     and (len(self.rho_updates) - 1) < st.adaptive_rho_max_adaptions:
                 rho_update_due = True
-            if rho_update_due:
+            if update_suggested(rho_update_due):
                 rho_update_due = False
                 self.recover_mu()
                 if self.adapt_rho_vec():
+                    if aa is not None:   # the operator changed: restart the accelerator, :272-275
+                        aa.restart()
+                        aa.log.append((it, "rho_adapted"))
                     self.w[n:] = self.mu / self.rho_vec + self.s  # :278
             x_tl, s_tl = admm_x()
             admm_w(x_tl, s_tl)
+            # acceleration_post!, accelerator_interface.jl:85-114: safeguarding
+            if aa is not None and self.accelerator_active and aa.success and st.safeguard:
+                nrm_tol = np.linalg.norm(aa.f) * st.safeguard_tol
+                aa.f[:] = self.w_prev - self.w        # compute_accelerated_res_norm!, :120-123
+                if np.linalg.norm(aa.f) > nrm_tol:
+                    aa.log.append((it, "acc_guarded_declined"))
+                    self.w_prev[:] = aa.g_last          # reset_accelerated_vector!, :126-130
+                    self.w[:] = aa.g_last
+                    admm_z()
+                    x_tl, s_tl = admm_x()
+                    admm_w(x_tl, s_tl)
+                    safeguarding_iter += 1
+                else:
+                    aa.log.append((it, "acc_guarded_accepted"))
             if record_history:
                 history.append(self.w.copy())
             if iter_callback is not None:
@@ -1135,7 +1278,7 @@ class Workspace:
                     break
             if it % st.check_infeasibility == 0:
                 infeasibility_check_due = True
-            elif infeasibility_check_due:
+            elif update_suggested(infeasibility_check_due):
                 infeasibility_check_due = False
                 self.recover_mu()
                 dy -= self.mu
@@ -1153,7 +1296,7 @@ class Workspace:
 
         self.recover_mu()  # :167
         times["iter_time"] = time.perf_counter() - iter_start
-        if it == st.max_iter and status == "Undetermined":
+        if it + safeguarding_iter == st.max_iter and status == "Undetermined":
             res_info = self.calculate_result_info()
             status = "Max_iter_reached"
         w_exit = self.w.copy()
@@ -1170,8 +1313,8 @@ class Workspace:
         self.s[:] = s
         self.mu[:] = mu
         times["solver_time"] = time.perf_counter() - t0
-        return Result(x, -mu, s, cost, it, status, res_info, times, w=w_exit,
-                      rho_vec=self.rho_vec.copy(), kkt=self.kkt, history=history)
+        return Result(x, -mu, s, cost, it + safeguarding_iter, status, res_info, times, w=w_exit,
+                      rho_vec=self.rho_vec.copy(), kkt=self.kkt, history=history, safeguarding_iter=safeguarding_iter)
 
     # update!(q, b), interface.jl:187-211
     def update(self, q=None, b=None):

@@ -344,6 +344,27 @@ def test_iterate_parity_first_iterations(scaling):
         assert np.isclose(res.info.r_dual, ref.info.r_dual, rtol=1e-6, atol=1e-12)
 
 
+@pytest.mark.parametrize("scaling", [0, 10])
+def test_accelerated_iterates_match_oracle(scaling):
+    # Anderson acceleration (aa.cuh) against the oracle's restatement of the same method: the history update,
+    # the QR least squares, the candidate and the safeguard decisions.  The least-squares solve amplifies
+    # rounding by cond(R), so the trajectories are compared over the first accelerated iterations only and
+    # to 1e-6 (the plain ADMM trajectories above agree to 1e-8).
+    P, q, A, b, sets = _small_qp(seed=7)
+    cones = cosmo_b200.problems.to_oracle_cones(sets)
+    for iters in (2, 5, 14, 45):  # first update, first candidate (3 columns), memory almost full, restart + rho adaption
+        ost = O.Settings(kkt_solver="cg", scaling=scaling, max_iter=iters, eps_abs=1e-14, eps_rel=1e-14, accelerator="anderson")
+        ref = O.solve(P, q, A, b, cones, ost)
+        model = cosmo_b200.Model()
+        model.set(P, q, A, b, sets, cosmo_b200.Settings(scaling=scaling, max_iter=iters, eps_abs=1e-14, eps_rel=1e-14,
+                                                        accelerator="AndersonAccelerator"))
+        res = model.optimize()
+        w = model.engine.w()
+        assert res.iter == ref.iter == iters and res.safeguarding_iter == ref.safeguarding_iter
+        assert np.linalg.norm(w - ref.w) / np.linalg.norm(ref.w) < 1e-6, iters
+        assert np.allclose(res.x, ref.x, rtol=1e-5, atol=1e-7)
+
+
 # ---------------------------------------------------------------------------
 # solve-level parity on the reference's literal problems
 # ---------------------------------------------------------------------------
@@ -419,6 +440,45 @@ def test_g15_g16_exp_pow_cone_problems(name, builder, status, obj, atol, kw):
     if obj is not None:
         assert abs(res.obj_val - obj) < atol
         assert abs(res.obj_val - ref.obj_val) < 1e-4 and np.allclose(res.x, ref.x, atol=1e-3)
+
+
+_AA_MINE = dict(accelerator="AndersonAccelerator")
+_AA_REF = dict(accelerator="anderson")
+
+
+@pytest.mark.parametrize("builder,x,obj,tol", [(G.g1_qp_nonneg, G.G1_X, G.G1_OBJ, 1e-3), (G.g1_qp_box, G.G1_X, G.G1_OBJ, 1e-3),
+                                               (G.g12_lp, G.G12_X, G.G12_OBJ, 1e-2), (G.g3_hs21, G.G3_X, G.G3_OBJ, 1e-3),
+                                               (G.g13_lovasz_petersen, None, G.G13_OBJ, 1e-3)])
+def test_accelerated_solves_reach_the_reference_answers(builder, x, obj, tol):
+    # the reference runs these with its default (accelerated) settings; the accelerated oracle is the comparison
+    res, _ = _solve_mine(builder, **_AA_MINE)
+    ref = _solve_oracle(builder, **_AA_REF)
+    plain = _solve_oracle(builder)
+    assert res.status == "Solved" == ref.status and abs(res.obj_val - obj) < tol
+    if x is not None:
+        assert np.max(np.abs(res.x - x)) < tol
+    assert abs(res.iter - ref.iter) <= 30 and res.iter <= plain.iter + 1
+    assert np.allclose(res.x, ref.x, atol=10 * tol)
+
+
+def test_accelerated_statuses_and_exp_pow_problems():
+    assert _solve_mine(G.g2_box_primal_infeasible_1, **_AA_MINE)[0].status == "Primal_infeasible"
+    assert _solve_mine(G.g2_box_dual_infeasible, check_infeasibility=20, scaling=0, **_AA_MINE)[0].status == "Dual_infeasible"
+    for name, builder, status, obj, atol, kw in G.G15_G16:
+        res, _ = _solve_mine(builder, **kw, **_AA_MINE)
+        assert res.status == status, name
+        if obj is not None:
+            assert abs(res.obj_val - obj) < atol, name
+
+
+def test_accelerator_rho_adaption_limits():
+    # AccelerationTests/max_rho_adaption.jl:21-36 with the accelerator on: exactly 2, then exactly 1 adaption
+    res, _ = _solve_mine(G.g1_qp_nonneg, adaptive_rho_interval=25, adaptive_rho_max_adaptions=2, rho=1e-6, eps_abs=1e-6,
+                         eps_rel=1e-4, **_AA_MINE)
+    assert len(res.info.rho_updates) - 1 == 2
+    res, _ = _solve_mine(G.g1_qp_nonneg, adaptive_rho_interval=25, adaptive_rho_max_adaptions=1, rho=1e-6, eps_abs=1e-4,
+                         eps_rel=1e-4, **_AA_MINE)
+    assert len(res.info.rho_updates) - 1 == 1
 
 
 @pytest.mark.parametrize("scaling", [0, 10])

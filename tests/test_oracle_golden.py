@@ -200,3 +200,80 @@ def test_exp_pow_projections_land_in_cone():
             w = v.copy()
             O.project_cone(w, cone)          # idempotence (up to the iteration tolerances)
             assert np.max(np.abs(w - v)) < 1e-3 * (1.0 + np.max(np.abs(v)))
+
+
+# ---------------------------------------------------------------------------
+# Accelerated runs (the reference's default: Anderson type-II, QR, restarted memory 15, safeguarded).
+# COSMOAccelerators.jl is not part of the reference tree -> iterate-level parity unpinned; what the
+# reference's own tests pin is behaviour, reproduced here.
+# ---------------------------------------------------------------------------
+_AA = dict(accelerator="anderson")
+
+
+@pytest.mark.parametrize("builder,x,obj,tol", [(G.g1_qp_nonneg, G.G1_X, G.G1_OBJ, 1e-3), (G.g1_qp_box, G.G1_X, G.G1_OBJ, 1e-3),
+                                               (G.g12_lp, G.G12_X, G.G12_OBJ, 1e-2), (G.g3_hs21, G.G3_X, G.G3_OBJ, 1e-3),
+                                               (G.g13_lovasz_petersen, None, G.G13_OBJ, 1e-3)])
+def test_accelerated_runs_reach_the_reference_answers(builder, x, obj, tol):
+    # simple.jl:21-47, examples/lp.jl, moi_wrapper.jl:219-276, lovasz_petersen.jl run with default settings
+    # (accelerator on) in the reference; test/UnitTests/AccelerationTests/anderson_accelerator.jl asks :Solved
+    plain, _ = _solve(builder)
+    res, _ = _solve(builder, **_AA)
+    assert res.status == "Solved" and abs(res.obj_val - obj) < tol
+    if x is not None:
+        assert np.max(np.abs(res.x - x)) < tol
+    assert res.iter <= plain.iter + 1      # never slower than plain ADMM on these, usually 2-6x faster
+    assert res.iter == (res.iter - res.safeguarding_iter) + res.safeguarding_iter and res.safeguarding_iter >= 0
+
+
+def test_accelerated_statuses_of_infeasible_problems():
+    assert _solve(G.g2_box_primal_infeasible_1, **_AA)[0].status == "Primal_infeasible"
+    assert _solve(G.g2_box_primal_infeasible_2, **_AA)[0].status == "Primal_infeasible"
+    assert _solve(G.g2_box_dual_infeasible, check_infeasibility=20, scaling=0, **_AA)[0].status == "Dual_infeasible"
+    for name, builder, status, obj, atol, kw in G.G15_G16:
+        res, _ = _solve(builder, **kw, **_AA)
+        assert res.status == status, name
+        if obj is not None:
+            assert abs(res.obj_val - obj) < atol, name
+
+
+def test_accelerator_restarts_and_max_rho_adaptions():
+    P, q, cons = G.g1_qp_nonneg()
+    Pm, qm, A, b, cones = O.assemble(P, q, cons)
+    # AccelerationTests/max_rho_adaption.jl:21-36 (default accelerator): exactly 2, then exactly 1 adaption
+    ws = O.Workspace(Pm, qm, A, b, cones, O.Settings(adaptive_rho_interval=25, adaptive_rho_max_adaptions=2, rho=1e-6,
+                                                     eps_abs=1e-6, eps_rel=1e-4, **_AA))
+    ws.optimize()
+    assert len(ws.rho_updates) - 1 == 2
+    ws = O.Workspace(Pm, qm, A, b, cones, O.Settings(adaptive_rho_interval=25, adaptive_rho_max_adaptions=1, rho=1e-6,
+                                                     eps_abs=1e-4, eps_rel=1e-4, **_AA))
+    ws.optimize()
+    assert len(ws.rho_updates) - 1 == 1
+    # AccelerationTests/adaptive_rho_acc_restarts.jl:19-25: one accelerator restart per rho adaption
+    ws = O.Workspace(Pm, qm, A, b, cones, O.Settings(adaptive_rho_interval=23, rho=1e-4, safeguard=False,
+                                                     accelerator_mem=5, **_AA))
+    res = ws.optimize()
+    assert res.status == "Solved"
+    assert sum(1 for e in ws.accelerator.log if e[1] == "rho_adapted") == len(ws.rho_updates) - 1 >= 1
+
+
+def test_anderson_qr_solves_the_least_squares_problem():
+    # the updated QR factorisation reproduces numpy's least squares solution of min |f - F eta|
+    rng = np.random.default_rng(3)
+    dim, mem = 40, 6
+    aa = O.AndersonAccelerator(dim, mem)
+    M = rng.standard_normal((dim, dim)) * 0.1
+    x = rng.standard_normal(dim)
+    fs, gs = [], []
+    for k in range(mem + 1):
+        g = M @ x + 1.0
+        aa.update(g, x, k + 2)
+        fs.append(x - g); gs.append(g.copy())
+        x = g
+    F = np.column_stack([fs[i + 1] - fs[i] for i in range(mem)])
+    Gm = np.column_stack([gs[i + 1] - gs[i] for i in range(mem)])
+    assert np.allclose(aa.Q[:, :mem] @ aa.R[:mem, :mem], F, atol=1e-12)
+    eta = np.linalg.lstsq(F, fs[-1], rcond=None)[0]
+    g_acc = gs[-1].copy()
+    aa.accelerate(g_acc, x, mem + 2)
+    assert aa.success and np.allclose(aa.eta[:mem], eta, rtol=1e-8, atol=1e-10)
+    assert np.allclose(g_acc, gs[-1] - Gm @ eta, atol=1e-9)
