@@ -159,7 +159,7 @@ def nccl_unique_id() -> bytes:
 
 
 class SolveOutput:
-    __slots__ = ("x", "s", "mu", "obj_val", "iter", "status", "r_prim", "r_dual", "max_norm_prim", "max_norm_dual",
+    __slots__ = ("x", "s", "mu", "obj_val", "iter", "safeguarding_iter", "status", "r_prim", "r_dual", "max_norm_prim", "max_norm_dual",
                  "rho", "rho_updates", "times", "kkt_inner_iterations", "kkt_multiplications", "kernel_launches")
 
 
@@ -309,6 +309,7 @@ class Engine:
         o = SolveOutput()
         o.x, o.s, o.mu = x, s, mu
         o.obj_val, o.iter, o.status = r.obj_val, r.iter, STATUS[r.status]
+        o.safeguarding_iter = r.safeguarding_iter
         o.r_prim, o.r_dual, o.max_norm_prim, o.max_norm_dual = r.r_prim, r.r_dual, r.max_norm_prim, r.max_norm_dual
         o.rho = r.rho
         o.rho_updates = rho_updates[:min(r.n_rho_updates, rho_updates.shape[0])].copy()

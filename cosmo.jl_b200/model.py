@@ -505,7 +505,7 @@ class Model:
         times["setup_time"] = setup_time
         times["solver_time"] = time.perf_counter() - t0
         info = ResultInfo(out.r_prim, out.r_dual, out.max_norm_prim, out.max_norm_dual, list(out.rho_updates))
-        return Result(x, -mu, s, out.obj_val, out.iter, 0, out.status, info, times,
+        return Result(x, -mu, s, out.obj_val, out.iter, out.safeguarding_iter, out.status, info, times,
                       kkt_inner_iterations=out.kkt_inner_iterations, kernel_launches=out.kernel_launches)
 
     def empty_model(self):  # empty_model!, interface.jl:84-100
