@@ -23,8 +23,16 @@ Parity pinning
   **parity unpinned** at iterate level for these two; they are pinned at
   solution level against the direct KKT solve (as the reference's own disabled
   test kktsolver.jl:104-109 demands).
-* The accelerator (COSMOAccelerators.jl) is not restated: the oracle runs the
-  reference with ``accelerator = EmptyAccelerator``.
+* The exponential / power cones are pinned on the ten known-answer problems of
+  test/UnitTests/exp_cone.jl and pow_cone.jl and the property test of sets.jl:84-110.
+* The accelerator lives in COSMOAccelerators.jl (^0.1.0), NOT vendored under the
+  reference tree.  ``AndersonAccelerator`` restates the reference's default variant
+  (type-II, QR-updated least squares, restarted memory, no regulariser) from the
+  published method and the call sites accelerator_interface.jl:58-130: **parity
+  unpinned** at iterate level; pinned behaviourally as the reference's own
+  AccelerationTests do (status, #restarts == #rho adaptions, max adaptions) and by
+  the accelerated runs reaching the reference's known answers.  The default stays
+  ``accelerator = "empty"`` (EmptyAccelerator), the iterate-level pinned setting.
 """
 from __future__ import annotations
 
