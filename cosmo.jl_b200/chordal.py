@@ -18,6 +18,10 @@ Restated (not ported) from the reference:
     the clique's row and -1 in the parent's row of the same (i,j)
   * reverse_decomposition!                       chordal_decomposition.jl:129-213 (x truncated, s = sum of
     blocks, mu = block value)
+  * psd_completion! / psd_complete!               chordal_decomposition.jl:215-311 (`complete_dual`): the entries
+    of the dual matrix outside the pattern are chosen so that Y = -mat(mu) is positive semidefinite -- the
+    maximum-determinant completion, clique by clique from the root of the clique tree
+    (Vandenberghe & Andersen, Chordal Graphs and Semidefinite Optimization, alg. 10.2)
 """
 from __future__ import annotations
 
@@ -186,6 +190,7 @@ class DecompositionInfo:
     cone_offsets: Dict[int, int] = field(default_factory=dict)
     num_overlaps: int = 0
     clique_sizes: List[int] = field(default_factory=list)
+    trees: Dict[int, "CliqueTree"] = field(default_factory=dict)   # clique tree of every decomposed cone
 
 
 def decompose(P, q, A, b, sets, merge: str = "parent_child", min_dim: int = 3):
@@ -236,6 +241,7 @@ def decompose(P, q, A, b, sets, merge: str = "parent_child", min_dim: int = 3):
             nc = len(c)
             row_ptr += nc * (nc + 1) // 2
         info.cone_offsets[k] = off
+        info.trees[k] = tree
         info.blocks[k] = [(starts[t], tree.cliques[t]) for t in range(len(tree.cliques))]
         info.clique_sizes += [len(c) for c in tree.cliques]
         # owner (clique, local row) of every pattern entry; overlaps get +1/-1 columns
@@ -288,9 +294,77 @@ def decompose(P, q, A, b, sets, merge: str = "parent_child", min_dim: int = 3):
     return P2, q2, A2, b2, sets_new, info
 
 
-def reverse(info: DecompositionInfo, x2, s2, mu2):
+def psd_complete(Y: np.ndarray, tree: CliqueTree) -> np.ndarray:
+    """psd_complete! (chordal_decomposition.jl:262-311): fill the entries of the symmetric matrix `Y` that lie
+    outside the cliques of `tree` so that the result is positive semidefinite (given that every clique block
+    is).  Cliques are visited parents first; for clique k with separator alpha = C_k & C_parent and residual
+    nu = C_k minus alpha, the unknown entries between nu and eta = (vertices of the cliques visited so far) minus C_k are
+        Y[eta, nu] = Y[eta, alpha] Y[alpha, alpha]^-1 Y[alpha, nu]
+    (pseudo-inverse when the separator block is singular, as the reference's try/catch does)."""
+    W = np.array(Y, dtype=np.float64)
+    W = np.triu(W) + np.triu(W, 1).T
+    ncl = len(tree.cliques)
+    children: List[List[int]] = [[] for _ in range(ncl)]
+    roots = []
+    for k, p in enumerate(tree.parent):
+        (children[p] if p >= 0 else roots).append(k)
+    seen = np.zeros(W.shape[0], dtype=bool)
+    stack = list(reversed(roots))
+        while stack:
+        k = stack.pop()
+        c = tree.cliques[k]
+        alpha = tree.sep[k] if tree.parent[k] >= 0 else np.zeros(0, dtype=np.int64)
+        nu = np.setdiff1d(c, alpha)
+        eta = np.nonzero(seen)[0]
+        eta = np.setdiff1d(eta, c)
+        if len(eta) and len(nu):
+            if len(alpha):
+                Waa = W[np.ix_(alpha, alpha)]
+                Wan = W[np.ix_(alpha, nu)]
+                try:
+                    Z = np.linalg.solve(Waa, Wan)
+                    if not np.all(np.isfinite(Z)):
+                        raise np.linalg.LinAlgError
+                except np.linalg.LinAlgError:
+                    Z = np.linalg.pinv(Waa) @ Wan
+                blk = W[np.ix_(eta, alpha)] @ Z
+            else:   # a new connected component: no coupling with what was completed before
+                blk = np.zeros((len(eta), len(nu)))
+            W[np.ix_(eta, nu)] = blk
+            W[np.ix_(nu, eta)] = blk.T
+        seen[c] = True
+        stack.extend(reversed(children[k]))
+    return W
+
+
+def _svec_to_mat(v: np.ndarray, N: int) -> np.ndarray:
+    """populate_upper_triangle!(X, v, 1/sqrt 2) + symmetrise (convexset.jl:432-442)"""
+    X = np.zeros((N, N))
+    iu = np.triu_indices(N)
+    # column-major upper triangle: (0,0), (0,1), (1,1), (0,2) ...
+    order = np.lexsort((iu[0], iu[1]))
+    X[iu[0][order], iu[1][order]] = v
+    X = X + np.triu(X, 1).T
+    off = ~np.eye(N, dtype=bool)
+    X[off] /= np.sqrt(2.0)
+    return X
+
+
+def _mat_to_svec(X: np.ndarray) -> np.ndarray:
+    N = X.shape[0]
+    iu = np.triu_indices(N)
+    order = np.lexsort((iu[0], iu[1]))
+    i, j = iu[0][order], iu[1][order]
+    v = X[i, j].copy()
+    v[i != j] *= np.sqrt(2.0)
+    return v
+
+
+def reverse(info: DecompositionInfo, x2, s2, mu2, complete_dual: bool = False):
     """reverse_decomposition! (chordal_decomposition.jl:129-213): x = x'[1:n]; s = sum of clique blocks;
-    mu = the clique block's value (overlaps carry equal values at optimality)."""
+    mu = the clique block's value (overlaps carry equal values at optimality).  With `complete_dual`
+    (settings.complete_dual, :146) the entries of every decomposed dual matrix outside its cliques are
+    filled by `psd_complete` so that y = -mu is in the PSD cone."""
     x = np.asarray(x2)[:info.n_orig].copy()
     s = np.zeros(info.m_orig)
     mu = np.zeros(info.m_orig)
@@ -308,4 +382,10 @@ def reverse(info: DecompositionInfo, x2, s2, mu2):
                 seg = slice(start + svec_index(0, bj), start + svec_index(bj, bj) + 1)
                 s[orig] += s2[seg]
                 mu[orig] = mu2[seg]
+        if complete_dual:   # complete!(mu, ::PsdConeTriangle, ...), chordal_decomposition.jl:245-257
+            S = info.sets_orig[k]
+            N = S.sqrt_dim
+            seg = slice(off, off + S.dim)
+            Y = psd_complete(_svec_to_mat(-mu[seg], N), info.trees[k])
+            mu[seg] = -_mat_to_svec(Y)
     return x, s, mu

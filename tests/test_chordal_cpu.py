@@ -69,3 +69,54 @@ def test_random_banded_maxcut_decomposition(merge):
     assert np.allclose(x, ref.x, atol=2e-3 * max(1, np.abs(ref.x).max()))
     # the reassembled slack is PSD and satisfies the original equality A x + s = b
     assert np.max(np.abs(A @ x + s - b)) < 1e-3
+
+
+def test_psd_completion_of_a_banded_matrix():
+    # psd_complete! (chordal_decomposition.jl:262-311): keep the entries of a positive definite matrix on a
+    # chordal pattern, complete the rest -> PSD, pattern entries untouched, inverse has the pattern's zeros
+    # (the maximum-determinant completion), and a matrix that is already "its own completion" is reproduced
+    rng = np.random.default_rng(3)
+    nv = 30
+    rows, cols, _ = cosmo_b200.problems.banded_random_graph(nv, 3.0, 4, seed=5)
+    for merge in ("none", "parent_child"):
+        tree = chordal.chordal_cliques(nv, rows, cols)
+        if merge == "parent_child":
+            tree = chordal.parent_child_merge(tree)
+        B = rng.standard_normal((nv, nv))
+        X = B @ B.T + nv * np.eye(nv)
+        mask = np.zeros((nv, nv), dtype=bool)
+        for c in tree.cliques:
+            mask[np.ix_(c, c)] = True
+        Y = chordal.psd_complete(np.where(mask, X, 0.0), tree)
+        assert np.allclose(Y, Y.T) and np.allclose(Y[mask], X[mask])
+        assert np.linalg.eigvalsh(Y).min() > 1e-8
+        Yinv = np.linalg.inv(Y)
+        assert np.max(np.abs(Yinv[~mask])) < 1e-9 * np.abs(Yinv).max()      # zeros of the inverse off the pattern
+        Y2 = chordal.psd_complete(np.where(mask, Y, 0.0), tree)             # idempotent
+        assert np.allclose(Y2, Y, atol=1e-9)
+
+
+def test_g15_maxcut_completed_dual_recovers_the_primal_matrix():
+    # examples/maxcut.jl:73-83: the dual variable of the PSD constraint of the dual MAXCUT SDP is the primal
+    # matrix Y (Y_ii = 1, Y PSD, 1/4 <L, Y> = optimum); after the decomposition only its clique entries are
+    # determined and `complete_dual` fills the rest
+    rows = np.array([0, 0, 1, 1, 2]); cols = np.array([1, 3, 2, 3, 3]); w = np.array([1.0, 8, 2, 10, 6])
+    P, q, A, b, sets = cosmo_b200.problems.maxcut_dual_sdp(4, rows, cols, w)
+    P2, q2, A2, b2, sets2, info = chordal.decompose(P, q, A, b, sets, merge="none")
+    dec = _solve_oracle(P2, q2, A2, b2, sets2, eps_abs=1e-8, eps_rel=1e-8, scaling=0)
+    x, s, mu = chordal.reverse(info, dec.x, dec.s, -dec.y, complete_dual=True)
+    x0, s0, mu0 = chordal.reverse(info, dec.x, dec.s, -dec.y)
+    Y = chordal._svec_to_mat(-mu, 4)
+    Y0 = chordal._svec_to_mat(-mu0, 4)
+    assert Y0[0, 2] == 0.0 and abs(Y[0, 2]) > 1e-3                  # (1,3) is the only entry outside the cliques
+    keep = np.ones((4, 4), dtype=bool); keep[0, 2] = keep[2, 0] = False
+    assert np.allclose(Y[keep], Y0[keep])
+    assert np.linalg.eigvalsh(Y).min() > -1e-6 and np.allclose(np.diag(Y), 1.0, atol=1e-4)
+    L = np.zeros((4, 4))
+    for a, c_, ww in zip(rows, cols, w):
+        L[a, a] += ww; L[c_, c_] += ww; L[a, c_] -= ww; L[c_, a] -= ww
+    assert abs(0.25 * np.sum(L * Y) - dec.obj_val) < 1e-3
+    # the undecomposed solve returns a PSD dual matrix with the same clique entries
+    ref = _solve_oracle(P, q, A, b, sets, eps_abs=1e-8, eps_rel=1e-8, scaling=0)
+    Yref = chordal._svec_to_mat(ref.y, 4)
+    assert np.allclose(Yref[keep], Y[keep], atol=1e-3)
