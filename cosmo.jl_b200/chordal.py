@@ -310,7 +310,7 @@ def psd_complete(Y: np.ndarray, tree: CliqueTree) -> np.ndarray:
         (children[p] if p >= 0 else roots).append(k)
     seen = np.zeros(W.shape[0], dtype=bool)
     stack = list(reversed(roots))
-        while stack:
+    while stack:
         k = stack.pop()
         c = tree.cliques[k]
         alpha = tree.sep[k] if tree.parent[k] >= 0 else np.zeros(0, dtype=np.int64)
