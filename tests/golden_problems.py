@@ -229,3 +229,97 @@ G15_G16 = [
     ("pow_dual_infeasible", g16_pow_dual_infeasible, "Dual_infeasible", None, None, {}),
     ("dualpow_feasible", g16_dualpow_feasible, "Solved", -1.0, 1e-3, {}),
 ]
+
+
+# ---------------------------------------------------------------------------
+# G4 / G5 / G6 / G11
+# ---------------------------------------------------------------------------
+def _svec_scale(N):
+    """diagonal of the map 'unscaled upper triangle (MOI) -> svec' (sqrt 2 on off-diagonal entries)"""
+    out = []
+    for j in range(N):
+        for i in range(j + 1):
+            out.append(1.0 if i == j else np.sqrt(2.0))
+    return np.array(out)
+
+
+def g4_small_sdp():
+    """test/UnitTests/moi_wrapper.jl:39-106 — min <C,X> s.t. <A1,X> = 11, <A2,X> = 19, X PSD (3x3), x = upper
+    triangle of X by columns; the test asserts the two constraint primals (11, 19 at atol 1e-3)."""
+    A1_t = np.array([1.0, 0, 3, 2, 14, 5])
+    A2_t = np.array([0.0, 4, 6, 16, 0, 4])
+    C_t = np.array([1.0, 4, 9, 6, 0, 7])
+    cons = [O.Constraint(A1_t[None, :], [-11.0], O.ZeroSet(1)), O.Constraint(A2_t[None, :], [-19.0], O.ZeroSet(1)),
+            O.Constraint(np.diag(_svec_scale(3)), np.zeros(6), O.PsdConeTriangle(6))]
+    return np.zeros((6, 6)), C_t, cons
+
+
+G4_A1 = np.array([1.0, 0, 3, 2, 14, 5])
+G4_A2 = np.array([0.0, 4, 6, 16, 0, 4])
+
+
+def g5_sigma_max_lmi():
+    """test/UnitTests/nuclear_norm_minimization.jl:16-41 — min t s.t. [tI Y; Y' tI] PSD (PsdConeTriangle(21)),
+    Y[2,1] <= 4, Y[2,2] >= 3, sum(Y) >= 12; x = [t; vec(Y)].  Expected: t = sigma_max(Y) (1e-3)."""
+    q = np.concatenate([[1.0], np.zeros(9)])
+    c1 = np.zeros((1, 10)); c1[0, 2] = -1.0
+    c2 = np.zeros((1, 10)); c2[0, 5] = 1.0
+    c3 = np.concatenate([[0.0], np.ones(9)])[None, :]
+    A_lmi = np.zeros((21, 10))
+    for r in (0, 2, 5, 9, 14, 20):                       # diagonal entries of the 6x6 matrix
+        A_lmi[r, 0] = -1.0
+    for col, r in enumerate((6, 7, 8, 10, 11, 12, 15, 16, 17)):   # rows 7,8,9,11,12,13,16,17,18 (1-based)
+        A_lmi[r, 1 + col] = -np.sqrt(2.0)
+    cons = [O.Constraint(c1, [4.0], O.Nonnegatives(1)), O.Constraint(c2, [-3.0], O.Nonnegatives(1)),
+            O.Constraint(c3, [-12.0], O.Nonnegatives(1)), O.Constraint(-A_lmi, np.zeros(21), O.PsdConeTriangle(21))]
+    return np.zeros((10, 10)), q, cons
+
+
+def g6_chordal_sdp_data():
+    """examples/chordal_decomposition.jl:7-10 — min c'x s.t. B - A1 x1 - A2 x2 PSD (9x9, common sparsity pattern)."""
+    A1 = np.array([[-4.0, 0, -2, 0, 0, -1, 0, 0, 0], [0, -3, -1, 0, 0, 0, 0, 0, 0], [-2, -1, -2, 0, 0, 5, 4, -4, 0],
+                   [0, 0, 0, -4, -5, 0, 0, 3, 0], [0, 0, 0, -5, 4, 0, 0, 2, 0], [-1, 0, 5, 0, 0, 5, -4, -4, -5],
+                   [0, 0, 4, 0, 0, -4, -1, -1, -3], [0, 0, -4, 3, 2, -4, -1, 2, -2], [0, 0, 0, 0, 0, -5, -3, -2, -3]])
+    A2 = np.array([[-5.0, 0, 3, 0, 0, -2, 0, 0, 0], [0, -3, -5, 0, 0, 0, 0, 0, 0], [3, -5, 3, 0, 0, 5, -4, -5, 0],
+                   [0, 0, 0, 3, 2, 0, 0, -2, 0], [0, 0, 0, 2, 4, 0, 0, -3, 0], [-2, 0, 5, 0, 0, 1, -5, -2, -4],
+                   [0, 0, -4, 0, 0, -5, -2, -3, 3], [0, 0, -5, -2, -3, -2, -3, 5, 3], [0, 0, 0, 0, 0, -4, 3, 3, -4]])
+    B = np.array([[-0.11477375644968069, 0, 6.739182490600791, 0, 0, -1.2185593245043502, 0, 0, 0],
+                  [0, 1.2827680528587497, -5.136452036888789, 0, 0, 0, 0, 0, 0],
+                  [6.739182490600791, -5.136452036888789, 7.344770673489607, 0, 0, -0.2224400187044442, -10.505300166831221,
+                   -1.2627361794562273, 0],
+                  [0, 0, 0, 10.327710040060499, 8.91534585379813, 0, 0, -6.525873789637007, 0],
+                  [0, 0, 0, 8.91534585379813, 0.8370459338528677, 0, 0, -6.210900615408826, 0],
+                  [-1.2185593245043502, 0, -0.2224400187044442, 0, 0, -3.8185953011245024, -0.994033914192722,
+                   2.8156077981712997, 1.4524716674219218],
+                  [0, 0, -10.505300166831221, 0, 0, -0.994033914192722, 0.029162208619863517, -2.8123790276830745,
+                   7.663416446183705],
+                  [0, 0, -1.2627361794562273, -6.525873789637007, -6.210900615408826, 2.8156077981712997,
+                   -2.8123790276830745, 4.71893305728242, 6.322431630550857],
+                  [0, 0, 0, 0, 0, 1.4524716674219218, 7.663416446183705, 6.322431630550857, 0.5026094532322212]])
+    c = np.array([-0.21052661285686525, -1.263324575834677])
+    return A1, A2, B, c
+
+
+def _svec(M):
+    N = M.shape[0]
+    out = []
+    for j in range(N):
+        for i in range(j + 1):
+            out.append(M[i, j] if i == j else np.sqrt(2.0) * M[i, j])
+    return np.array(out)
+
+
+def g6_chordal_sdp():
+    """the same problem as a PsdConeTriangle(45) constraint  svec(B) - svec(A1) x1 - svec(A2) x2 in K."""
+    A1, A2, B, c = g6_chordal_sdp_data()
+    A = -np.column_stack([_svec(A1), _svec(A2)])
+    return np.zeros((2, 2)), c, [O.Constraint(A, _svec(B), O.PsdConeTriangle(45))]
+
+
+G6_CLIQUES = [[0, 2, 5], [1, 2], [2, 5, 6, 7], [3, 4, 7], [5, 6, 7, 8]]   # docs/src/decomposition.md:43 (0-based)
+
+
+def g11_iteration_limit():
+    """test/UnitTests/moi_wrapper.jl:201-217 — max x s.t. x >= 10 with max_iter = 2: Max_iter_reached,
+    rho_updates == [0.1]."""
+    return np.zeros((1, 1)), np.array([-1.0]), [O.Constraint([[1.0]], [-10.0], O.Nonnegatives(1))]

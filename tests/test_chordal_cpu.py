@@ -120,3 +120,53 @@ def test_g15_maxcut_completed_dual_recovers_the_primal_matrix():
     ref = _solve_oracle(P, q, A, b, sets, eps_abs=1e-8, eps_rel=1e-8, scaling=0)
     Yref = chordal._svec_to_mat(ref.y, 4)
     assert np.allclose(Yref[keep], Y[keep], atol=1e-3)
+
+
+def _mine(cons):
+    out = []
+    for c in cons:
+        S = c.convex_set
+        out.append((c.A, c.b, getattr(cosmo_b200, type(S).__name__)(S.dim)))
+    return out
+
+
+def _assemble_mine(builder):
+    P, q, cons = builder()
+    model = cosmo_b200.Model()
+    cosmo_b200.assemble(model, P, q, [cosmo_b200.Constraint(A, b, S) for A, b, S in _mine(cons)], cosmo_b200.Settings())
+    return model.P0, model.q0, model.A0, model.b0, model.sets0
+
+
+def test_g6_documented_cliques_and_decomposed_optimum():
+    from tests import golden_problems as G
+    P, q, A, b, sets = _assemble_mine(G.g6_chordal_sdp)
+    P2, q2, A2, b2, sets2, info = chordal.decompose(P, q, A, b, sets, merge="none")
+    # docs/src/decomposition.md:43: {1,3,6}, {2,3}, {3,6,7,8}, {4,5,8}, {6,7,8,9}
+    assert sorted(sorted(c.tolist()) for _, c in info.blocks[0]) == sorted(G.G6_CLIQUES)
+    ref = _solve_oracle(P, q, A, b, sets, eps_abs=1e-7, eps_rel=1e-7)
+    dec = _solve_oracle(P2, q2, A2, b2, sets2, eps_abs=1e-7, eps_rel=1e-7)
+    assert ref.status == dec.status == "Solved" and abs(ref.obj_val - dec.obj_val) < 1e-4
+    x, s, mu = chordal.reverse(info, dec.x, dec.s, -dec.y, complete_dual=True)
+    assert np.allclose(x, ref.x, atol=1e-3)
+    A1, A2m, B, c = G.g6_chordal_sdp_data()
+    S = B - A1 * x[0] - A2m * x[1]
+    assert np.linalg.eigvalsh(S).min() > -1e-4                      # primal feasible
+    Y = chordal._svec_to_mat(-mu, 9)                                 # completed dual (examples/...: complete_dual = true)
+    assert np.linalg.eigvalsh(Y).min() > -1e-4
+    assert abs(np.sum(S * Y)) < 1e-2 * max(1.0, np.abs(S).max() * np.abs(Y).max())   # complementary slackness
+    # stationarity of  min c'x  s.t.  B - A1 x1 - A2 x2 = S >= 0 :  c_i + <A_i, Y> = 0
+    assert abs(np.sum(A1 * Y) + c[0]) < 1e-3 and abs(np.sum(A2m * Y) + c[1]) < 1e-3
+
+
+def test_g5_sigma_max_lmi_decomposed():
+    # nuclear_norm_minimization.jl:16-41 runs with decompose = true, compact_transformation = true
+    from tests import golden_problems as G
+    P, q, A, b, sets = _assemble_mine(G.g5_sigma_max_lmi)
+    P2, q2, A2, b2, sets2, info = chordal.decompose(P, q, A, b, sets, merge="none")
+    assert len(sets2) > len(sets)                                    # the 6x6 arrow pattern does decompose
+    dec = _solve_oracle(P2, q2, A2, b2, sets2)
+    assert dec.status == "Solved"
+    x, s, mu = chordal.reverse(info, dec.x, dec.s, -dec.y)
+    Y = x[1:].reshape(3, 3, order="F")
+    assert Y[1, 0] <= 4 + 1e-6 and Y[1, 1] >= 3 - 1e-6 and Y.sum() - 12.0 >= -1e-3
+    assert abs(np.linalg.svd(Y, compute_uv=False).max() - x[0]) <= 1e-3

@@ -443,6 +443,50 @@ def test_g15_g16_exp_pow_cone_problems(name, builder, status, obj, atol, kw):
         assert abs(res.obj_val - ref.obj_val) < 1e-4 and np.allclose(res.x, ref.x, atol=1e-3)
 
 
+def test_g4_g5_g11_literal_problems():
+    # G4 moi_wrapper.jl:39-106 (constraint primals 11 / 19 at 1e-3, check_termination = 1)
+    res, _ = _solve_mine(G.g4_small_sdp, check_termination=1)
+    ref = _solve_oracle(G.g4_small_sdp, check_termination=1)
+    assert res.status == "Solved" == ref.status and abs(res.iter - ref.iter) <= 2
+    assert abs(G.G4_A1 @ res.x - 11.0) < 1e-3 and abs(G.G4_A2 @ res.x - 19.0) < 1e-3
+    assert np.allclose(res.x, ref.x, atol=1e-4)
+    # G5 nuclear_norm_minimization.jl:31-40: t = sigma_max(Y) at 1e-3, the three inequalities hold
+    res, _ = _solve_mine(G.g5_sigma_max_lmi)
+    ref = _solve_oracle(G.g5_sigma_max_lmi)
+    Y = res.x[1:].reshape(3, 3, order="F")
+    assert res.status == "Solved" == ref.status and res.iter == ref.iter
+    assert Y[1, 0] <= 4 + 1e-6 and Y[1, 1] >= 3 - 1e-6 and Y.sum() - 12.0 >= -1e-3
+    assert abs(np.linalg.svd(Y, compute_uv=False).max() - res.x[0]) <= 1e-3 and abs(res.obj_val - ref.obj_val) < 1e-6
+    # G11 moi_wrapper.jl:201-217: two iterations, ITERATION_LIMIT, rho never adapted
+    res, _ = _solve_mine(G.g11_iteration_limit, max_iter=2)
+    assert res.status == "Max_iter_reached" and res.iter == 2 and list(res.info.rho_updates) == [0.1]
+
+
+def test_g6_chordal_sdp_through_the_clique_batch():
+    # examples/chordal_decomposition.jl:7-23 with NoMerge: the documented cliques (docs/src/decomposition.md:43)
+    # become five PsdConeTriangle blocks projected in one batched launch; optimum = the undecomposed optimum
+    # (Agler), and the completed dual (complete_dual = true) is PSD.  Default tolerances: with the CG plugin
+    # and its 1/k^1.5 tolerance schedule neither the engine nor the oracle reaches eps = 1e-7 on this P = 0
+    # problem within max_iter (both report Max_iter_reached, measured), at 1e-5 both solve it.
+    from cosmo_b200 import chordal
+    P, q, cons = G.g6_chordal_sdp()
+    Pm, qm, A0, b0, cones0 = O.assemble(P, q, cons)
+    sets0 = [cosmo_b200.PsdConeTriangle(45)]
+    P2, q2, A2, b2, sets2, info = chordal.decompose(Pm, qm, A0, b0, sets0, merge="none")
+    assert sorted(sorted(c.tolist()) for _, c in info.blocks[0]) == sorted(G.G6_CLIQUES)
+    model = cosmo_b200.Model()
+    model.set(P2, q2, A2, b2, sets2, cosmo_b200.Settings())
+    dec = model.optimize()
+    ref = O.solve(P2, q2, A2, b2, cosmo_b200.problems.to_oracle_cones(sets2), O.Settings(kkt_solver="cg"))
+    full = O.solve(Pm, qm, A0, b0, cones0, O.Settings(eps_abs=1e-7, eps_rel=1e-7))      # undecomposed, direct KKT
+    assert dec.status == "Solved" == ref.status == full.status
+    assert abs(dec.iter - ref.iter) <= 50 and abs(dec.obj_val - ref.obj_val) < 1e-4
+    assert abs(dec.obj_val - full.obj_val) < 1e-3
+    x, s, mu = chordal.reverse(info, dec.x, dec.s, -dec.y, complete_dual=True)
+    assert np.allclose(x, full.x, atol=1e-3)
+    assert np.linalg.eigvalsh(chordal._svec_to_mat(-mu, 9)).min() > -1e-3
+
+
 _AA_MINE = dict(accelerator="AndersonAccelerator")
 _AA_REF = dict(accelerator="anderson")
 

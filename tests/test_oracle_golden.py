@@ -277,3 +277,29 @@ def test_anderson_qr_solves_the_least_squares_problem():
     aa.accelerate(g_acc, x, mem + 2)
     assert aa.success and np.allclose(aa.eta[:mem], eta, rtol=1e-8, atol=1e-10)
     assert np.allclose(g_acc, gs[-1] - Gm @ eta, atol=1e-9)
+
+
+def test_g4_small_sdp_constraint_primals():
+    # moi_wrapper.jl:39-106: <A1, X> = 11, <A2, X> = 19 at atol 1e-3 (check_termination = 1 there), X PSD
+    res, _ = _solve(G.g4_small_sdp, check_termination=1)
+    assert res.status == "Solved"
+    assert abs(G.G4_A1 @ res.x - 11.0) < 1e-3 and abs(G.G4_A2 @ res.x - 19.0) < 1e-3
+    X = np.zeros((3, 3))
+    X[np.triu_indices(3)] = res.x[[0, 1, 3, 2, 4, 5]]     # x = (X11, X12, X22, X13, X23, X33)
+    X = X + np.triu(X, 1).T
+    assert np.linalg.eigvalsh(X).min() > -1e-4
+
+
+def test_g5_sigma_max_lmi():
+    # nuclear_norm_minimization.jl:31-40 (undecomposed here; the decomposed run is in test_chordal_cpu.py)
+    res, _ = _solve(G.g5_sigma_max_lmi)
+    assert res.status == "Solved"
+    Y = res.x[1:].reshape(3, 3, order="F")
+    assert Y[1, 0] <= 4 + 1e-6 and Y[1, 1] >= 3 - 1e-6 and Y.sum() - 12.0 >= -1e-3
+    assert abs(np.linalg.svd(Y, compute_uv=False).max() - res.x[0]) <= 1e-3
+
+
+def test_g11_iteration_limit_keeps_rho():
+    res, _ = _solve(G.g11_iteration_limit, max_iter=2)
+    assert res.status == "Max_iter_reached" and res.iter == 2
+    assert list(res.info.rho_updates) == [0.1]
