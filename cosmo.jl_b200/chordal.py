@@ -11,8 +11,11 @@ Restated (not ported) from the reference:
     any perfect elimination ordering gives a valid decomposition, only the clique set differs)
   * supernodes / cliques / clique tree          trees.jl:390-513 (Pothen-Sun rule: v joins a child's
     supernode iff |hadj(child)| = |hadj(v)| + 1)
-  * merge strategy                              NoMerge, or ParentChildMerge(t_fill, t_size)
-    (clique_merging.jl:278-285, 641-648); the default CliqueGraphMerge is not restated
+  * merge strategy                              NoMerge; ParentChildMerge(t_fill, t_size) in two flavours --
+    `parent_child` (bottom-up variant with the clique-size rule, the one the C5 measurements use) and
+    `parent_child_reference` (the reference's top-down walk, clique_merging.jl:262-283, 641-648);
+    `clique_graph` = CliqueGraphMerge, the reference default (reduced clique graph, complexity weights,
+    permissible edges, clique tree rebuilt by Kruskal; clique_graph.jl, clique_merging.jl:34-67, 204-259, 305-600)
   * compact ("clique tree based") augmentation  transformations.jl:152-374: every clique becomes a
     PsdConeTriangle block; an entry (i,j) inside the separator of a clique gets a new variable with +1 in
     the clique's row and -1 in the parent's row of the same (i,j)
@@ -179,6 +182,255 @@ def parent_child_merge(tree: CliqueTree, t_fill: int = 8, t_size: int = 8) -> Cl
     return CliqueTree(cliques, par2, seps, tree.order)
 
 
+def _tree_from_sets(cl: List[set], parent: List[int], order: np.ndarray) -> CliqueTree:
+    cliques = [np.array(sorted(c), dtype=np.int64) for c in cl]
+    seps = [np.intersect1d(c, cliques[parent[k]]) if parent[k] >= 0 else np.zeros(0, dtype=np.int64)
+            for k, c in enumerate(cliques)]
+    return CliqueTree(cliques, list(parent), seps, order)
+
+
+def _post_order(parent: List[int]) -> List[int]:
+    """children before parents, roots last (post_order, trees.jl)"""
+    n = len(parent)
+    children: List[List[int]] = [[] for _ in range(n)]
+    roots = []
+    for k, p in enumerate(parent):
+        (children[p] if p >= 0 else roots).append(k)
+    out: List[int] = []
+    for r in roots:
+        stack = [(r, 0)]
+        while stack:
+            v, i = stack.pop()
+            if i < len(children[v]):
+                stack.append((v, i + 1))
+                stack.append((children[v][i], 0))
+            else:
+                out.append(v)
+    return out
+
+
+def parent_child_merge_reference(tree: CliqueTree, t_fill: int = 8, t_size: int = 8, snd_post: Optional[List[int]] = None,
+                                 return_log: bool = False):
+    """ParentChildMerge exactly as the reference walks it (clique_merging.jl:98-106 initialise!, :262-283
+    traverse / evaluate, :177-201 merge_child!, :295-303 update_strategy!): the supernode tree is traversed in
+    descending topological order (root first); clique c is merged into its *current* parent when
+        (|C_par| - |sep_c|) (|C_c| - |sep_c|) <= t_fill   or   max(|snd_c|, |snd_par|) <= t_size ,
+    with snd = clique minus its separator.  A merge moves only the child's supernode into the parent's."""
+    n = len(tree.cliques)
+    sep = [set(x.tolist()) for x in tree.sep]
+    snd = [set(c.tolist()) - sep[k] for k, c in enumerate(tree.cliques)]
+    parent = list(tree.parent)
+    children: List[set] = [set() for _ in range(n)]
+    for k, p in enumerate(parent):
+        if p >= 0:
+            children[p].add(k)
+    post = list(snd_post) if snd_post is not None else _post_order(parent)
+    log_pairs, log_dec = [], []
+    for ind in range(n - 2, -1, -1):             # clique_ind = length(snd) - 1 ... 1 (1-based)
+        c = post[ind]
+        par = parent[c]
+        if par < 0:                               # a second root (disconnected pattern): nothing to merge into
+            continue
+        d_snd, d_sep = len(snd[c]), len(sep[c])
+        p_snd, p_sep = len(snd[par]), len(sep[par])
+        fill = ((p_snd + p_sep) - d_sep) * ((d_snd + d_sep) - d_sep)
+        do_merge = fill <= t_fill or max(d_snd, p_snd) <= t_size
+        log_pairs.append((par, c))
+        log_dec.append(do_merge)
+        if do_merge:                              # merge_child!
+            snd[par] |= snd[c]
+            snd[c] = set()
+            sep[c] = set()
+            for g in children[c]:
+                parent[g] = par
+            parent[c] = -2                        # removed
+            children[par].discard(c)
+            children[par] |= children[c]
+            children[c] = set()
+    alive = [k for k in range(n) if parent[k] != -2]
+    idx = {k: i for i, k in enumerate(alive)}
+    cl = [snd[k] | sep[k] for k in alive]
+    par2 = [idx[parent[k]] if parent[k] >= 0 else -1 for k in alive]
+    out = _tree_from_sets(cl, par2, tree.order)
+    return (out, log_pairs, log_dec) if return_log else out
+
+
+# ---- CliqueGraphMerge (the reference's default merge strategy) ------------------------------------------
+def reduced_clique_graph(cliques: List[set], seps: List[set]) -> Tuple[List[int], List[int]]:
+    """compute_reduced_clique_graph! (clique_graph.jl:19-49, Habib & Stacho): for every separator, largest
+    first, the cliques that contain it form the separator graph H (an edge when two of them intersect in more
+    than the separator); two such cliques get an edge of the reduced clique graph iff they lie in different
+    connected components of H.  Returns (rows, cols) with row > col; separators that occur several times in
+    `seps` contribute their edges several times (the reference then *adds* the duplicate weights)."""
+    rows: List[int] = []
+    cols: List[int] = []
+    for separator in sorted(seps, key=len, reverse=True):      # sort! is stable, as is sorted()
+        if not separator:
+            # the empty separator of a root would link every pair of cliques from different connected components
+            # of the pattern (O(p^2) edges of weight n1^3 + n2^3 - (n1+n2)^3 < 0 that can never be merged and never
+            # make an edge impermissible); they are left out, so a disconnected pattern keeps a forest
+            continue
+        ind = [k for k, c in enumerate(cliques) if separator <= c]
+        H: Dict[int, List[int]] = {v: [] for v in ind}
+        for a in range(len(ind)):
+            for b_ in range(a + 1, len(ind)):
+                ca, cb = ind[a], ind[b_]
+                if (cliques[ca] & cliques[cb]) != separator:    # inter_equal, clique_graph.jl:113-131
+                    H[ca].append(cb)
+                    H[cb].append(ca)
+        comp: Dict[int, int] = {}
+        for v in ind:                                            # find_components (DFS)
+            if v in comp:
+                continue
+            comp[v] = v
+            stack = [v]
+            while stack:
+                u = stack.pop()
+                for w in H[u]:
+                    if w not in comp:
+                        comp[w] = v
+                        stack.append(w)
+        for a in range(len(ind)):
+            for b_ in range(a + 1, len(ind)):
+                ca, cb = ind[a], ind[b_]
+                if comp[ca] != comp[cb]:
+                    rows.append(max(ca, cb))
+                    cols.append(min(ca, cb))
+    return rows, cols
+
+
+def _complexity_weight(c_a: set, c_b: set) -> float:
+    """ComplexityWeight: |Ca|^3 + |Cb|^3 - |Ca u Cb|^3 (clique_merging.jl:24-31, 395-405)"""
+    return float(len(c_a) ** 3 + len(c_b) ** 3 - len(c_a | c_b) ** 3)
+
+
+class CliqueGraph:
+    """State of CliqueGraphMerge (clique_merging.jl:55-67): weighted edges of the reduced clique graph and the
+    adjacency table.  Edges are keyed (row, col) with row > col and iterated in CSC order (col, then row), the
+    order Julia's `findmax(edges.nzval)` / `findnz` see them in."""
+
+    def __init__(self, cliques: List[set], seps: List[set]):
+        self.snd = [set(c) for c in cliques]
+        self.num = len(cliques)
+        rows, cols = reduced_clique_graph(self.snd, [set(x) for x in seps])
+        self.edges: Dict[Tuple[int, int], float] = {}
+        for r, c in zip(rows, cols):                             # sparse(rows, cols, weights): duplicates add up
+            self.edges[(r, c)] = self.edges.get((r, c), 0.0) + _complexity_weight(self.snd[r], self.snd[c])
+        self.edges = {e: w for e, w in self.edges.items() if w != 0.0}
+        self.adj: Dict[int, set] = {k: set() for k in range(self.num)}
+        for (r, c) in self.edges:
+            self.adj[r].add(c)
+            self.adj[c].add(r)
+        self.log: List[Tuple[int, int, bool]] = []
+
+    def _csc(self):
+        return sorted(self.edges, key=lambda e: (e[1], e[0]))
+
+    def permissible(self, edge) -> bool:                        # ispermissible, clique_graph.jl:149-158
+        c1, c2 = edge
+        for nb in self.adj[c1] & self.adj[c2]:
+            if (self.snd[c1] & self.snd[nb]) != (self.snd[c2] & self.snd[nb]):
+                return False
+        return True
+
+    def traverse(self):                                          # clique_merging.jl:242-259
+        order = self._csc()
+        if not order:
+            return None
+        by_weight = sorted(order, key=lambda e: -self.edges[e])   # stable: ties keep CSC order
+        for e in by_weight:
+            if self.permissible(e):
+                return e
+        return None
+
+    def merge(self, edge) -> None:                              # merge_two_cliques! + update_strategy!
+        c1, removed = edge
+        self.snd[c1] |= self.snd[removed]
+        self.snd[removed] = set()
+        self.num -= 1
+        neighbors = set(self.adj[c1])
+        new_neighbors = self.adj[removed] - neighbors - {c1}
+        for nb in (neighbors - {removed}) | new_neighbors:
+            w = _complexity_weight(self.snd[c1], self.snd[nb])
+            key = (max(c1, nb), min(c1, nb))
+            if w != 0.0:
+                self.edges[key] = w
+            else:
+                self.edges.pop(key, None)                      # dropzeros!
+        for key in [e for e in self.edges if removed in e]:
+            del self.edges[key]
+        self.adj[c1] |= new_neighbors
+        for nb in new_neighbors:
+            self.adj[nb].add(c1)
+        del self.adj[removed]
+        for st in self.adj.values():
+            st.discard(removed)
+
+    def run(self) -> None:                                      # _merge_cliques!, clique_merging.jl:112-133
+        while self.num > 1:
+            cand = self.traverse()
+            if cand is None:
+                break
+            do_merge = self.edges[cand] >= 0                    # evaluate, :286-293
+            self.log.append((cand[0], cand[1], do_merge))
+            if not do_merge:
+                break
+            self.merge(cand)
+
+    def clique_tree(self, order: np.ndarray) -> CliqueTree:
+        """clique_tree_from_graph! (clique_merging.jl:577-600): maximum-weight spanning tree of the clique
+        graph under the weights |Ci & Cj| (Kruskal, :480-506), rooted at the clique that holds the vertex
+        eliminated last (:532-550)."""
+        alive = [k for k in range(len(self.snd)) if self.snd[k]]
+        inter = {e: float(len(self.snd[e[0]] & self.snd[e[1]])) for e in self._csc()}
+        edges_sorted = sorted(inter, key=lambda e: -inter[e])     # sortperm(V, rev = true), stable
+        uf = {k: k for k in alive}
+
+        def find(a):
+            while uf[a] != a:
+                uf[a] = uf[uf[a]]
+                a = uf[a]
+            return a
+
+        mst: Dict[int, List[int]] = {k: [] for k in alive}
+        found = 0
+        for (r, c) in edges_sorted:
+            if found >= len(alive) - 1:
+                break
+            ra, rb = find(r), find(c)
+            if ra != rb:
+                uf[ra] = rb
+                mst[r].append(c)
+                mst[c].append(r)
+                found += 1
+        parent = {k: -1 for k in alive}
+        seen = set()
+        last = int(order[-1]) if len(order) else -1
+        roots = [k for k in alive if last in self.snd[k]][:1] + alive
+        for r in roots:                                         # the pattern may be disconnected: several roots
+            if r in seen:
+                continue
+            seen.add(r)
+            stack = [r]
+            while stack:
+                u = stack.pop()
+                for v in sorted(mst[u]):
+                    if v not in seen:
+                        seen.add(v)
+                        parent[v] = u
+                        stack.append(v)
+        idx = {k: i for i, k in enumerate(alive)}
+        return _tree_from_sets([self.snd[k] for k in alive], [idx[parent[k]] if parent[k] >= 0 else -1 for k in alive], order)
+
+
+def clique_graph_merge(tree: CliqueTree) -> CliqueTree:
+    """CliqueGraphMerge(edge_weight = ComplexityWeight()), the reference's default `merge_strategy`
+    (settings.jl; clique_merging.jl:34-67, 147-166)."""
+    g = CliqueGraph([set(c.tolist()) for c in tree.cliques], [set(x.tolist()) for x in tree.sep])
+    g.run()
+    return g.clique_tree(tree.order)
+
+
 @dataclass
 class DecompositionInfo:
     n_orig: int
@@ -234,6 +486,12 @@ def decompose(P, q, A, b, sets, merge: str = "parent_child", min_dim: int = 3):
         tree = chordal_cliques(N, ii, jj)
         if merge == "parent_child":
             tree = parent_child_merge(tree)
+        elif merge == "parent_child_reference":
+            tree = parent_child_merge_reference(tree)
+        elif merge == "clique_graph":
+            tree = clique_graph_merge(tree)
+        elif merge != "none":
+            raise ValueError("merge must be 'none', 'parent_child', 'parent_child_reference' or 'clique_graph'")
         # row offsets of the clique blocks
         starts = []
         for c in tree.cliques:

@@ -170,3 +170,125 @@ def test_g5_sigma_max_lmi_decomposed():
     Y = x[1:].reshape(3, 3, order="F")
     assert Y[1, 0] <= 4 + 1e-6 and Y[1, 1] >= 3 - 1e-6 and Y.sum() - 12.0 >= -1e-3
     assert abs(np.linalg.svd(Y, compute_uv=False).max() - x[0]) <= 1e-3
+
+
+# ---------------------------------------------------------------------------
+# clique merging: the reference's literal fixtures, 1-based there, 0-based here
+# ---------------------------------------------------------------------------
+def _example_tree():
+    """test/UnitTests/DecompositionTests/clique_merging_example.jl:6-24"""
+    snd = [{15, 16, 17}, {5, 9}, {3, 4}, {1}, {2}, {6}, {7, 8}, {12, 13, 14}, {10, 11}]
+    sep = [set(), {15, 16}, {5, 15}, {3}, {3, 4}, {9, 16}, {9, 15}, {16, 17}, {13, 14, 17}]
+    parents = [0, 1, 2, 3, 3, 2, 2, 1, 8]
+    cliques = [np.array(sorted(a | b)) for a, b in zip(snd, sep)]
+    tree = chordal.CliqueTree(cliques, [p - 1 for p in parents], [np.array(sorted(x), dtype=np.int64) for x in sep],
+                              np.arange(1, 18))
+    return tree, snd, sep
+
+
+def test_g10_parent_child_merge_log():
+    # clique_merging_example.jl:88-97: pairs [1 2; 1 3; 1 4; 1 5; 1 6; 1 7; 1 8; 8 9],
+    # decisions [T T T T T F F T], 6 merges
+    tree, snd, sep = _example_tree()
+    out, pairs, dec = chordal.parent_child_merge_reference(tree, snd_post=list(range(8, -1, -1)), return_log=True)
+    assert [(a + 1, b + 1) for a, b in pairs] == [(1, 2), (1, 3), (1, 4), (1, 5), (1, 6), (1, 7), (1, 8), (8, 9)]
+    assert dec == [True, True, True, True, True, False, False, True] and sum(dec) == 6
+    got = sorted(sorted(c.tolist()) for c in out.cliques)
+    assert got == sorted([sorted({15, 16, 17, 5, 9, 3, 4, 1, 2, 6}), [7, 8, 9, 15], sorted({12, 13, 14, 16, 17, 10, 11})])
+    # first merge (:72-84): fill-in 2, supernode size 3
+    assert ((3 + 0) - 2) * ((2 + 2) - 2) == 2
+
+
+def test_g10_clique_graph_of_the_example_tree():
+    # clique_merging_example.jl:46-62, 102-121: edges of the reduced clique graph with their complexity weights;
+    # all weights are negative -> no merge, and the recomputed clique tree has the original parents
+    tree, snd, sep = _example_tree()
+    g = chordal.CliqueGraph([set(c.tolist()) for c in tree.cliques], [set(x.tolist()) for x in tree.sep])
+    rows = [2, 8, 3, 6, 7, 4, 5, 5, 9]
+    cols = [1, 1, 2, 2, 2, 3, 3, 4, 8]
+    ref = {}
+    for r, c in zip(rows, cols):
+        a, b = set(tree.cliques[r - 1].tolist()), set(tree.cliques[c - 1].tolist())
+        ref[(r - 1, c - 1)] = float(len(a) ** 3 + len(b) ** 3 - len(a | b) ** 3)
+    assert g.edges == ref and all(w < 0 for w in ref.values())
+    g.run()
+    assert sum(1 for e in g.log if e[2]) == 0
+    out = g.clique_tree(tree.order)
+    assert [p + 1 for p in out.parent] == [0, 1, 2, 3, 3, 2, 2, 1, 8]
+
+
+def _habib_stacho():
+    """reduced_clique_graph.jl:6-8 (Habib & Stacho 2011, Fig. 1)"""
+    snd = [{4, 5}, {1, 4, 6}, {1, 7}, {1, 8}, {1, 3, 4}, {1, 2, 3}, {2, 3, 9}, {3, 4, 11}, {3, 10}]
+    sep = [{1, 3}, {1, 4}, {2, 3}, {3, 4}, {1}, {3}, {4}]
+    return snd, sep
+
+
+def _valid_clique_tree(t):
+    """running intersection property (check_clique_tree of the reference's test utilities)"""
+    cl = [set(c.tolist()) for c in t.cliques]
+    for k, p in enumerate(t.parent):
+        if p < 0:
+            continue
+        anc, q = set(), p
+        while q >= 0:
+            anc |= cl[q]
+            q = t.parent[q]
+        if not (cl[k] & anc) <= cl[p]:
+            return False
+    return sum(1 for p in t.parent if p < 0) >= 1      # a forest when the pattern is disconnected
+
+
+def test_g10_reduced_clique_graph_habib_stacho():
+    # reduced_clique_graph.jl:10-43: edges, permissible edges
+    snd, sep = _habib_stacho()
+    rows, cols = chordal.reduced_clique_graph(snd, sep)
+    edges_ref = [(2, 1), (5, 1), (8, 1), (9, 8), (9, 5), (9, 7), (7, 6), (6, 4), (5, 4), (4, 2), (4, 3), (3, 2), (5, 3),
+                 (6, 3), (9, 6), (8, 5), (5, 2), (6, 5)]
+    got = {(r + 1, c + 1) for r, c in zip(rows, cols)}
+    assert got <= set(edges_ref) and got == set(edges_ref)
+    g = chordal.CliqueGraph(snd, sep)
+    permissible_ref = {edges_ref[i - 1] for i in (7, 11, 16, 17, 18)}
+    for e in g.edges:
+        if g.permissible(e):
+            assert (e[0] + 1, e[1] + 1) in permissible_ref
+
+
+def test_g10_merging_two_cliques_updates_the_graph():
+    # reduced_clique_graph.jl:46-87
+    snd, sep = _habib_stacho()
+    g = chordal.CliqueGraph(snd, sep)
+    assert g.edges[(4, 1)] < 0                                   # cand [5, 2]: evaluate is false ...
+    g.merge((4, 1))                                              # ... the test merges it anyway
+    assert g.snd[1] == set() and g.snd[4] == {1, 3, 4, 6}
+    assert 1 not in g.adj and not any(1 in s for s in g.adj.values())
+    g = chordal.CliqueGraph(snd, sep)
+    assert g.edges[(6, 5)] < 0
+    g.merge((6, 5))                                              # cand [7, 6]
+    assert g.snd[5] == set() and g.snd[6] == {1, 2, 3, 9}
+    assert 5 not in g.adj and not any(5 in s for s in g.adj.values())
+    t = g.clique_tree(np.arange(1, 12))                          # recomputation step -> a valid clique tree
+    assert len(t.cliques) == 8 and _valid_clique_tree(t)
+
+
+@pytest.mark.parametrize("merge", ["clique_graph", "parent_child_reference"])
+def test_merge_strategies_give_valid_decompositions(merge):
+    nv = 40
+    rows, cols, w = cosmo_b200.problems.banded_random_graph(nv, 3.0, 5, seed=4)
+    tree0 = chordal.chordal_cliques(nv, rows, cols)
+    tree = chordal.clique_graph_merge(tree0) if merge == "clique_graph" else chordal.parent_child_merge_reference(tree0)
+    assert len(tree.cliques) <= len(tree0.cliques) and _valid_clique_tree(tree)
+    cl0 = [set(c.tolist()) for c in tree0.cliques]
+    cl = [set(c.tolist()) for c in tree.cliques]
+    assert all(any(c <= d for d in cl) for c in cl0)             # merging only enlarges cliques
+    if merge == "clique_graph":                                  # every merge saved projection work
+        assert sum(len(c) ** 3 for c in cl) <= sum(len(c) ** 3 for c in cl0)
+    P, q, A, b, sets = cosmo_b200.problems.maxcut_dual_sdp(nv, rows, cols, w)
+    P2, q2, A2, b2, sets2, info = chordal.decompose(P, q, A, b, sets, merge=merge)
+    ref = _solve_oracle(P, q, A, b, sets, eps_abs=1e-6, eps_rel=1e-6)
+    dec = _solve_oracle(P2, q2, A2, b2, sets2, eps_abs=1e-6, eps_rel=1e-6)
+    assert ref.status == dec.status == "Solved"
+    assert abs(ref.obj_val - dec.obj_val) < 1e-3 * max(1, abs(ref.obj_val))
+    x, s, mu = chordal.reverse(info, dec.x, dec.s, -dec.y, complete_dual=True)
+    assert np.allclose(x, ref.x, atol=2e-3 * max(1, np.abs(ref.x).max()))
+    assert np.linalg.eigvalsh(chordal._svec_to_mat(-mu, nv)).min() > -1e-3
