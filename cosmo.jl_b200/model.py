@@ -233,6 +233,12 @@ class Settings:
     accelerator_min_mem: int = 3
     safeguard: bool = True
     safeguard_tol: float = 2.0
+    # chordal decomposition of PsdConeTriangle constraints (settings.jl:50-53,129-135; host side, chordal.py).
+    # The reference defaults to decompose = true with CliqueGraphMerge; here it is opt-in.
+    decompose: bool = False
+    merge_strategy: str = "CliqueGraphMerge"   # "NoMerge" | "ParentChildMerge" | "CliqueGraphMerge"
+    complete_dual: bool = False
+    compact_transformation: bool = True         # the only transformation restated
 
     _KKT = {"CGIndirectKKTSolver": _eng.KKT_CG, "MINRESIndirectKKTSolver": _eng.KKT_MINRES,
             "IndirectReducedKKTSolver:MINRES": _eng.KKT_MINRES_REDUCED}
@@ -378,6 +384,7 @@ class Model:
         self.engine: Optional[_eng.Engine] = None
         self.settings = Settings()
         self.times = {}
+        self._dec = None          # chordal DecompositionInfo of the problem the engine holds (settings.decompose)
 
     # assemble!(model, P, q, constraints; settings, x0, y0), interface.jl:30-77
     def assemble(self, P, q, constraints: Union[Constraint, Sequence[Constraint]], settings: Optional[Settings] = None,
@@ -428,6 +435,7 @@ class Model:
         self.mu = np.zeros(m)
         self.is_assembled = True
         self.is_scaled = False
+        self._dec = None
         if self.engine is not None:
             self.engine.close()
             self.engine = None
@@ -463,7 +471,11 @@ class Model:
             if b.shape != (self.m,):
                 raise ValueError("The dimension of b, does not agree with the model dimension, m.")
             self.b0 = b.copy()
-        if self.engine is not None:
+        if self.engine is not None and getattr(self, "_dec", None) is not None:
+            # the row map of b into the clique blocks is rebuilt with the decomposition at the next optimize!
+            self.engine.close()
+            self.engine = None
+        elif self.engine is not None:
             qs = (self.D * self.q0) * self.c if q is not None else None
             bs = self.E * self.b0 if b is not None else None
             self.engine.update_qb(qs, bs)
@@ -473,11 +485,29 @@ class Model:
         st = self.settings
         t0 = time.perf_counter()
         if self.engine is None:
+            # chordal_decomposition!(ws), chordal_decomposition.jl:1-30 (before setup!, solver.jl:88-93)
+            self._dec = None
+            P0, q0, A0, b0, sets0 = self.P0, self.q0, self.A0, self.b0, self.sets0
+            if st.decompose:
+                from . import chordal as _chordal
+                if not st.compact_transformation:
+                    raise _eng.EngineError(_eng.ERR_UNSUPPORTED, "only compact_transformation = true is implemented")
+                merge = {"NoMerge": "none", "ParentChildMerge": "parent_child_reference",
+                         "CliqueGraphMerge": "clique_graph"}.get(st.merge_strategy)
+                if merge is None:
+                    raise ValueError("unknown merge_strategy %r" % (st.merge_strategy,))
+                P2, q2, A2, b2, sets2, info = _chordal.decompose(P0, q0, A0, b0, sets0, merge=merge)
+                if info.blocks:                   # at least one cone was decomposed
+                    self._dec = info
+                    P0, q0, A0, b0, sets0 = P2, q2, A2, b2, sets2
+                    self._x2 = np.concatenate([self.x, np.zeros(A2.shape[1] - self.n)])
+                    self._s2, self._mu2 = np.zeros(A2.shape[0]), np.zeros(A2.shape[0])
+            m2, n2 = A0.shape
             if st.scaling != 0:
-                P, q, A, b, sets, D, E, c = ruiz_equilibrate(self.P0, self.q0, self.A0, self.b0, self.sets0, st)
+                P, q, A, b, sets, D, E, c = ruiz_equilibrate(P0, q0, A0, b0, sets0, st)
             else:
-                P, q, A, b, sets = self.P0, self.q0, self.A0, self.b0, self.sets0
-                D, E, c = np.ones(self.n), np.ones(self.m), 1.0
+                P, q, A, b, sets = P0, q0, A0, b0, sets0
+                D, E, c = np.ones(n2), np.ones(m2), 1.0
             self.D, self.E, self.c = D, E, c
             set_tuples = [set_tuple(S) for S in sets]
             self.engine = _eng.Engine(P, q, A, b, set_tuples, st.to_struct(),
@@ -486,7 +516,10 @@ class Model:
         else:
             self.engine.update_settings(st.to_struct())
         # scale_variables! (scaling.jl:118-123)
-        self.engine.warm_start(self.x / self.D, self.E * self.s, (self.mu / self.E) * self.c)
+        if self._dec is not None:   # the decomposed problem keeps its own iterates between solves
+            self.engine.warm_start(self._x2 / self.D, self.E * self._s2, (self._mu2 / self.E) * self.c)
+        else:
+            self.engine.warm_start(self.x / self.D, self.E * self.s, (self.mu / self.E) * self.c)
         return time.perf_counter() - t0
 
     # optimize!(model), solver.jl:78-203
@@ -500,6 +533,10 @@ class Model:
         x = self.D * out.x.astype(np.float64)
         s = out.s.astype(np.float64) / self.E
         mu = self.E * out.mu.astype(np.float64) / self.c
+        if self._dec is not None:   # reverse_decomposition! (+ psd_completion!), chordal_decomposition.jl:129-151
+            from . import chordal as _chordal
+            self._x2, self._s2, self._mu2 = x.copy(), s.copy(), mu.copy()
+            x, s, mu = _chordal.reverse(self._dec, x, s, mu, complete_dual=self.settings.complete_dual)
         self.x, self.s, self.mu = x.copy(), s.copy(), mu.copy()
         times = dict(out.times)
         times["setup_time"] = setup_time

@@ -485,6 +485,12 @@ def test_g6_chordal_sdp_through_the_clique_batch():
     x, s, mu = chordal.reverse(info, dec.x, dec.s, -dec.y, complete_dual=True)
     assert np.allclose(x, full.x, atol=1e-3)
     assert np.linalg.eigvalsh(chordal._svec_to_mat(-mu, 9)).min() > -1e-3
+    # the same through the solver-level flags (Settings(decompose = true, merge_strategy, complete_dual))
+    model = cosmo_b200.Model()
+    cosmo_b200.assemble(model, P, q, _to_mine(cons), cosmo_b200.Settings(decompose=True, merge_strategy="NoMerge", complete_dual=True))
+    res = model.optimize()
+    assert res.status == "Solved" and res.iter == dec.iter and abs(res.obj_val - dec.obj_val) < 1e-9
+    assert res.x.shape == (2,) and res.y.shape == (45,) and np.allclose(res.x, x, atol=1e-9) and np.allclose(res.y, -mu, atol=1e-9)
 
 
 _AA_MINE = dict(accelerator="AndersonAccelerator")
