@@ -366,6 +366,35 @@ def test_accelerated_iterates_match_oracle(scaling):
         assert np.allclose(res.x, ref.x, rtol=1e-5, atol=1e-7)
 
 
+def test_engine_matches_committed_golden_iterates():
+    # tests/golden/oracle_iterates.npz (generated by tests/golden/make_golden.py from the pinned oracle):
+    # w after k iterations of plain and accelerated runs, without running the oracle here
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_iterates.npz"))
+    P, q, A, b, sets = _small_qp(seed=7)
+    for acc, name in (("empty", "EmptyAccelerator"), ("anderson", "AndersonAccelerator")):
+        for scaling in (0, 10):
+            for iters in (5, 14, 33):
+                key = "qp40x70_seed7/%s/scaling%d/it%d" % (acc, scaling, iters)
+                model = cosmo_b200.Model()
+                model.set(P, q, A, b, sets, cosmo_b200.Settings(scaling=scaling, max_iter=iters, eps_abs=1e-14, eps_rel=1e-14,
+                                                                accelerator=name))
+                res = model.optimize()
+                w = model.engine.w()
+                assert [res.iter, res.safeguarding_iter] == gold[key + "/iter_sg"].tolist(), key
+                assert np.linalg.norm(w - gold[key + "/w"]) / np.linalg.norm(gold[key + "/w"]) < 1e-8, key
+    res, _ = _solve_mine(G.g1_qp_nonneg, scaling=0)
+    assert res.iter == int(gold["g1_qp_nonneg/iter_obj"][0]) and abs(res.obj_val - gold["g1_qp_nonneg/iter_obj"][1]) < 1e-9
+    assert np.allclose(res.x, gold["g1_qp_nonneg/x"], atol=1e-7) and np.allclose(res.s, gold["g1_qp_nonneg/s"], atol=1e-7)
+    assert np.allclose(res.y, gold["g1_qp_nonneg/y"], atol=1e-6)
+    res, _ = _solve_mine(G.g13_lovasz_petersen, eps_abs=1e-6, eps_rel=1e-6)
+    assert abs(res.iter - int(gold["g13_lovasz_petersen/iter_obj"][0])) <= 25
+    assert abs(res.obj_val - gold["g13_lovasz_petersen/iter_obj"][1]) < 1e-6
+    res, _ = _solve_mine(G.g15_exp_feasible, eps_abs=1e-4, eps_rel=1e-4)
+    assert abs(res.iter - int(gold["g15_exp_feasible/iter_obj"][0])) <= 25
+    assert abs(res.obj_val - gold["g15_exp_feasible/iter_obj"][1]) < 1e-4 and np.allclose(res.x, gold["g15_exp_feasible/x"], atol=1e-3)
+
+
 # ---------------------------------------------------------------------------
 # solve-level parity on the reference's literal problems
 # ---------------------------------------------------------------------------
