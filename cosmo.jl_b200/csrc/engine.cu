@@ -1427,7 +1427,10 @@ bool Engine<T>::dual_infeasible() {
 template <typename T>
 void Engine<T>::aa_prepare() {   // _make_accelerator!, setup.jl:10-14 (built once per dimension / memory)
   const long long dim = (long long)n_ + m_;
-  int mem = (int)std::min<long long>(std::max(st_.accelerator_mem, 3), std::min<long long>(dim, 32));
+  if (st_.accelerator_mem <= 2) throw EngineError{COSMO_B200_ERR_INVALID, "accelerator: Memory has to be bigger than two."};
+  if (st_.accelerator_mem > 32 && dim > 32)
+    throw EngineError{COSMO_B200_ERR_UNSUPPORTED, "accelerator_mem > 32 is not supported by the device accelerator"};
+  int mem = (int)std::min<long long>(st_.accelerator_mem, std::max<long long>(dim, 1));   // mem = min(mem, dim)
   if (aa_mem_ != mem) {
     aaG_.alloc((size_t)dim * mem, false); aaQ_.alloc((size_t)dim * mem, false);
     aaR_.alloc((size_t)mem * mem); aa_eta_.alloc(32);

@@ -252,6 +252,11 @@ class Settings:
             raise _eng.EngineError(_eng.ERR_UNSUPPORTED,
                                    "accelerator %r: the engine implements EmptyAccelerator and AndersonAccelerator"
                                    "{T, Type2{QRDecomp}, RestartedMemory, NoRegularizer}" % self.accelerator)
+        if self.accelerator == "AndersonAccelerator":
+            if self.accelerator_mem <= 2:
+                raise ValueError("Memory has to be bigger than two.")      # AndersonAccelerator ctor (DomainError)
+            if self.accelerator_mem > 32:
+                raise _eng.EngineError(_eng.ERR_UNSUPPORTED, "accelerator_mem > 32 is not supported by the device accelerator")
         s = _eng.default_settings()
         for name in ("rho", "sigma", "alpha", "eps_abs", "eps_rel", "eps_prim_inf", "eps_dual_inf", "max_iter",
                      "check_termination", "check_infeasibility", "scaling", "adaptive_rho_interval",

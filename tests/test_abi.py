@@ -91,3 +91,20 @@ def test_ruiz_matches_oracle():
     assert np.allclose(P1.toarray(), P2.toarray(), rtol=1e-12, atol=1e-14)
     assert np.allclose(q1, q2, rtol=1e-12) and np.allclose(b1, b2, rtol=1e-12)
     assert np.allclose(s1[1].l, s2[1].l, rtol=1e-12) and np.allclose(s1[1].u, s2[1].u, rtol=1e-12)
+
+
+def test_accelerator_settings_mapping_and_validation():
+    import cosmo_b200
+    from cosmo_b200 import engine as E
+    st = cosmo_b200.Settings().to_struct()
+    assert (st.accelerator, st.accelerator_mem, st.accelerator_min_mem, st.safeguard, st.safeguard_tol) == (E.ACC_EMPTY, 15, 3, 1, 2.0)
+    st = cosmo_b200.Settings(accelerator="AndersonAccelerator", accelerator_mem=7, safeguard=False, safeguard_tol=3.0).to_struct()
+    assert (st.accelerator, st.accelerator_mem, st.safeguard, st.safeguard_tol) == (E.ACC_ANDERSON, 7, 0, 3.0)
+    with pytest.raises(ValueError):        # AndersonAccelerator(dim; mem <= 2) throws a DomainError in the package
+        cosmo_b200.Settings(accelerator="AndersonAccelerator", accelerator_mem=2).to_struct()
+    with pytest.raises(E.EngineError):
+        cosmo_b200.Settings(accelerator="AndersonAccelerator", accelerator_mem=64).to_struct()
+    with pytest.raises(E.EngineError):     # Type-I / rolling-memory variants are not implemented
+        cosmo_b200.Settings(accelerator="AndersonAccelerator{Type1}").to_struct()
+    d = E.default_settings()
+    assert (d.accelerator, d.accelerator_mem, d.accelerator_min_mem, d.safeguard, d.safeguard_tol) == (0, 15, 3, 1, 2.0)
