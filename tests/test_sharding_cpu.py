@@ -96,6 +96,58 @@ def _worker(rank, world, port, out):
         mine = w[sh.rows].copy()
         O.project(mine, cosmo_b200.problems.to_oracle_cones(sh.sets))
         ok = ok and np.allclose(mine, ref[sh.rows], rtol=0, atol=1e-14)
+        # Anderson acceleration over sharded rows (aa.cuh / Engine::aa_update, aa_accelerate): every rank keeps
+        # [w_x (replicated); w_s restricted to its rows]; inner products run over [lo, dim) with lo = 0 on rank 0
+        # and lo = n elsewhere, followed by an allreduce -> the same R, eta and candidate as the unsharded method
+        m_full = A.shape[0]
+        dim_full = n + m_full
+        idx = np.concatenate([np.arange(n), n + sh.rows])          # this rank's slice of the operator variable
+        lo = 0 if rank == 0 else n
+
+        def gdot(a, b_):
+            t_ = torch.tensor([float(a[lo:] @ b_[lo:])], dtype=torch.float64)
+            dist.all_reduce(t_, op=dist.ReduceOp.SUM)
+            return t_.item()
+
+        mem = 5
+        aa = O.AndersonAccelerator(dim_full, mem)                   # the unsharded restatement, on full vectors
+        Gm, Qm, Rm = np.zeros((len(idx), mem)), np.zeros((len(idx), mem)), np.zeros((mem, mem))
+        g_last = f_last = None
+        it = 0
+        Mop = rng.standard_normal((dim_full, dim_full)) * (0.5 / np.sqrt(dim_full))
+        cst = rng.standard_normal(dim_full)
+        xk = rng.standard_normal(dim_full)
+        for k in range(2 * mem + 3):                                # crosses one memory restart
+            gk = Mop @ xk + cst
+            aa.update(gk, xk, k + 2)
+            g_acc = gk.copy()
+            aa.accelerate(g_acc, xk, k + 2)
+            # ---- sharded emulation of the same step ----
+            gl, xl = gk[idx], xk[idx]
+            fl = xl - gl
+            cand = gl.copy()
+            if g_last is not None:
+                j = it % mem
+                if j == 0 and it != 0:
+                    it = 0
+                Gm[:, j] = gl - g_last
+                qv = fl - f_last
+                for i in range(j):
+                    Rm[i, j] = gdot(Qm[:, i], qv)
+                    qv = qv - Rm[i, j] * Qm[:, i]
+                Rm[j, j] = np.sqrt(gdot(qv, qv))
+                Qm[:, j] = qv / Rm[j, j]
+                it += 1
+                l = min(it, mem)
+                if l >= 3:
+                    eta = np.array([gdot(Qm[:, c_], fl) for c_ in range(l)])
+                    eta = np.linalg.solve(np.triu(Rm[:l, :l]), eta)
+                    if np.linalg.norm(eta) <= 1e4:
+                        cand = gl - Gm[:, :l] @ eta
+            g_last, f_last = gl.copy(), fl.copy()
+            ok = ok and np.allclose(cand, g_acc[idx], rtol=1e-9, atol=1e-9)
+            xk = g_acc                                               # continue from the accelerated point
+        ok = ok and aa.num_accelerated_steps >= mem
         # the 128-byte ncclUniqueId travels as a python object over the plumbing backend
         obj = [bytes(range(128)) if rank == 0 else None]
         dist.broadcast_object_list(obj, src=0)
