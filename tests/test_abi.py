@@ -108,3 +108,36 @@ def test_accelerator_settings_mapping_and_validation():
         cosmo_b200.Settings(accelerator="AndersonAccelerator{Type1}").to_struct()
     d = E.default_settings()
     assert (d.accelerator, d.accelerator_mem, d.accelerator_min_mem, d.safeguard, d.safeguard_tol) == (0, 15, 3, 1, 2.0)
+
+
+def test_c_header_layout_matches_ctypes_mirror(tmp_path):
+    # compile a plain C program against include/cosmo_b200.h, link it with the shared library, and compare the
+    # layout the C compiler sees with the ctypes structures the Python binding marshals
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    lib_path = E.load_library()._name
+    exe = str(tmp_path / "abi_probe")
+    subprocess.run([cc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "abi_probe.c"),
+                    lib_path, "-Wl,-rpath," + os.path.dirname(lib_path), "-o", exe], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    vals = {}
+    for line in out.splitlines():
+        k, _, v = line.partition(" ")
+        vals[k] = v
+    mirror = {"cosmo_b200_csc": E.CscStruct, "cosmo_b200_set": E.SetStruct, "cosmo_b200_problem": E.ProblemStruct,
+              "cosmo_b200_settings": E.SettingsStruct, "cosmo_b200_result": E.ResultStruct}
+    checked = 0
+    for k, v in vals.items():
+        if k.startswith("sizeof."):
+            assert ctypes.sizeof(mirror[k[len("sizeof."):]]) == int(v), k
+            checked += 1
+        elif "." in k and k.split(".")[0] in mirror:
+            st, field = k.split(".")
+            assert getattr(mirror[st], field).offset == int(v), k
+            checked += 1
+    assert checked >= 35
+    assert vals["abi"] == "2" and vals["defaults"] == "0.1 1e-06 1.6 5000 0 15 2"
+    assert int(vals["create_null"]) == E.ERR_INVALID and "null" in vals["last_error"]
