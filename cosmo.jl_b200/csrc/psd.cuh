@@ -694,6 +694,10 @@ __global__ void psd_large_lammax_kernel(int N, const T* __restrict__ A, T* __res
   }
 }
 
+}  // namespace cosmo
+#include "psd_sign.cuh"
+namespace cosmo {
+
 // ---------------------------------------------------------------------------
 // Host-side batch object
 // ---------------------------------------------------------------------------
@@ -718,6 +722,9 @@ struct PsdBatch {
   long long warm_count = 0;
   bool warm_enabled = true;
   int last_sweeps = 0;
+  PsdSign<T> sign_;      // experimental GEMM-only projection (psd_sign.cuh), COSMO_B200_PSD_SIGN=1
+  bool sign_enabled = PsdSign<T>::enabled();
+  long long sign_projections = 0, sign_fallbacks = 0;
   T* R_d = nullptr;      // npairs * 64 * 64 pivot rotations
   int* act_d = nullptr;  // per pair: pivot needed work this round
   std::vector<T> lam_host;
@@ -843,6 +850,14 @@ struct PsdBatch {
       ++launches;
     }
     for (const auto& d : large_h) {
+      if (sign_enabled) {   // experimental: Pi_+(X) = (X + sign(X) X) / 2 by Newton-Schulz products, no eigenvectors
+        const int N = d.N;
+        const int g = (int)std::min<long long>(((long long)N * N + kBlock - 1) / kBlock, kMaxGrid);
+        psd_large_load_kernel<T><<<g, kBlock, 0, st>>>(d, ws, A_d, V_d, fro_d);
+        ++launches;
+        if (sign_.project(d, A_d, fro_d, g, V_d, s, st, launches)) { ++sign_projections; continue; }
+        ++sign_fallbacks;
+      }
       large_eig(d, ws, st, max_sweeps, launches, /*allow_warm=*/true);
       const int N = d.N;
       const int g = (int)std::min<long long>(((long long)N * N + kBlock - 1) / kBlock, kMaxGrid);
