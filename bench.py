@@ -114,7 +114,8 @@ def oracle_iterations(P, q, A, b, sets, iters, warm):
     """Time `iters` ADMM iterations of the oracle port after `warm` untimed ones (same settings)."""
     import cosmo_b200
     from oracle import cosmo_oracle as O
-    cones = cosmo_b200.problems.to_oracle_cones(sets)
+    from oracle.bridge import to_oracle_cones
+    cones = to_oracle_cones(sets)
     marks = {}
 
     def cb(it, ws):

@@ -114,36 +114,6 @@ def closest_correlation_sdp(N=2000, seed=12345):
     return P, q, A, b, sets
 
 
-def to_oracle_cones(sets):
-    """Translate cosmo_b200 set objects into the oracle's cone classes (tests / bench only)."""
-    from oracle import cosmo_oracle as O
-    out = []
-    for S in sets:
-        if isinstance(S, M.ZeroSet):
-            out.append(O.ZeroSet(S.dim))
-        elif isinstance(S, M.Nonnegatives):
-            out.append(O.Nonnegatives(S.dim))
-        elif isinstance(S, M.Box):
-            out.append(O.Box(S.l, S.u))
-        elif isinstance(S, M.SecondOrderCone):
-            out.append(O.SecondOrderCone(S.dim))
-        elif isinstance(S, M.PsdCone):
-            out.append(O.PsdCone(S.dim))
-        elif isinstance(S, M.PsdConeTriangle):
-            out.append(O.PsdConeTriangle(S.dim))
-        elif isinstance(S, M.DualExponentialCone):
-            out.append(O.DualExponentialCone(3, S.MAX_ITER, S.TOL))
-        elif isinstance(S, M.ExponentialCone):
-            out.append(O.ExponentialCone(3, S.MAX_ITER, S.TOL))
-        elif isinstance(S, M.DualPowerCone):
-            out.append(O.DualPowerCone(S.alpha, S.MAX_ITER, S.TOL))
-        elif isinstance(S, M.PowerCone):
-            out.append(O.PowerCone(S.alpha, S.MAX_ITER, S.TOL))
-        else:
-            raise TypeError(S)
-    return out
-
-
 def banded_random_graph(nv=10_000, mean_degree=3.0, bandwidth=20, seed=1):
     """BASELINE config C5 graph: random sparse graph with mean degree ~3 whose edges join vertices at
     index distance <= `bandwidth` (bounded treewidth => the chordal extension has small cliques, the

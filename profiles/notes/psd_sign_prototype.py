@@ -13,10 +13,11 @@ import numpy as np, time, sys
 sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))))
 import cosmo_b200
 from oracle import cosmo_oracle as O
+from oracle.bridge import to_oracle_cones
 # closest correlation problem: take w_s iterates (the matrices that get projected)
 N=300
 P,q,A,b,sets=cosmo_b200.problems.closest_correlation_sdp(N=N,seed=3)
-cones=cosmo_b200.problems.to_oracle_cones(sets)
+cones=to_oracle_cones(sets)
 mats=[]
 def cb(it,ws):
     if it in (1,2,10,30,60):

@@ -21,6 +21,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 import cosmo_b200  # noqa: E402  (problem generators only; no GPU needed)
 from oracle import cosmo_oracle as O  # noqa: E402
+from oracle.bridge import to_oracle_cones
 from tests import golden_problems as G  # noqa: E402
 
 KNOWN = [
@@ -45,7 +46,7 @@ def _run(P, q, A, b, cones, **kw):
 def iterates():
     out = {}
     P, q, A, b, sets = cosmo_b200.problems.random_sparse_qp(40, 70, 0.15, seed=7)
-    cones = cosmo_b200.problems.to_oracle_cones(sets)
+    cones = to_oracle_cones(sets)
     for acc in ("empty", "anderson"):
         for scaling in (0, 10):
             for iters in (5, 14, 33):

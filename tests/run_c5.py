@@ -53,7 +53,8 @@ def main():
             "kernel_launches": int(out.kernel_launches)}
     if rank == 0 and world == 1 and "--cpu" in sys.argv:
         from oracle import cosmo_oracle as O
-        cones = cosmo_b200.problems.to_oracle_cones(sets2)
+        from oracle.bridge import to_oracle_cones
+        cones = to_oracle_cones(sets2)
         k = min(iters, 20)
         t0 = time.time()
         O.solve(P2, q2, A2, b2, cones, O.Settings(kkt_solver="cg", scaling=0, adaptive_rho=False, max_iter=k, eps_abs=0.0, eps_rel=0.0))

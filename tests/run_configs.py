@@ -10,6 +10,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import cosmo_b200
 from oracle import cosmo_oracle as O
+from oracle.bridge import to_oracle_cones
 
 
 def timed(name, P, q, A, b, sets, iters, cpu_iters, **kw):
@@ -29,7 +30,7 @@ def timed(name, P, q, A, b, sets, iters, cpu_iters, **kw):
             "kkt_inner_per_iter": res.kkt_inner_iterations / max(res.iter, 1), "first_solve_incl_setup_s": setup_plus,
             "obj": res.obj_val, "r_prim": res.info.r_prim, "r_dual": res.info.r_dual}
     if cpu_iters:
-        cones = cosmo_b200.problems.to_oracle_cones(sets)
+        cones = to_oracle_cones(sets)
         t0 = time.time()
         ref = O.solve(P, q, A, b, cones, O.Settings(kkt_solver="cg", max_iter=cpu_iters, **st))
         cpu = time.time() - t0

@@ -4,6 +4,7 @@ import scipy.sparse as sp
 import cosmo_b200
 from cosmo_b200 import engine as E
 from oracle import cosmo_oracle as O
+from oracle.bridge import to_oracle_cones
 for N in [int(a) for a in sys.argv[1:]] or [200, 500, 1000, 2000]:
     rng = np.random.default_rng(N)
     d = N * (N + 1) // 2
@@ -11,13 +12,13 @@ for N in [int(a) for a in sys.argv[1:]] or [200, 500, 1000, 2000]:
     eng = E.Engine(sp.identity(1, format="csc"), np.zeros(1), sp.csc_matrix((d, 1)), np.zeros(d),
                    [(S.code, S.dim, None, None) for S in sets], cosmo_b200.Settings(scaling=0).to_struct())
     ws = rng.standard_normal(d)
-    t0 = time.time(); ref = ws.copy(); O.project(ref, cosmo_b200.problems.to_oracle_cones(sets)); tcpu = time.time() - t0
+    t0 = time.time(); ref = ws.copy(); O.project(ref, to_oracle_cones(sets)); tcpu = time.time() - t0
     eng.project(ws)
     t0 = time.time(); got = eng.project(ws); tgpu = time.time() - t0
     # a nearby matrix (ADMM-like small change)
     ws2 = got + 1e-3 * rng.standard_normal(d)
     t0 = time.time(); got2 = eng.project(ws2); tgpu2 = time.time() - t0
-    ref2 = ws2.copy(); O.project(ref2, cosmo_b200.problems.to_oracle_cones(sets))
+    ref2 = ws2.copy(); O.project(ref2, to_oracle_cones(sets))
     err2 = np.linalg.norm(got2 - ref2) / np.linalg.norm(ws2)
     ws3 = got2 + 1e-5 * rng.standard_normal(d)
     t0 = time.time(); got3 = eng.project(ws3); tgpu3 = time.time() - t0

@@ -13,6 +13,7 @@ import torch.distributed as dist
 import cosmo_b200
 from cosmo_b200 import sharding
 from oracle import cosmo_oracle as O
+from oracle.bridge import to_oracle_cones
 
 
 def gather_rows(local, rows, m, world):
@@ -58,7 +59,7 @@ def main():
             okw = dict(kw)
             if okw.pop("accelerator", None) == "AndersonAccelerator":
                 okw["accelerator"] = "anderson"
-            ref = O.solve(P, q, A, b, pr.to_oracle_cones(sets), O.Settings(kkt_solver="cg", **okw))
+            ref = O.solve(P, q, A, b, to_oracle_cones(sets), O.Settings(kkt_solver="cg", **okw))
             # accelerated runs with inexact (CG) KKT solves amplify the inner solver's rounding: both runs stop
             # at the same iteration but agree to the solver tolerance only (measured 8e-6 on x for the SOCP)
             tol = 2e-4 if "accelerator" in kw else 1e-5

@@ -64,6 +64,7 @@ def test_host_mirror_assemble_matches_reference_ordering():
     # moi_wrapper.jl:266-271 / interface.jl:411-475: merge Zero & Nonneg, stable sort by type
     from tests import golden_problems as G
     from oracle import cosmo_oracle as O
+    from oracle.bridge import to_oracle_cones
     P, q, cons = G.g3_hs21()
     Pm, qm, A, b, cones = O.assemble(P, q, cons)
     mine = [cosmo_b200.Constraint(c.A, c.b, _conv(c.convex_set)) for c in cons]
@@ -75,6 +76,7 @@ def test_host_mirror_assemble_matches_reference_ordering():
 
 def _conv(c):
     from oracle import cosmo_oracle as O
+    from oracle.bridge import to_oracle_cones
     if isinstance(c, O.Box):
         return cosmo_b200.Box(c.l, c.u)
     return getattr(cosmo_b200, type(c).__name__)(c.dim)
@@ -82,10 +84,11 @@ def _conv(c):
 
 def test_ruiz_matches_oracle():
     from oracle import cosmo_oracle as O
+    from oracle.bridge import to_oracle_cones
     P, q, A, b, sets = cosmo_b200.problems.random_sparse_qp(60, 90, 0.2, seed=3)
     st = cosmo_b200.Settings()
     P1, q1, A1, b1, s1, D, Em, c = cosmo_b200.ruiz_equilibrate(P, q, A, b, sets, st)
-    P2, q2, A2, b2, s2, sm = O.scale_ruiz(P, q, A, b, cosmo_b200.problems.to_oracle_cones(sets), O.Settings())
+    P2, q2, A2, b2, s2, sm = O.scale_ruiz(P, q, A, b, to_oracle_cones(sets), O.Settings())
     assert np.allclose(D, sm.D, rtol=1e-13) and np.allclose(Em, sm.E, rtol=1e-13) and abs(c - sm.c) < 1e-13 * abs(c)
     assert np.allclose(A1.toarray(), A2.toarray(), rtol=1e-12, atol=1e-14)
     assert np.allclose(P1.toarray(), P2.toarray(), rtol=1e-12, atol=1e-14)

@@ -8,10 +8,11 @@ import scipy.sparse as sp
 import cosmo_b200
 from cosmo_b200 import chordal
 from oracle import cosmo_oracle as O
+from oracle.bridge import to_oracle_cones
 
 
 def _solve_oracle(P, q, A, b, sets, **kw):
-    return O.solve(P, q, A, b, cosmo_b200.problems.to_oracle_cones(sets), O.Settings(**kw))
+    return O.solve(P, q, A, b, to_oracle_cones(sets), O.Settings(**kw))
 
 
 def test_svec_index_roundtrip():

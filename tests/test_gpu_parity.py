@@ -10,6 +10,7 @@ import scipy.sparse as sp
 import cosmo_b200
 from cosmo_b200 import engine as E
 from oracle import cosmo_oracle as O
+from oracle.bridge import to_oracle_cones
 from tests import golden_problems as G
 
 pytestmark = pytest.mark.gpu
@@ -134,7 +135,7 @@ def test_project_composite_matches_oracle():
     n = 4
     A = sp.random(m, n, density=0.3, random_state=rng, format="csc")
     eng = _engine(sp.identity(n, format="csc"), np.zeros(n), A, np.zeros(m), sets)
-    cones = cosmo_b200.problems.to_oracle_cones(sets)
+    cones = to_oracle_cones(sets)
     for trial in range(3):
         ws = rng.standard_normal(m) * (10.0 ** trial)
         ws[3] = np.nan if trial == 2 else ws[3]          # NaN propagates through max(x, 0) like Julia
@@ -160,7 +161,7 @@ def test_soc_branches():
     ws = np.array([5.0, 1, 1, 1, -5.0, 1, 1, 1, 0.5, 1, 2, 2])
     eng = _engine(sp.identity(1, format="csc"), np.zeros(1), sp.csc_matrix((12, 1)), np.zeros(12), sets)
     ref = ws.copy()
-    O.project(ref, cosmo_b200.problems.to_oracle_cones(sets))
+    O.project(ref, to_oracle_cones(sets))
     got = eng.project(ws)
     assert np.array_equal(got[:8], ref[:8])
     assert np.allclose(got[8:], ref[8:], rtol=1e-15)
@@ -191,7 +192,7 @@ def test_project_exp_pow_cones():
     ws = np.concatenate([np.asarray(v, dtype=float) for v in pts])
     m = ws.size
     eng = _engine(sp.identity(1, format="csc"), np.zeros(1), sp.csc_matrix((m, 1)), np.zeros(m), sets)
-    cones = cosmo_b200.problems.to_oracle_cones(sets)
+    cones = to_oracle_cones(sets)
     ref = ws.copy()
     O.project(ref, cones)
     got = eng.project(ws)
@@ -215,7 +216,7 @@ def test_project_psd_large_path(N):
     eng = _engine(sp.identity(1, format="csc"), np.zeros(1), sp.csc_matrix((d, 1)), np.zeros(d), sets)
     ws = rng.standard_normal(d)
     ref = ws.copy()
-    O.project(ref, cosmo_b200.problems.to_oracle_cones(sets))
+    O.project(ref, to_oracle_cones(sets))
     got = eng.project(ws)
     assert np.linalg.norm(got - ref) / np.linalg.norm(ws) < 1e-12
 
@@ -243,7 +244,7 @@ def test_project_psd_sign_function_path(kind, monkeypatch):
     m = ws.size
     eng = _engine(sp.identity(1, format="csc"), np.zeros(1), sp.csc_matrix((m, 1)), np.zeros(m), sets)
     ref = ws.copy()
-    O.project(ref, cosmo_b200.problems.to_oracle_cones(sets))
+    O.project(ref, to_oracle_cones(sets))
     got = eng.project(ws)
     nrm = np.linalg.norm(ws) + 1e-300
     assert np.linalg.norm(got - ref) / nrm < 1e-12
@@ -258,7 +259,7 @@ def test_project_psd_batch_of_cliques():
     eng = _engine(sp.identity(1, format="csc"), np.zeros(1), sp.csc_matrix((m, 1)), np.zeros(m), sets)
     ws = rng.standard_normal(m)
     ref = ws.copy()
-    O.project(ref, cosmo_b200.problems.to_oracle_cones(sets))
+    O.project(ref, to_oracle_cones(sets))
     got = eng.project(ws)
     assert np.linalg.norm(got - ref) / np.linalg.norm(ws) < 1e-12
     # idempotence: projecting a projected point changes nothing (size-independent property)
@@ -318,7 +319,7 @@ def test_minres_kkt_solve_matches_oracle(name, kind):
 @pytest.mark.parametrize("name,kind", [("MINRESIndirectKKTSolver", "minres"), ("IndirectReducedKKTSolver:MINRES", "minres_reduced")])
 def test_minres_solve_matches_oracle(name, kind):
     P, q, A, b, sets = _small_qp(seed=12)
-    cones = cosmo_b200.problems.to_oracle_cones(sets)
+    cones = to_oracle_cones(sets)
     ref = O.solve(P, q, A, b, cones, O.Settings(kkt_solver=kind, max_iter=300))
     model = cosmo_b200.Model()
     model.set(P, q, A, b, sets, cosmo_b200.Settings(kkt_solver=name, max_iter=300))
@@ -339,7 +340,7 @@ def test_residuals_match_oracle():
     eng = E.Engine(Ps, qs, As, bs, _tuples(ss), st.to_struct(), D=D, E=Em, c=c)
     rng = np.random.default_rng(8)
     x, s, mu = rng.standard_normal(n), rng.standard_normal(m), rng.standard_normal(m)
-    ws = O.Workspace(P, q, A, b, cosmo_b200.problems.to_oracle_cones(sets), O.Settings())
+    ws = O.Workspace(P, q, A, b, to_oracle_cones(sets), O.Settings())
     ws.setup()
     ws.xv, ws.s, ws.mu = x, s, mu
     for ign in (False, True):
@@ -356,7 +357,7 @@ def test_residuals_match_oracle():
 @pytest.mark.parametrize("scaling", [0, 10])
 def test_iterate_parity_first_iterations(scaling):
     P, q, A, b, sets = _small_qp(seed=7)
-    cones = cosmo_b200.problems.to_oracle_cones(sets)
+    cones = to_oracle_cones(sets)
     for iters in (1, 5, 40, 90):   # 40/80: rho adaptation + infeasibility checks are crossed
         ost = O.Settings(kkt_solver="cg", scaling=scaling, max_iter=iters, eps_abs=1e-14, eps_rel=1e-14)
         ref = O.solve(P, q, A, b, cones, ost)
@@ -381,7 +382,7 @@ def test_accelerated_iterates_match_oracle(scaling):
     # the QR least squares, the candidate, the safeguard decisions (two candidates are declined at iterations
     # 31-32 of this problem) and the memory restarts.  Measured agreement of w: 1e-13; asserted 1e-9.
     P, q, A, b, sets = _small_qp(seed=7)
-    cones = cosmo_b200.problems.to_oracle_cones(sets)
+    cones = to_oracle_cones(sets)
     for iters in (2, 5, 14, 33, 45):  # first update, first candidate, memory almost full, declined candidates, restarts
         ost = O.Settings(kkt_solver="cg", scaling=scaling, max_iter=iters, eps_abs=1e-14, eps_rel=1e-14, accelerator="anderson")
         ref = O.solve(P, q, A, b, cones, ost)
@@ -537,7 +538,7 @@ def test_g6_chordal_sdp_through_the_clique_batch():
     model = cosmo_b200.Model()
     model.set(P2, q2, A2, b2, sets2, cosmo_b200.Settings())
     dec = model.optimize()
-    ref = O.solve(P2, q2, A2, b2, cosmo_b200.problems.to_oracle_cones(sets2), O.Settings(kkt_solver="cg"))
+    ref = O.solve(P2, q2, A2, b2, to_oracle_cones(sets2), O.Settings(kkt_solver="cg"))
     full = O.solve(Pm, qm, A0, b0, cones0, O.Settings(eps_abs=1e-7, eps_rel=1e-7))      # undecomposed, direct KKT
     assert dec.status == "Solved" == ref.status == full.status
     assert abs(dec.iter - ref.iter) <= 50 and abs(dec.obj_val - ref.obj_val) < 1e-4
@@ -629,7 +630,7 @@ def test_g14_model_updates_and_warm_start():
 # solve-level parity on the BASELINE problem families at oracle-sized instances
 # ---------------------------------------------------------------------------
 def _parity(P, q, A, b, sets, tol_x=1e-5, **kw):
-    cones = cosmo_b200.problems.to_oracle_cones(sets)
+    cones = to_oracle_cones(sets)
     ref = O.solve(P, q, A, b, cones, O.Settings(kkt_solver="cg", **kw))
     model = cosmo_b200.Model()
     model.set(P, q, A, b, sets, cosmo_b200.Settings(**kw))
@@ -691,7 +692,7 @@ def test_c5_maxcut_chordal_clique_batch():
     assert len(sets2) > 10
     res, ref = _parity(P2, q2, A2, b2, sets2, tol_x=1e-4, eps_abs=1e-6, eps_rel=1e-6)
     assert res.status == "Solved" and abs(res.iter - ref.iter) <= 25
-    full = O.solve(P, q, A, b, cosmo_b200.problems.to_oracle_cones(sets), O.Settings(kkt_solver="cg", eps_abs=1e-6, eps_rel=1e-6))
+    full = O.solve(P, q, A, b, to_oracle_cones(sets), O.Settings(kkt_solver="cg", eps_abs=1e-6, eps_rel=1e-6))
     assert abs(full.obj_val - res.obj_val) <= 1e-3 * max(1.0, abs(full.obj_val))
     x, s, mu = chordal.reverse(info, res.x, res.s, -res.y)
     assert np.max(np.abs(A @ x + s - b)) < 1e-3

@@ -66,6 +66,7 @@ def _worker(rank, world, port, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from oracle import cosmo_oracle as O
+        from oracle.bridge import to_oracle_cones
         P, q, A, b, sets = _mixed_problem(seed=5)
         sh = sharding.make_shard(P, q, A, b, sets, rank, world)
         n = A.shape[1]
@@ -92,9 +93,9 @@ def _worker(rank, world, port, out):
         # projection is rank-local: cones are whole
         w = rng.standard_normal(A.shape[0])
         ref = w.copy()
-        O.project(ref, cosmo_b200.problems.to_oracle_cones(sets))
+        O.project(ref, to_oracle_cones(sets))
         mine = w[sh.rows].copy()
-        O.project(mine, cosmo_b200.problems.to_oracle_cones(sh.sets))
+        O.project(mine, to_oracle_cones(sh.sets))
         ok = ok and np.allclose(mine, ref[sh.rows], rtol=0, atol=1e-14)
         # Anderson acceleration over sharded rows (aa.cuh / Engine::aa_update, aa_accelerate): every rank keeps
         # [w_x (replicated); w_s restricted to its rows]; inner products run over [lo, dim) with lo = 0 on rank 0
