@@ -185,7 +185,9 @@ typedef struct {
 
 /* ---- lifecycle ---------------------------------------------------------- */
 int cosmo_b200_abi_version(void);
-/* COSMO.Settings{T}() defaults (settings.jl:101-139) with kkt_solver = CG */
+/* COSMO.Settings{T}() defaults (settings.jl:101-139) with kkt_solver = CG and accelerator = COSMO_B200_ACC_EMPTY
+   (the reference default is the Anderson accelerator, settings.jl:136-138: set accelerator = COSMO_B200_ACC_ANDERSON;
+   the Julia shim of INTEGRATION.md copies it from ws.accelerator) */
 int cosmo_b200_default_settings(cosmo_b200_settings* out);
 /* _make_kkt_solver! + Variables{T}(m,n,C) + classify_constraints! + set_rho_vec!
    (setup.jl:1-7,75-85; types.jl:263-279; parameters.jl:3-13): uploads the problem. */
