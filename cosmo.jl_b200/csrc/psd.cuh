@@ -32,8 +32,11 @@ namespace cosmo {
 
 struct PsdConeDesc {
   int off;       // first row of the cone in s
-  int N;         // matrix side
-  int triangle;  // 1: svec upper triangle (PsdConeTriangle), 0: column-major square (PsdCone)
+  int N;         // side of the real symmetric matrix that is diagonalised
+  int triangle;  // 1: svec upper triangle (PsdConeTriangle), 0: column-major square (PsdCone),
+                 // 2: PsdConeTriangle{T, Complex{T}} (convexset.jl:344-360, 444-490): the Hermitian Nc x Nc matrix
+                 //    X = A + iB is handled through its real embedding [[A, -B], [B, A]] of side N = 2 Nc, whose
+                 //    projection is the embedding of the projection of X (small path only, Nc <= 48)
 };
 
 constexpr int kPsdSmallMax = 96;   // 2 * (N+1)^2 * 8 B <= 227 KB shared memory
@@ -98,10 +101,26 @@ __global__ void __launch_bounds__(kBlock) psd_small_kernel(const PsdConeDesc* __
   for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
     const int i = e % N, j = e / N;
     T v;
-    if (d.triangle) {
+    if (d.triangle == 1) {
       const int a = i < j ? i : j, b = i < j ? j : i;
       v = x[svec_pos(a, b)];
       if (a != b) v *= inv_sqrt2;
+    } else if (d.triangle == 2) {
+      // real embedding of the Hermitian matrix: block (bi, bj) of [[A, -B], [B, A]], entry (I, J)
+      const int Nc = N >> 1;
+      const int I = i % Nc, bi = i / Nc, J = j % Nc, bj = j / Nc;
+      const int a = I < J ? I : J, b = I < J ? J : I;
+      if (bi == bj) {                                   // A = Re X (symmetric)
+        v = x[svec_pos(a, b)];
+        if (a != b) v *= inv_sqrt2;
+      } else if (I == J) {
+        v = T(0);                                       // Im X has a zero diagonal
+      } else {
+        // Im X[a, b], a < b, sits behind the real triangle, strictly upper entries column by column
+        const T im_ab = x[(long long)Nc * (Nc + 1) / 2 + (long long)b * (b - 1) / 2 + a] * inv_sqrt2;
+        const T b_IJ = (I < J) ? im_ab : -im_ab;        // B = Im X is antisymmetric
+        v = (bi == 1) ? b_IJ : -b_IJ;                   // lower-left block B, upper-right block -B
+      }
     } else {
       v = (x[(long long)j * N + i] + x[(long long)i * N + j]) / T(2);   // symmetrize_upper!, algebra.jl:201-208
     }
@@ -201,7 +220,36 @@ __global__ void __launch_bounds__(kBlock) psd_small_kernel(const PsdConeDesc* __
     V[i + k * ld] *= (lam > T(0)) ? sqrt(lam) : T(0);
   }
   __syncthreads();
-  if (d.triangle) {
+  if (d.triangle == 2) {
+    // X+ = A+ + i B+ from the projected embedding P = V V':  A+ = (P11 + P22) / 2,  B+ = (P21 - P12) / 2
+    const int Nc = N >> 1;
+    const int tri = Nc * (Nc + 1) / 2;
+    for (int e = threadIdx.x; e < Nc * Nc; e += blockDim.x) {
+      const bool imag = e >= tri;
+      const int ee = imag ? e - tri : e;
+      int i, j;
+      if (!imag) {          // (i, j), i <= j, of the triangle
+        j = (int)((sqrt(8.0 * (double)ee + 1.0) - 1.0) * 0.5);
+        while ((long long)(j + 1) * (j + 2) / 2 <= ee) ++j;
+        while ((long long)j * (j + 1) / 2 > ee) --j;
+        i = ee - j * (j + 1) / 2;
+      } else {              // (i, j), i < j, of the strict triangle: ee = j (j - 1) / 2 + i
+        j = (int)((sqrt(8.0 * (double)ee + 1.0) + 1.0) * 0.5);
+        while ((long long)j * (j + 1) / 2 <= ee) ++j;
+        while ((long long)j * (j - 1) / 2 > ee) --j;
+        i = ee - j * (j - 1) / 2;
+      }
+      T acc = 0;
+      if (!imag) {
+        for (int k = 0; k < N; ++k) acc += V[i + k * ld] * V[j + k * ld] + V[Nc + i + k * ld] * V[Nc + j + k * ld];
+        acc *= T(0.5);
+        s[d.off + e] = (i == j) ? acc : sqrt2 * acc;
+      } else {
+        for (int k = 0; k < N; ++k) acc += V[Nc + i + k * ld] * V[j + k * ld] - V[i + k * ld] * V[Nc + j + k * ld];
+        s[d.off + e] = sqrt2 * T(0.5) * acc;
+      }
+    }
+  } else if (d.triangle) {
     const int tri = N * (N + 1) / 2;
     for (int e = threadIdx.x; e < tri; e += blockDim.x) {
       // invert e -> (i, j), i <= j

@@ -103,6 +103,20 @@ class PsdConeTriangle(AbstractConvexSet):
             raise ValueError("dimension must be N(N+1)/2")
 
 
+class ComplexPsdConeTriangle(AbstractConvexSet):
+    """COSMO.PsdConeTriangle{T, Complex{T}}(dim), dim = N^2: Hermitian PSD matrices, real upper triangle (sqrt 2 scaled
+    off the diagonal) followed by the imaginary parts of the strict upper triangle (convexset.jl:344-360)."""
+    code = _eng.PSD_TRIANGLE_COMPLEX
+
+    def __init__(self, dim):
+        if dim < 0:
+            raise ValueError("dimension must be nonnegative")
+        self.dim = int(dim)
+        self.sqrt_dim = math.isqrt(self.dim)
+        if self.sqrt_dim * self.sqrt_dim != self.dim:
+            raise ValueError("dimension must be a square")
+
+
 class ExponentialCone(AbstractConvexSet):
     """COSMO.ExponentialCone(): cl{(x,y,z) | y > 0, y e^(x/y) <= z}, convexset.jl:497-507."""
     code = _eng.EXP
@@ -134,7 +148,7 @@ class DualPowerCone(PowerCone):
 
 
 # cones whose rows may only be scaled by one common factor (rectify_scaling!, convexset.jl:955-957)
-SCALAR_SCALED_CONES = (SecondOrderCone, PsdCone, PsdConeTriangle, ExponentialCone, PowerCone)
+SCALAR_SCALED_CONES = (SecondOrderCone, PsdCone, PsdConeTriangle, ComplexPsdConeTriangle, ExponentialCone, PowerCone)
 # cones that cannot be split across ranks
 ATOMIC_CONES = SCALAR_SCALED_CONES
 

@@ -66,7 +66,9 @@ enum {
   COSMO_B200_EXP = 6,          /* ExponentialCone,      convexset.jl:497-618 */
   COSMO_B200_DUAL_EXP = 7,     /* DualExponentialCone,  convexset.jl:749-789 */
   COSMO_B200_POW = 8,          /* PowerCone(alpha),     convexset.jl:625-742 */
-  COSMO_B200_DUAL_POW = 9      /* DualPowerCone(alpha), convexset.jl:765-789 */
+  COSMO_B200_DUAL_POW = 9,     /* DualPowerCone(alpha), convexset.jl:765-789 */
+  COSMO_B200_PSD_TRIANGLE_COMPLEX = 10 /* PsdConeTriangle{T, Complex{T}}(dim), dim = N^2 (convexset.jl:344-360,444-490);
+                                          N <= 48 (projected through the real 2N x 2N embedding in shared memory) */
 };
 
 /* status (src/solver.jl:113,161,175,311-353) */

@@ -25,6 +25,8 @@ def to_oracle_cones(sets):
             out.append(O.PsdCone(S.dim))
         elif isinstance(S, M.PsdConeTriangle):
             out.append(O.PsdConeTriangle(S.dim))
+        elif isinstance(S, M.ComplexPsdConeTriangle):
+            out.append(O.ComplexPsdConeTriangle(S.dim))
         elif isinstance(S, M.DualExponentialCone):
             out.append(O.DualExponentialCone(3, S.MAX_ITER, S.TOL))
         elif isinstance(S, M.ExponentialCone):

@@ -105,6 +105,18 @@ class PsdConeTriangle:  # convexset.jl:362-377 (svec upper triangle)
 
 
 @dataclass
+class ComplexPsdConeTriangle:  # PsdConeTriangle{T, Complex{T}}, convexset.jl:344-379: dim = N^2
+    dim: int
+
+    @property
+    def sqrt_dim(self):
+        r = math.isqrt(self.dim)
+        if r * r != self.dim:
+            raise ValueError("dimension must be a square")
+        return r
+
+
+@dataclass
 class ExponentialCone:  # convexset.jl:497-507  K_exp = cl{(x,y,z) | y > 0, y e^(x/y) <= z}
     dim: int = 3
     MAX_ITER: int = 100
@@ -142,7 +154,7 @@ class DualPowerCone:  # convexset.jl:765-775
             raise ValueError("The exponent alpha of the dual power cone has to be in (0, 1).")
 
 
-SCALAR_SCALED_CONES = (SecondOrderCone, PsdCone, PsdConeTriangle, ExponentialCone, DualExponentialCone, PowerCone,
+SCALAR_SCALED_CONES = (SecondOrderCone, PsdCone, PsdConeTriangle, ComplexPsdConeTriangle, ExponentialCone, DualExponentialCone, PowerCone,
                        DualPowerCone)  # rectify_scaling!, convexset.jl:955-957
 
 
@@ -175,6 +187,45 @@ def extract_upper_triangle(X: np.ndarray, scaling: float) -> np.ndarray:
     r, c = iu[0][order], iu[1][order]
     v = X[r, c]
     return np.where(r == c, v, scaling * v)
+
+
+def populate_upper_triangle_complex(x: np.ndarray, N: int, scaling: float) -> np.ndarray:
+    """populate_upper_triangle!(A::Matrix{Complex}, x, scaling), convexset.jl:456-472 (upper triangle only)."""
+    A = np.zeros((N, N), dtype=complex)
+    k = 0
+    for j in range(N):
+        for i in range(j):
+            A[i, j] = scaling * x[k]
+            k += 1
+        A[j, j] = x[k]
+        k += 1
+    for j in range(N):
+        for i in range(j):
+            A[i, j] += 1j * scaling * x[k]
+            k += 1
+    return A
+
+
+def extract_upper_triangle_complex(A: np.ndarray, scaling: float) -> np.ndarray:
+    """extract_upper_triangle!(A::Matrix{Complex}, x, scaling), convexset.jl:474-490."""
+    N = A.shape[0]
+    re, im = [], []
+    for j in range(N):
+        for i in range(j):
+            re.append(scaling * A[i, j].real)
+            im.append(scaling * A[i, j].imag)
+        re.append(A[j, j].real)
+    return np.array(re + im)
+
+
+def _psd_project_hermitian(Xu: np.ndarray) -> np.ndarray:
+    """_project! for a Hermitian matrix given by its upper triangle (zheevr + rank-k update, convexset.jl:219-263);
+    numpy's eigh (zheevd) stands in for zheevr."""
+    X = np.triu(Xu) + np.triu(Xu, 1).conj().T
+    w, Z = np.linalg.eigh(X)
+    pos = w > 0
+    V = Z[:, pos] * np.sqrt(w[pos])
+    return V @ V.conj().T
 
 
 def _psd_project_upper(X: np.ndarray) -> np.ndarray:
@@ -374,6 +425,12 @@ def project_cone(x: np.ndarray, cone) -> None:
             X = populate_upper_triangle(x, N, 1.0 / math.sqrt(2.0))
             Xp = _psd_project_upper(X)
             x[:] = extract_upper_triangle(Xp, math.sqrt(2.0))
+    elif isinstance(cone, ComplexPsdConeTriangle):  # convexset.jl:402-412 with R = Complex{T}
+        if x.shape[0] == 1:
+            x[:] = max(x[0], 0.0)
+        else:
+            X = populate_upper_triangle_complex(x, cone.sqrt_dim, 1.0 / math.sqrt(2.0))
+            x[:] = extract_upper_triangle_complex(_psd_project_hermitian(X), math.sqrt(2.0))
     elif isinstance(cone, ExponentialCone):
         _project_exp(x, cone)
     elif isinstance(cone, PowerCone):
@@ -400,12 +457,18 @@ def project(s: np.ndarray, cones) -> None:
 # ---- dual-cone / recession predicates ------------------------------------
 def _is_pos_def(X: np.ndarray, tol: float) -> bool:
     """is_pos_def!, algebra.jl:226-233 (Cholesky success on X + tol I, upper)."""
+    if np.iscomplexobj(X):   # Hermitian case: zpotrf on the upper triangle
+        Xs = np.triu(X) + np.triu(X, 1).conj().T + tol * np.eye(X.shape[0])
+        c, info = _lapack.zpotrf(Xs, lower=0)
+        return info == 0
     Xs = np.triu(X) + np.triu(X, 1).T + tol * np.eye(X.shape[0])
     c, info = _lapack.dpotrf(Xs, lower=0)
     return info == 0
 
 
 def _cone_matrix(x, cone):
+    if isinstance(cone, ComplexPsdConeTriangle):
+        return populate_upper_triangle_complex(x, cone.sqrt_dim, 1.0 / math.sqrt(2.0))
     if isinstance(cone, PsdCone):
         n = cone.sqrt_dim
         return x.reshape(n, n, order="F")
@@ -419,7 +482,7 @@ def in_dual(x, cone, tol) -> bool:
         return not np.any(x < -tol)
     if isinstance(cone, SecondOrderCone):  # convexset.jl:116-118
         return np.linalg.norm(x[1:]) <= (tol + x[0])
-    if isinstance(cone, (PsdCone, PsdConeTriangle)):  # convexset.jl:324-329,415-419
+    if isinstance(cone, (PsdCone, PsdConeTriangle, ComplexPsdConeTriangle)):  # convexset.jl:324-329,415-419
         return _is_pos_def(_cone_matrix(x, cone), tol)
     if isinstance(cone, ExponentialCone):
         return _exp_in_dual(x, tol)
@@ -441,7 +504,7 @@ def in_pol_recc(x, cone, tol) -> bool:
         return np.linalg.norm(x[1:]) <= (tol - x[0])
     if isinstance(cone, Box):  # convexset.jl:858-860
         return (not np.any((cone.u == np.inf) & (x > tol))) and (not np.any((cone.l == -np.inf) & (x < -tol)))
-    if isinstance(cone, (PsdCone, PsdConeTriangle)):  # convexset.jl:331-336,421-425 + algebra.jl:235-238
+    if isinstance(cone, (PsdCone, PsdConeTriangle, ComplexPsdConeTriangle)):  # convexset.jl:331-336,421-425 + algebra.jl:235-238
         return _is_pos_def(-_cone_matrix(x, cone), tol)
     if isinstance(cone, (ExponentialCone, PowerCone, DualExponentialCone, DualPowerCone)):
         return in_dual(-x, cone, tol)  # convexset.jl:616-618, 740-742, 781

@@ -323,3 +323,20 @@ def g11_iteration_limit():
     """test/UnitTests/moi_wrapper.jl:201-217 — max x s.t. x >= 10 with max_iter = 2: Max_iter_reached,
     rho_updates == [0.1]."""
     return np.zeros((1, 1)), np.array([-1.0]), [O.Constraint([[1.0]], [-10.0], O.Nonnegatives(1))]
+
+
+def g17_complex_least_eigenvalue():
+    """test/UnitTests/least_eigenvalue.jl:8-39 — min <C, X> s.t. tr X = 1, X Hermitian PSD, for
+    C = [1 i 0; -i 1 i; 0 -i 1]: the least eigenvalue 1 - sqrt 2 (atol = rtol = 1e-4); PsdConeTriangle{T, Complex{T}}(9)."""
+    C = np.array([[1, 1j, 0], [-1j, 1, 1j], [0, -1j, 1]])
+    d = 3
+    vec_c = O.extract_upper_triangle_complex(C, np.sqrt(2.0))
+    id_vec = np.zeros(d * d)
+    for k in range(1, d + 1):
+        id_vec[k * (k + 1) // 2 - 1] = 1.0
+    cons = [O.Constraint(id_vec[None, :], [-1.0], O.ZeroSet(1)),
+            O.Constraint(np.eye(d * d), np.zeros(d * d), O.ComplexPsdConeTriangle(d * d))]
+    return np.zeros((d * d, d * d)), vec_c, cons
+
+
+G17_OBJ = 1.0 - np.sqrt(2.0)

@@ -303,3 +303,36 @@ def test_g11_iteration_limit_keeps_rho():
     res, _ = _solve(G.g11_iteration_limit, max_iter=2)
     assert res.status == "Max_iter_reached" and res.iter == 2
     assert list(res.info.rho_updates) == [0.1]
+
+
+def test_g17_complex_psd_least_eigenvalue():
+    # least_eigenvalue.jl:33-39: obj = 1 - sqrt 2 at atol = rtol = 1e-4 (eps 1e-5)
+    res, _ = _solve(G.g17_complex_least_eigenvalue)
+    assert res.status == "Solved" and abs(res.obj_val - G.G17_OBJ) < 1e-4 + 1e-4 * abs(G.G17_OBJ)
+    res, _ = _solve(G.g17_complex_least_eigenvalue, accelerator="anderson")
+    assert res.status == "Solved" and abs(res.obj_val - G.G17_OBJ) < 1e-4 + 1e-4 * abs(G.G17_OBJ)
+
+
+def test_complex_psd_projection_and_its_real_embedding():
+    # the device projects PsdConeTriangle{T, Complex{T}} through the real embedding [[A, -B], [B, A]] of X = A + iB:
+    # Pi(embedding) = embedding(Pi), checked here against the Hermitian eigendecomposition
+    rng = np.random.default_rng(9)
+    for N in (1, 2, 5, 12):
+        Z = rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))
+        X = (Z + Z.conj().T) / 2
+        x = O.extract_upper_triangle_complex(X, np.sqrt(2.0))
+        assert x.shape == (N * N,)
+        assert np.allclose(np.triu(O.populate_upper_triangle_complex(x, N, 1 / np.sqrt(2.0))), np.triu(X))
+        p = x.copy()
+        O.project_cone(p, O.ComplexPsdConeTriangle(N * N))
+        w, V = np.linalg.eigh(X)
+        Xp = (V * np.maximum(w, 0)) @ V.conj().T
+        assert np.allclose(p, O.extract_upper_triangle_complex(Xp, np.sqrt(2.0)), atol=1e-12)
+        A, B = X.real, X.imag
+        M = np.block([[A, -B], [B, A]])
+        wm, Vm = np.linalg.eigh(M)
+        Mp = (Vm * np.maximum(wm, 0)) @ Vm.T
+        assert np.allclose(Mp[:N, :N], Xp.real, atol=1e-12) and np.allclose(Mp[N:, :N], Xp.imag, atol=1e-12)
+        assert np.allclose(Mp[N:, N:], Xp.real, atol=1e-12) and np.allclose(Mp[:N, N:], -Xp.imag, atol=1e-12)
+        # membership predicates (convexset.jl:415-425)
+        assert O.in_dual(p, O.ComplexPsdConeTriangle(N * N), 1e-8) and O.in_pol_recc(-p, O.ComplexPsdConeTriangle(N * N), 1e-8)
