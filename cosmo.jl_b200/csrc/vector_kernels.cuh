@@ -180,15 +180,13 @@ __global__ void __launch_bounds__(kBlock) rho_vec_kernel(int m, const unsigned c
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kBlock) scale_kernel(int n, const T* __restrict__ a, const T* __restrict__ x,
-                                                       T* __restrict__ y) {
+__global__ void __launch_bounds__(kBlock) scale_kernel(int n, const T* __restrict__ a, const T* x, T* y) {   // y may alias x
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] = a[i] * x[i];
 }
 
 // y = a - b
 template <typename T>
-__global__ void __launch_bounds__(kBlock) sub_kernel(int n, const T* __restrict__ a, const T* __restrict__ b,
-                                                     T* __restrict__ y) {
+__global__ void __launch_bounds__(kBlock) sub_kernel(int n, const T* a, const T* __restrict__ b, T* y) {   // y may alias a
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] = a[i] - b[i];
 }
 
