@@ -52,7 +52,7 @@ for N in [int(a) for a in sys.argv[1:]] or [300, 1000, 2000]:
         O.project(ref, to_oracle_cones(sets))
         t_cpu = time.time() - t0
         row = {"N": N, "matrix": name, "cpu_dsyevr_s": round(t_cpu, 4)}
-        for mode in ("0", "1"):
+        for mode in ("0", "1", "2"):      # block Jacobi / hand-written symmetric products / cuBLAS comparator
             os.environ["COSMO_B200_PSD_SIGN"] = mode
             eng = E.Engine(sp.identity(1, format="csc"), np.zeros(1), sp.csc_matrix((d, 1)), np.zeros(d),
                            [cosmo_b200.model.set_tuple(S) for S in sets], cosmo_b200.Settings(scaling=0).to_struct())
@@ -60,7 +60,7 @@ for N in [int(a) for a in sys.argv[1:]] or [300, 1000, 2000]:
             t0 = time.time()
             got = eng.project(ws)
             dt = time.time() - t0
-            key = "sign" if mode == "1" else "jacobi"
+            key = {"0": "jacobi", "1": "sign", "2": "sign_cublas"}[mode]
             row[key + "_s"] = round(dt, 4)
             row[key + "_relerr"] = float(np.linalg.norm(got - ref) / (np.linalg.norm(ws) + 1e-300))
             eng.close()
