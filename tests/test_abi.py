@@ -144,3 +144,34 @@ def test_c_header_layout_matches_ctypes_mirror(tmp_path):
     assert checked >= 35
     assert vals["abi"] == "2" and vals["defaults"] == "0.1 1e-06 1.6 5000 0 15 2"
     assert int(vals["create_null"]) == E.ERR_INVALID and "null" in vals["last_error"]
+
+
+def _build_c_example(tmp_path):
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    lib_path = E.load_library()._name
+    exe = str(tmp_path / "solve_qp")
+    subprocess.run([cc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "solve_qp.c"),
+                    lib_path, "-Wl,-rpath," + os.path.dirname(lib_path), "-lm", "-o", exe], check=True)
+    return exe
+
+
+def test_c_example_builds_and_fails_loudly_without_a_gpu(tmp_path):
+    # examples/solve_qp.c: the reference's examples/qp.jl through the C ABI from plain C
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu-marked run of the same program")
+    out = subprocess.run([_build_c_example(tmp_path)], capture_output=True, text=True)
+    assert out.returncode == 3 and "no CPU fallback" in out.stdout     # arguments passed validation, then: no device
+
+
+@pytest.mark.gpu
+def test_c_example_solves_the_reference_qp(tmp_path):
+    import subprocess
+    out = subprocess.run([_build_c_example(tmp_path)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.startswith("status 1 ")                              # COSMO_B200_SOLVED; x = (0.3, 0.7), obj 1.88 checked in C
