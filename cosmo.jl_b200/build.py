@@ -7,15 +7,23 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcosmo_b200.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["common.cuh", "spmv.cuh", "vector_kernels.cuh", "psd.cuh", "cg_persistent.cuh", "../../include/cosmo_b200.h"]
+import glob
+
+
+def _deps():
+    """Every source the library is compiled from: all of csrc/ plus the public header."""
+    deps = sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh"))
+                  + glob.glob(os.path.join(CSRC, "*.h")))
+    deps.append(os.path.join(HERE, "..", "include", "cosmo_b200.h"))
+    deps.append(os.path.abspath(__file__))
+    return deps
 
 
 def _stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return any(os.path.getmtime(d) > t for d in _deps())
 
 
 def nvcc_path():
