@@ -1,0 +1,564 @@
+// tc_gemm.cuh -- fp64-accurate products of symmetric matrices on the 5th-generation tensor cores (sm_100a).
+//
+// The PSD projection of a large cone (convexset.jl:219-263 in the reference: dsyevr + clamp + syrk) is computed here
+// as  Pi_+(X) = (X + sign(X) X) / 2  with sign(X) from a Newton-Schulz iteration (psd_tc.cuh) -- nothing but
+// N x N x N products of symmetric, commuting matrices.  tcgen05.mma has no fp64 kind, so every product is evaluated
+// by error-free slicing (Ozaki scheme I):
+//
+//     M[r, :] = 2^(e_r - 6) * sum_p D_p[r, :] * 128^-(p-1),   D_p int8 digits in [-64, 64]   (slice_rows_kernel)
+//     (A B)[m, n] = sA[m] sB[n] * sum_s 128^-(s-2) G_s[m, n],  G_s = sum_{p+q=s} A_p B_q^T     (int32, EXACT)
+//
+// G_s is accumulated by tcgen05.mma.kind::i8 in TMEM (|G_s| <= 8 * K * 64^2 < 2^31 for K <= 65536), the sum over s is
+// a Horner recurrence in fp64 registers of the epilogue warps (acc <- acc / 128 + G_s, least significant group first),
+// so the only rounding errors are the truncation of the slices (2^-7k relative to the row maximum) and one fp64
+// rounding per group.  k = 7 slices reproduce dgemm to ~1e-15 relative to |A|_row |B|_col.
+//
+// Kernel anatomy (one persistent CTA per SM, 10 warps):
+//   warp 0      TMA producer: cp.async.bulk.tensor (3-d maps over the [slice][row][k] int8 arrays, 128 x KSTEP byte
+//               boxes, hardware swizzle) into a ring of shared-memory stages, mbarrier complete_tx
+//   warp 1      MMA issuer: one elected lane walks the pass list of the plan and issues tcgen05.mma (M = N = 128,
+//               K = 32 bytes) from shared-memory descriptors into up to four 128-column TMEM accumulators;
+//               tcgen05.commit releases the stage / publishes the accumulators
+//   warps 2..9  epilogue: tcgen05.ld 32x32b, int32 -> fp64 Horner accumulation, scaling, fused
+//               out = c0 * (A B) + c1 * D + c2 * I, mirrored store (the product of commuting symmetric matrices is
+//               symmetric: only tiles of the upper triangle are computed) and two fused Frobenius reductions.
+// The "plan" (built on the host, copied to shared memory) says which slices a stage holds and which (A slice, B slice,
+// accumulator) products are issued per stage, so that operand tiles are re-used across the slice pairs of several
+// groups while they sit in shared memory (L2 -> SM traffic is what bounds an int8 product of this shape).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+namespace cosmo {
+namespace tc {
+
+constexpr int kTile = 128;         // output tile side = rows of one operand tile = UMMA M = UMMA N
+constexpr int kMaxSlices = 8;
+constexpr int kMaxOps = 32;        // products per stage
+constexpr int kMaxPasses = 36;
+constexpr int kThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kEpiWarps = 8;
+constexpr int kSmemBudget = 200 * 1024;   // ring of operand stages (the rest: plan, barriers, reduction scratch)
+
+struct MmaOp { uint8_t a, b, acc, first; };   // stage slot of the A / B tile, accumulator 0..3, 1: first write of acc in its batch
+struct Pass {
+  uint8_t nA, nB, nops, flags;     // flags: 1 = first pass of a batch (wait for the TMEM slots), 2 = last (publish them)
+  uint8_t slot_mask, ngroups, pad0, pad1;   // TMEM halves used by the batch: bit 0 -> accumulators 0,1; bit 1 -> 2,3
+  uint8_t sliceA[kMaxSlices], sliceB[kMaxSlices];
+  uint8_t acc_order[4];            // last pass only: accumulators of the batch in Horner order (descending s)
+  MmaOp ops[kMaxOps];
+};
+struct Plan {
+  int npasses, stage_tiles, nstages, kstep;
+  Pass p[kMaxPasses];
+};
+
+// Host: the pass list for k slices.  `gpb` groups per batch (1, 2 or 4): the accumulators of a batch live in TMEM
+// together, so a stage's tiles serve the slice pairs of all of them.
+inline bool make_plan(Plan& pl, int k, int gpb, int kstep, std::string& err) {
+  memset(&pl, 0, sizeof(pl));
+  if (k < 1 || k > kMaxSlices || (gpb != 1 && gpb != 2 && gpb != 4) || (kstep != 32 && kstep != 64 && kstep != 128)) {
+    err = "tc::make_plan: bad parameters";
+    return false;
+  }
+  const int tile_bytes = kTile * kstep;
+  const int max_tiles = std::min(2 * kMaxSlices, kSmemBudget / (2 * tile_bytes));   // at least two stages
+  pl.kstep = kstep;
+  int stage_tiles = 0, batch = 0;
+  for (int s_hi = k + 1; s_hi >= 2; s_hi -= gpb, ++batch) {
+    const int ng = std::min(gpb, s_hi - 1);
+    const int slot_mask = (gpb == 4) ? 3 : (1 << (batch & 1));
+    const int acc0 = (gpb == 4) ? 0 : 2 * (batch & 1);
+    // pairs of the batch, ordered by A slice so that a pass holds few A tiles and many B tiles
+    struct Pr { int p, q, acc; };
+    std::vector<Pr> prs;
+    for (int p = 1; p <= k; ++p)
+      for (int g = 0; g < ng; ++g) {
+        const int s = s_hi - g, q = s - p;
+        if (q >= 1 && q <= k) prs.push_back({p, q, acc0 + g});
+      }
+    bool first_write[4] = {true, true, true, true};
+    size_t i = 0;
+    bool first_pass = true;
+    while (i < prs.size()) {
+      if (pl.npasses >= kMaxPasses) { err = "tc::make_plan: too many passes"; return false; }
+      Pass& ps = pl.p[pl.npasses++];
+      ps.flags = first_pass ? 1 : 0;
+      first_pass = false;
+      ps.slot_mask = (uint8_t)slot_mask;
+      int ia[kMaxSlices + 1], ib[kMaxSlices + 1];
+      for (int t = 0; t <= kMaxSlices; ++t) ia[t] = ib[t] = -1;
+      while (i < prs.size() && ps.nops < kMaxOps) {
+        const Pr& pr = prs[i];
+        const int needA = ia[pr.p] < 0, needB = ib[pr.q] < 0;
+        if (ps.nA + ps.nB + needA + needB > max_tiles) break;
+        if (needA) { ia[pr.p] = ps.nA; ps.sliceA[ps.nA++] = (uint8_t)(pr.p - 1); }
+        if (needB) { ib[pr.q] = ps.nB; ps.sliceB[ps.nB++] = (uint8_t)(pr.q - 1); }
+        ps.ops[ps.nops++] = MmaOp{(uint8_t)ia[pr.p], (uint8_t)ib[pr.q], (uint8_t)pr.acc, (uint8_t)(first_write[pr.acc] ? 1 : 0)};
+        first_write[pr.acc] = false;
+        ++i;
+      }
+      if (ps.nops == 0) { err = "tc::make_plan: stage too small"; return false; }
+      stage_tiles = std::max(stage_tiles, (int)ps.nA + ps.nB);
+      if (i == prs.size()) {
+        ps.flags |= 2;
+        ps.ngroups = (uint8_t)ng;
+        for (int g = 0; g < ng; ++g) ps.acc_order[g] = (uint8_t)(acc0 + g);   // s_hi first: least significant group
+      }
+    }
+  }
+  pl.stage_tiles = stage_tiles;
+  pl.nstages = std::min(8, kSmemBudget / (stage_tiles * tile_bytes));
+  if (pl.nstages < 2) { err = "tc::make_plan: fewer than two stages fit"; return false; }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra LAB_DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "LAB_DONE:\n\t}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, int8 x int8 -> int32, M = N = 128, K = 32
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// shared-memory matrix descriptor, K-major tile of 128 rows x KSTEP bytes written by TMA with a KSTEP-byte swizzle
+// (atoms of 8 rows x KSTEP bytes, stride between atoms along M/N = 8 * KSTEP)
+template <int KSTEP>
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
+  constexpr uint64_t layout = KSTEP == 128 ? 2 : (KSTEP == 64 ? 4 : 6);   // SWIZZLE_128B / 64B / 32B
+  constexpr uint64_t sbo = (8 * KSTEP) >> 4;
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+// instruction descriptor: S32 accumulate, signed 8-bit A and B, both K-major, N = 128, M = 128
+constexpr uint32_t kIdescI8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTile >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
+
+#define COSMO_TC_LD32(taddr, v)                                                                                          \
+  asm volatile(                                                                                                          \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                          \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                          \
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                          \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),      \
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),           \
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),          \
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                        \
+      : "r"(taddr))
+
+// ---------------------------------------------------------------------------------------------------------------
+// Slicing: one CTA per row.  scale[r] = 2^(e_r - 6) with 2^e_r > max |M[r, :]|; digits by round-to-nearest so that
+// every digit is in [-64, 64]; all operations are exact in fp64.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) slice_rows_kernel(const T* __restrict__ M, int N, int Np, int k, int8_t* __restrict__ slices,
+                                                        double* __restrict__ scale) {
+  const int r = blockIdx.x;
+  const T* row = M + (size_t)r * N;   // symmetric: row r == column r of the column-major matrix
+  __shared__ double red[8];
+  double mx = 0.0;
+  for (int c = threadIdx.x; c < N; c += blockDim.x) mx = fmax(mx, fabs((double)row[c]));
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int w = 1; w < 8; ++w) mx = fmax(mx, red[w]);
+  int e = 0;
+  if (mx > 0.0 && mx < 1.0e300) frexp(mx, &e);   // mx = f 2^e, f in [0.5, 1)  =>  |x| < 2^e
+  if (threadIdx.x == 0) scale[r] = ldexp(1.0, e - 6);
+  const double inv = ldexp(1.0, 6 - e);
+  const size_t plane = (size_t)Np * Np;
+  for (int c0 = threadIdx.x * 8; c0 < N; c0 += blockDim.x * 8) {
+    double t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = (c0 + j < N) ? (double)row[c0 + j] * inv : 0.0;
+    for (int p = 0; p < k; ++p) {
+      uint32_t lo = 0, hi = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const double d = rint(t[j]);
+        t[j] = (t[j] - d) * 128.0;
+        const uint32_t b = (uint32_t)(uint8_t)(int8_t)(int)d;
+        if (j < 4) lo |= b << (8 * j); else hi |= b << (8 * (j - 4));
+      }
+      *reinterpret_cast<uint2*>(slices + (size_t)p * plane + (size_t)r * Np + c0) = make_uint2(lo, hi);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The product kernel
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+struct GemmArgs {
+  int N, Np, ntiles, store;          // store: 1 = write `out`
+  const int2* tiles;                 // (bi, bj), bi <= bj: tiles of the upper triangle
+  const double* scaleA;              // Np row scales of the A operand
+  const double* scaleB;              // Np row (= column) scales of the B operand
+  T* out;                            // N x N, ld = N (symmetric, mirrored store)
+  const T* D;                        // optional: out = c0 * (A B) + c1 * D + c2 * I
+  const T* E;                        // optional reference of the second reduction
+  int e_identity;                    // 1: second reduction against the identity
+  const double* coef;                // device scalars c0, c1, c2
+  double* partial;                   // 2 per tile: sum w out^2, sum w (E - out)^2   (w: 1 on the diagonal, 2 above it)
+};
+
+template <typename T, int KSTEP>
+__global__ void __launch_bounds__(kThreads, 1) ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmapA,
+                                                                 const __grid_constant__ CUtensorMap tmapB,
+                                                                 const Plan* __restrict__ plan_g, const GemmArgs<T> args) {
+  constexpr int kTileBytes = kTile * KSTEP;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [ring of stages (1024-aligned)] [plan] [barriers] [tmem base] [reduction scratch]
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ Plan plan;
+  __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ double red[kEpiWarps][2];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(plan_g);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&plan);
+    for (int i = threadIdx.x; i < (int)(sizeof(Plan) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int nstages = plan.nstages;
+  const int stage_bytes = plan.stage_tiles * kTileBytes;
+  const int nk = args.Np / KSTEP;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < nstages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // the allocating warp also frees
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < args.ntiles; t += gridDim.x) {
+        const int2 tl = args.tiles[t];
+        const int m0 = tl.x * kTile, n0 = tl.y * kTile;
+        for (int pi = 0; pi < plan.npasses; ++pi) {
+          const Pass& ps = plan.p[pi];
+          const uint32_t bytes = (uint32_t)(ps.nA + ps.nB) * kTileBytes;
+          for (int ks = 0; ks < nk; ++ks) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], bytes);
+            uint8_t* dst = smem + (size_t)stage * stage_bytes;
+            for (int i = 0; i < ps.nA; ++i) tma_load_3d(dst + i * kTileBytes, &tmapA, &full_bar[stage], ks * KSTEP, m0, ps.sliceA[i]);
+            for (int i = 0; i < ps.nB; ++i)
+              tma_load_3d(dst + (ps.nA + i) * kTileBytes, &tmapB, &full_bar[stage], ks * KSTEP, n0, ps.sliceB[i]);
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, tphase[2] = {0, 0};
+      for (int t = blockIdx.x; t < args.ntiles; t += gridDim.x) {
+        for (int pi = 0; pi < plan.npasses; ++pi) {
+          const Pass& ps = plan.p[pi];
+          if (ps.flags & 1) {
+            for (int h = 0; h < 2; ++h)
+              if (ps.slot_mask & (1 << h)) mbar_wait(&tempty_bar[h], tphase[h] ^ 1);
+            tc_fence_after();
+          }
+          for (int ks = 0; ks < nk; ++ks) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sbase = smem_u32(smem + (size_t)stage * stage_bytes);
+            for (int o = 0; o < ps.nops; ++o) {
+              const MmaOp op = ps.ops[o];
+              const uint64_t ad = smem_desc<KSTEP>(sbase + op.a * kTileBytes);
+              const uint64_t bd = smem_desc<KSTEP>(sbase + (ps.nA + op.b) * kTileBytes);
+              const uint32_t d = tmem_base + (uint32_t)op.acc * kTile;
+#pragma unroll
+              for (int kk = 0; kk < KSTEP / 32; ++kk)
+                tc_mma_i8(d, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), kIdescI8, (ks | kk | (op.first ^ 1)) ? 1u : 0u);
+            }
+            tc_commit(&empty_bar[stage]);
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
+          }
+          if (ps.flags & 2) {
+            for (int h = 0; h < 2; ++h)
+              if (ps.slot_mask & (1 << h)) { tc_commit(&tfull_bar[h]); tphase[h] ^= 1; }
+          }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue warps =====
+    const int ew = warp - 2;
+    const int quad = warp & 3;            // TMEM lanes [32 quad, 32 quad + 32) are the ones this warp may read
+    const int half = ew >> 2;             // columns [64 half, 64 half + 64) of the tile
+    const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 64);
+    uint32_t tphase[2] = {0, 0};
+    const double c0 = args.coef[0], c1 = args.coef[1], c2 = args.coef[2];
+    for (int t = blockIdx.x; t < args.ntiles; t += gridDim.x) {
+      const int2 tl = args.tiles[t];
+      const int gm = tl.x * kTile + quad * 32 + lane;
+      const int gn0 = tl.y * kTile + half * 64;
+      double acc[64];
+#pragma unroll
+      for (int j = 0; j < 64; ++j) acc[j] = 0.0;
+      for (int pi = 0; pi < plan.npasses; ++pi) {
+        const Pass& ps = plan.p[pi];
+        if (!(ps.flags & 2)) continue;
+        for (int h = 0; h < 2; ++h)
+          if (ps.slot_mask & (1 << h)) { mbar_wait(&tfull_bar[h], tphase[h]); tphase[h] ^= 1; }
+        tc_fence_after();
+        for (int g = 0; g < ps.ngroups; ++g) {
+          const uint32_t ta = tlane + (uint32_t)ps.acc_order[g] * kTile;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            COSMO_TC_LD32(ta + c * 32, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[c * 32 + j] = fma(acc[c * 32 + j], 0.0078125, (double)(int)v[j]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0)
+          for (int h = 0; h < 2; ++h)
+            if (ps.slot_mask & (1 << h)) mbar_arrive(&tempty_bar[h]);
+      }
+      // ---- final epilogue of the tile ----
+      double r0 = 0.0, r1 = 0.0;
+      const int N = args.N;
+      if (gm < N) {
+        const double sa = args.scaleA[gm];
+#pragma unroll 4
+        for (int j = 0; j < 64; ++j) {
+          const int gn = gn0 + j;
+          if (gn >= N || gm > gn) continue;               // upper triangle only; the mirror is written below
+          double o = c0 * (acc[j] * sa * args.scaleB[gn]);
+          const size_t tidx = (size_t)gn * N + gm;        // element (gm, gn) of a column-major matrix (coalesced over lanes)
+          if (args.D) o += c1 * (double)args.D[tidx];
+          if (gm == gn) o += c2;
+          const double w = (gm == gn) ? 1.0 : 2.0;
+          r0 += w * o * o;
+          if (args.e_identity || args.E) {
+            const double ref = args.E ? (double)args.E[tidx] : ((gm == gn) ? 1.0 : 0.0);
+            r1 += w * (ref - o) * (ref - o);
+          }
+          if (args.store) {
+            args.out[tidx] = (T)o;
+            if (gm != gn) args.out[(size_t)gm * N + gn] = (T)o;
+          }
+        }
+      }
+      if (args.partial) {
+        for (int o = 16; o > 0; o >>= 1) {
+          r0 += __shfl_xor_sync(0xffffffffu, r0, o);
+          r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");     // previous tile's reader is done with red[]
+        if (lane == 0) { red[ew][0] = r0; red[ew][1] = r1; }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (ew == 0 && lane == 0) {
+          double a = 0.0, b = 0.0;
+          for (int w = 0; w < kEpiWarps; ++w) { a += red[w][0]; b += red[w][1]; }
+          args.partial[2 * t] = a;
+          args.partial[2 * t + 1] = b;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// One sliced operand: int8 [k][Np][Np] + Np scales, and its tensor map for the current (Np, kstep).
+struct Sliced {
+  int8_t* d = nullptr;
+  double* scale = nullptr;
+  CUtensorMap map;
+  int capNp = 0, capK = 0, mapNp = 0, mapKstep = 0;
+  ~Sliced() { cudaFree(d); cudaFree(scale); }
+  bool ensure(int Np, int k, cudaStream_t st) {
+    if (Np <= capNp && k <= capK) return true;
+    cudaFree(d); cudaFree(scale);
+    d = nullptr; scale = nullptr; capNp = capK = 0; mapNp = 0;
+    const size_t bytes = (size_t)k * Np * Np;
+    if (cudaMalloc(&d, bytes) != cudaSuccess || cudaMalloc(&scale, (size_t)Np * sizeof(double)) != cudaSuccess) return false;
+    capNp = Np; capK = k;
+    (void)st;
+    return true;
+  }
+  // zero padding rows / columns (and everything else) for a new (N, Np): called when the shape changes
+  bool clear(int Np, int k, cudaStream_t st) {
+    return cudaMemsetAsync(d, 0, (size_t)k * Np * Np, st) == cudaSuccess &&
+           cudaMemsetAsync(scale, 0, (size_t)Np * sizeof(double), st) == cudaSuccess;
+  }
+  bool make_map(int Np, int k, int kstep) {
+    if (mapNp == Np && mapKstep == kstep) return true;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)Np, (cuuint64_t)Np, (cuuint64_t)k};
+    const cuuint64_t strides[2] = {(cuuint64_t)Np, (cuuint64_t)Np * Np};
+    const cuuint32_t box[3] = {(cuuint32_t)kstep, (cuuint32_t)kTile, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapSwizzle sw = kstep == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (kstep == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, d, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return false;
+    mapNp = Np; mapKstep = kstep;
+    return true;
+  }
+};
+
+template <typename T>
+struct OzakiGemm {
+  Plan plan_h;
+  Plan* plan_d = nullptr;
+  int2* tiles_d = nullptr;
+  int tilesNp = 0, ntiles = 0;
+  int k = 7, kstep = 128, gpb = 1, num_sms = 148;
+  int N = 0, Np = 0;
+  bool ready = false;
+  std::string err;
+  ~OzakiGemm() { cudaFree(plan_d); cudaFree(tiles_d); }
+
+  static int env_int(const char* name, int def) {
+    const char* e = getenv(name);
+    return (e && *e) ? atoi(e) : def;
+  }
+  bool configure(int k_, int kstep_, int gpb_, cudaStream_t st) {
+    k = k_; kstep = kstep_; gpb = gpb_;
+    if (!make_plan(plan_h, k, gpb, kstep, err)) return false;
+    if (!plan_d && cudaMalloc(&plan_d, sizeof(Plan)) != cudaSuccess) { err = "cudaMalloc plan"; return false; }
+    if (cudaMemcpyAsync(plan_d, &plan_h, sizeof(Plan), cudaMemcpyHostToDevice, st) != cudaSuccess) { err = "copy plan"; return false; }
+    cudaStreamSynchronize(st);   // plan_h may change before the copy is consumed otherwise
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    const int smem = smem_bytes();
+    cudaError_t e1 = cudaFuncSetAttribute(ozaki_gemm_kernel<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e2 = cudaFuncSetAttribute(ozaki_gemm_kernel<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e3 = cudaFuncSetAttribute(ozaki_gemm_kernel<T, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { err = "cudaFuncSetAttribute(ozaki_gemm_kernel)"; return false; }
+    ready = true;
+    return true;
+  }
+  int smem_bytes() const { return plan_h.nstages * plan_h.stage_tiles * kTile * kstep + 1024; }
+  bool set_shape(int N_, cudaStream_t st) {
+    N = N_;
+    Np = (N + kTile - 1) / kTile * kTile;
+    if (tilesNp != Np) {
+      const int nt = Np / kTile;
+      std::vector<int2> tl;
+      for (int bj = 0; bj < nt; ++bj)
+        for (int bi = 0; bi <= bj; ++bi) tl.push_back(make_int2(bi, bj));
+      // long tiles first would not matter (all tiles cost the same); diagonal-major order keeps A/B tiles of
+      // concurrently running CTAs close in L2
+      cudaFree(tiles_d);
+      tiles_d = nullptr;
+      if (cudaMalloc(&tiles_d, tl.size() * sizeof(int2)) != cudaSuccess) { err = "cudaMalloc tiles"; return false; }
+      if (cudaMemcpyAsync(tiles_d, tl.data(), tl.size() * sizeof(int2), cudaMemcpyHostToDevice, st) != cudaSuccess) { err = "copy tiles"; return false; }
+      cudaStreamSynchronize(st);
+      ntiles = (int)tl.size();
+      tilesNp = Np;
+    }
+    return true;
+  }
+  // slices of an N x N symmetric matrix (ld = N) into `sl` (padding rows / columns must have been cleared)
+  bool slice(const T* M, Sliced& sl, cudaStream_t st) {
+    slice_rows_kernel<T><<<N, 256, 0, st>>>(M, N, Np, k, sl.d, sl.scale);
+    return cudaGetLastError() == cudaSuccess;
+  }
+  // out = c0 (A B) + c1 D + c2 I   (+ reductions into partial[2 * ntiles])
+  bool gemm(Sliced& A, Sliced& B, T* out, const T* D, const T* E, int e_identity, const double* coef_d, double* partial,
+            cudaStream_t st) {
+    if (!A.make_map(Np, k, kstep) || !B.make_map(Np, k, kstep)) { err = "cuTensorMapEncodeTiled failed"; return false; }
+    GemmArgs<T> a;
+    a.N = N; a.Np = Np; a.ntiles = ntiles; a.store = out ? 1 : 0;
+    a.tiles = tiles_d; a.scaleA = A.scale; a.scaleB = B.scale; a.out = out; a.D = D; a.E = E; a.e_identity = e_identity;
+    a.coef = coef_d; a.partial = partial;
+    const int grid = std::min(ntiles, num_sms);
+    const int smem = smem_bytes();
+    if (kstep == 128) ozaki_gemm_kernel<T, 128><<<grid, kThreads, smem, st>>>(A.map, B.map, plan_d, a);
+    else if (kstep == 64) ozaki_gemm_kernel<T, 64><<<grid, kThreads, smem, st>>>(A.map, B.map, plan_d, a);
+    else ozaki_gemm_kernel<T, 32><<<grid, kThreads, smem, st>>>(A.map, B.map, plan_d, a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { err = std::string("ozaki_gemm_kernel launch: ") + cudaGetErrorString(e); return false; }
+    return true;
+  }
+};
+
+}  // namespace tc
+}  // namespace cosmo
