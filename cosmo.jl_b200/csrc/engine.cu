@@ -1929,4 +1929,63 @@ int cosmo_b200_comm_p2p_attach(cosmo_b200_handle* h, const void* blobs, int32_t 
   ABI_GUARD(h, h->impl->p2p_attach(blobs, nranks));
 }
 
+// ---- diagnostics of the tensor-core PSD path (tc_gemm.cuh, psd_tc.cuh) ----------------------------------------
+// C = A B for symmetric commuting N x N fp64 matrices (column-major, ld = N) through the int8-sliced tcgen05 product.
+int cosmo_b200_tc_gemm_test(int32_t N, int32_t k, int32_t kstep, int32_t gpb, const double* A, const double* B, double* C,
+                            int32_t reps, double* ms_per_product, double* frob2) {
+  if (N <= 0 || !A || !B || !C) return COSMO_B200_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cosmo::g_create_error = "no CUDA device"; return COSMO_B200_ERR_CUDA; }
+  cudaStream_t st;
+  if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return COSMO_B200_ERR_CUDA;
+  int rc = COSMO_B200_OK;
+  double *A_d = nullptr, *B_d = nullptr, *C_d = nullptr, *coef_d = nullptr, *part_d = nullptr;
+  {
+    cosmo::tc::OzakiGemm<double> g;
+    cosmo::tc::Sliced sa, sb;
+    const size_t nn = (size_t)N * N;
+    const double coef[3] = {1.0, 0.0, 0.0};
+    bool ok = g.configure(k, kstep, gpb, st) && g.set_shape(N, st);
+    ok = ok && cudaMalloc(&A_d, nn * 8) == cudaSuccess && cudaMalloc(&B_d, nn * 8) == cudaSuccess && cudaMalloc(&C_d, nn * 8) == cudaSuccess &&
+         cudaMalloc(&coef_d, 3 * 8) == cudaSuccess && cudaMalloc(&part_d, (size_t)2 * (g.ntiles + 1) * 8) == cudaSuccess;
+    ok = ok && sa.ensure(g.Np, k, st) && sb.ensure(g.Np, k, st) && sa.clear(g.Np, k, st) && sb.clear(g.Np, k, st);
+    ok = ok && cudaMemcpyAsync(A_d, A, nn * 8, cudaMemcpyHostToDevice, st) == cudaSuccess &&
+         cudaMemcpyAsync(B_d, B, nn * 8, cudaMemcpyHostToDevice, st) == cudaSuccess &&
+         cudaMemcpyAsync(coef_d, coef, 3 * 8, cudaMemcpyHostToDevice, st) == cudaSuccess &&
+         cudaMemsetAsync(C_d, 0, nn * 8, st) == cudaSuccess;
+    ok = ok && g.slice(A_d, sa, st) && g.slice(B_d, sb, st);
+    ok = ok && g.gemm(sa, sb, C_d, nullptr, nullptr, 1, coef_d, part_d, st);
+    ok = ok && cudaStreamSynchronize(st) == cudaSuccess;
+    if (ok && reps > 0 && ms_per_product) {
+      cudaEvent_t e0, e1;
+      cudaEventCreate(&e0); cudaEventCreate(&e1);
+      cudaEventRecord(e0, st);
+      for (int r = 0; r < reps && ok; ++r) ok = g.gemm(sa, sb, C_d, nullptr, nullptr, 1, coef_d, part_d, st);
+      cudaEventRecord(e1, st);
+      ok = ok && cudaEventSynchronize(e1) == cudaSuccess;
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      *ms_per_product = ms / reps;
+      cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    ok = ok && cudaMemcpyAsync(C, C_d, nn * 8, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    if (ok && frob2) {
+      std::vector<double> part(2 * g.ntiles);
+      ok = cudaMemcpyAsync(part.data(), part_d, part.size() * 8, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+           cudaStreamSynchronize(st) == cudaSuccess;
+      frob2[0] = frob2[1] = 0.0;
+      for (int i = 0; i < g.ntiles; ++i) { frob2[0] += part[2 * i]; frob2[1] += part[2 * i + 1]; }
+    }
+    ok = ok && cudaStreamSynchronize(st) == cudaSuccess;
+    if (!ok) {
+      cudaError_t e = cudaGetLastError();
+      cosmo::g_create_error = "tc_gemm_test: " + (g.err.empty() ? std::string(cudaGetErrorString(e)) : g.err);
+      rc = COSMO_B200_ERR_CUDA;
+    }
+  }
+  cudaFree(A_d); cudaFree(B_d); cudaFree(C_d); cudaFree(coef_d); cudaFree(part_d);
+  cudaStreamDestroy(st);
+  return rc;
+}
+
 }  // extern "C"

@@ -744,6 +744,7 @@ __global__ void psd_large_lammax_kernel(int N, const T* __restrict__ A, T* __res
 
 }  // namespace cosmo
 #include "psd_sign.cuh"
+#include "psd_tc.cuh"
 namespace cosmo {
 
 // ---------------------------------------------------------------------------
@@ -773,6 +774,10 @@ struct PsdBatch {
   PsdSign<T> sign_;      // experimental GEMM-only projection (psd_sign.cuh), COSMO_B200_PSD_SIGN=1
   bool sign_enabled = PsdSign<T>::enabled();
   long long sign_projections = 0, sign_fallbacks = 0;
+  PsdTc<T> tc_;          // tensor-core projection (psd_tc.cuh): Newton-Schulz on int8-sliced tcgen05 products
+  bool tc_enabled = PsdTc<T>::enabled();
+  int tc_min_n = PsdTc<T>::min_n();
+  long long tc_projections = 0, tc_fallbacks = 0;
   T* R_d = nullptr;      // npairs * 64 * 64 pivot rotations
   int* act_d = nullptr;  // per pair: pivot needed work this round
   std::vector<T> lam_host;
@@ -898,6 +903,16 @@ struct PsdBatch {
       ++launches;
     }
     for (const auto& d : large_h) {
+      if (tc_enabled && !sign_enabled && d.N >= tc_min_n) {
+        const int N = d.N;
+        const int g = (int)std::min<long long>(((long long)N * N + kBlock - 1) / kBlock, kMaxGrid);
+        psd_large_load_kernel<T><<<g, kBlock, 0, st>>>(d, ws, A_d, V_d, fro_d);
+        ++launches;
+        if (tc_.project(d, A_d, fro_d, g, V_d, s, st, launches)) { ++tc_projections; continue; }
+        ++tc_fallbacks;
+        if (getenv("COSMO_B200_PSD_DEBUG")) fprintf(stderr, "[psd-tc] fallback to block Jacobi: %s\n", tc_.err.c_str());
+        cudaGetLastError();
+      }
       if (sign_enabled) {   // experimental: Pi_+(X) = (X + sign(X) X) / 2 by Newton-Schulz products, no eigenvectors
         const int N = d.N;
         const int g = (int)std::min<long long>(((long long)N * N + kBlock - 1) / kBlock, kMaxGrid);

@@ -14,14 +14,13 @@
 // with |lambda| < 1.5^-k |X| have not reached +-1 after k steps, but they enter the projection with weight
 // |lambda| only, so the iteration is capped instead of waiting for them.
 //
-// Status: written and compiled in round 1 after the GPU budget was spent -- NOT yet run on a GPU.  It is reachable
-// only through the environment switch and falls back to the block-Jacobi path when the iteration misbehaves.
-// COSMO_B200_PSD_SIGN=1 uses the hand-written symmetric-product kernel below; =2 swaps the products for cuBLAS
-// D/SGEMM (dlopen) followed by an elementwise epilogue -- a comparator for the product kernel, not the product.
+// Status: validated on B200 in round 2 (profiles/psd_sign_timing_r2_fp64fma.log).  Reachable only through the
+// environment switch; falls back to the block-Jacobi path when the iteration misbehaves.
+// COSMO_B200_PSD_SIGN=1 selects it: the same iteration as psd_tc.cuh with the products on the FP64 FMA pipe -- kept as
+// the comparator of the tensor-core path (measured on B200, round 2: N = 2000, 24-32 steps, 42-54 ms, 5e-14).
 //
 // Included from psd.cuh (after PsdConeDesc, svec_pos and bj_load8, before PsdBatch).
 #pragma once
-#include <dlfcn.h>
 
 namespace cosmo {
 
@@ -188,77 +187,6 @@ __global__ void __launch_bounds__(kBlock) sg_store_kernel(PsdConeDesc d, const T
   }
 }
 
-// ---- comparator backend: cuBLAS products + elementwise epilogue ------------------------------------------------
-struct CublasApi {
-  void* lib = nullptr;
-  void* handle = nullptr;
-  int (*Create)(void**) = nullptr;
-  int (*Destroy)(void*) = nullptr;
-  int (*SetStream)(void*, cudaStream_t) = nullptr;
-  int (*Dgemm)(void*, int, int, int, int, int, const double*, const double*, int, const double*, int, const double*, double*, int) = nullptr;
-  int (*Sgemm)(void*, int, int, int, int, int, const float*, const float*, int, const float*, int, const float*, float*, int) = nullptr;
-  bool load() {
-    if (handle) return true;
-    for (const char* name : {"libcublas.so.12", "libcublas.so"}) {
-      lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
-      if (lib) break;
-    }
-    if (!lib) return false;
-    Create = reinterpret_cast<decltype(Create)>(dlsym(lib, "cublasCreate_v2"));
-    Destroy = reinterpret_cast<decltype(Destroy)>(dlsym(lib, "cublasDestroy_v2"));
-    SetStream = reinterpret_cast<decltype(SetStream)>(dlsym(lib, "cublasSetStream_v2"));
-    Dgemm = reinterpret_cast<decltype(Dgemm)>(dlsym(lib, "cublasDgemm_v2"));
-    Sgemm = reinterpret_cast<decltype(Sgemm)>(dlsym(lib, "cublasSgemm_v2"));
-    if (!Create || !Destroy || !SetStream || !Dgemm || !Sgemm) return false;
-    return Create(&handle) == 0 && handle != nullptr;
-  }
-  ~CublasApi() { if (handle && Destroy) Destroy(handle); }
-  bool gemm(int N, const double* A, const double* B, double* C, cudaStream_t st) {
-    const double one = 1.0, zero = 0.0;
-    return SetStream(handle, st) == 0 && Dgemm(handle, 0, 0, N, N, N, &one, A, N, B, N, &zero, C, N) == 0;
-  }
-  bool gemm(int N, const float* A, const float* B, float* C, cudaStream_t st) {
-    const float one = 1.f, zero = 0.f;
-    return SetStream(handle, st) == 0 && Sgemm(handle, 0, 0, N, N, N, &one, A, N, B, N, &zero, C, N) == 0;
-  }
-};
-
-// the epilogues of sym_gemm_kernel applied to a full product C = A B that is already in memory
-template <typename T, int EPI>
-__global__ void __launch_bounds__(kBlock) sg_epilogue_kernel(int N, T* __restrict__ C, const T* __restrict__ A, const T* __restrict__ X,
-                                                             T* __restrict__ partial, const T* __restrict__ sc) {
-  __shared__ T red[kWarpsPerBlock][2];
-  const T inv_b = (EPI == SG_UPD) ? sc[2] : T(1), inv_b2 = (EPI == SG_UPD) ? sc[3] : T(1);
-  T dsum = T(0), fsum = T(0);
-  const long long total = (long long)N * N;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int i = (int)(e % N), j = (int)(e / N);
-    const T p = C[e];
-    if (EPI == SG_SQ) {
-      const T d = ((i == j) ? T(1) : T(0)) - p;
-      dsum += d * d;
-      fsum += p * p;
-    } else if (EPI == SG_UPD) {
-      C[e] = T(0.5) * inv_b * (T(3) * A[e] - inv_b2 * p);
-    } else if (EPI == SG_RES) {
-      const T d = p - X[e];
-      fsum += d * d;
-    }
-  }
-  if (EPI == SG_SQ || EPI == SG_RES) {
-    dsum = warp_sum(dsum);
-    fsum = warp_sum(fsum);
-    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = fsum; red[threadIdx.x >> 5][1] = dsum; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      T f = T(0), dd = T(0);
-      for (int w = 0; w < kWarpsPerBlock; ++w) { f += red[w][0]; dd += red[w][1]; }
-      partial[2 * blockIdx.x] = f;
-      partial[2 * blockIdx.x + 1] = dd;
-    }
-  }
-}
-
 // Host driver.  X (N x N symmetric) and its Frobenius partial sums come from psd_large_load_kernel; S0 is a second N x N
 // buffer of the caller.  Returns false when the iteration misbehaved (NaN) or memory ran out -- the caller then falls
 // back to the eigensolver.
@@ -269,15 +197,13 @@ struct PsdSign {
   T* S1_scratch = nullptr;
   int capN = 0;
   int last_steps = 0;
-  int backend = 1;     // 1: sym_gemm_kernel, 2: cuBLAS + epilogue kernel
-  CublasApi blas;
   ~PsdSign() {
     cudaFree(S1_d); cudaFree(U_d); cudaFree(sc_d); cudaFree(part_d);
     if (sc_h) cudaFreeHost(sc_h);
   }
   static bool enabled() {
     const char* e = getenv("COSMO_B200_PSD_SIGN");
-    return e && (e[0] == '1' || e[0] == '2');
+    return e && e[0] == '1';
   }
   bool ensure(int N) {
     if (N <= capN) return true;
@@ -301,29 +227,15 @@ struct PsdSign {
     ++launches;
     const int nt = (N + 127) / 128;
     const int ntiles = nt * (nt + 1) / 2;
-    {
-      const char* e = getenv("COSMO_B200_PSD_SIGN");
-      backend = (e && e[0] == '2') ? 2 : 1;
-      if (backend == 2 && !blas.load()) return false;
-    }
-    const int nparts = (backend == 2) ? g : ntiles;
+    const int nparts = ntiles;
     bool ok = true;
     // C = epi(A B); X is the third operand of SG_RES, sc the scalars of SG_UPD
     auto product = [&](int epi, const T* A, const T* B, const T* Xo, T* C) {
-      if (backend == 1) {
-        if (epi == SG_SQ) sym_gemm_kernel<T, SG_SQ><<<ntiles, kBlock, 0, st>>>(N, A, B, Xo, C, part_d, (const T*)nullptr);
-        else if (epi == SG_UPD) sym_gemm_kernel<T, SG_UPD><<<ntiles, kBlock, 0, st>>>(N, A, B, Xo, C, (T*)nullptr, sc_d);
-        else if (epi == SG_MUL) sym_gemm_kernel<T, SG_MUL><<<ntiles, kBlock, 0, st>>>(N, A, B, Xo, C, (T*)nullptr, (const T*)nullptr);
-        else sym_gemm_kernel<T, SG_RES><<<ntiles, kBlock, 0, st>>>(N, A, B, Xo, (T*)nullptr, part_d, (const T*)nullptr);
-        ++launches;
-      } else {
-        T* out = (epi == SG_RES) ? S1_scratch : C;       // SG_RES stores nothing: the product goes to a scratch matrix
-        ok = ok && blas.gemm(N, A, B, out, st);
-        if (epi == SG_SQ) sg_epilogue_kernel<T, SG_SQ><<<g, kBlock, 0, st>>>(N, out, A, Xo, part_d, (const T*)nullptr);
-        else if (epi == SG_UPD) sg_epilogue_kernel<T, SG_UPD><<<g, kBlock, 0, st>>>(N, out, A, Xo, (T*)nullptr, sc_d);
-        else if (epi == SG_RES) sg_epilogue_kernel<T, SG_RES><<<g, kBlock, 0, st>>>(N, out, A, Xo, part_d, (const T*)nullptr);
-        launches += 2;
-      }
+      if (epi == SG_SQ) sym_gemm_kernel<T, SG_SQ><<<ntiles, kBlock, 0, st>>>(N, A, B, Xo, C, part_d, (const T*)nullptr);
+      else if (epi == SG_UPD) sym_gemm_kernel<T, SG_UPD><<<ntiles, kBlock, 0, st>>>(N, A, B, Xo, C, (T*)nullptr, sc_d);
+      else if (epi == SG_MUL) sym_gemm_kernel<T, SG_MUL><<<ntiles, kBlock, 0, st>>>(N, A, B, Xo, C, (T*)nullptr, (const T*)nullptr);
+      else sym_gemm_kernel<T, SG_RES><<<ntiles, kBlock, 0, st>>>(N, A, B, Xo, (T*)nullptr, part_d, (const T*)nullptr);
+      ++launches;
     };
     const double tol = sizeof(T) == 8 ? 1e-7 : 3e-4;   // quadratic convergence: the step after delta < tol reaches ~delta^2
     const double rtol = sizeof(T) == 8 ? 5e-13 : 2e-5;  // accepted weighted residual |S^2 X - X|_F / |X|_F

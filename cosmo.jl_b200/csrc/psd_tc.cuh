@@ -1,0 +1,264 @@
+// psd_tc.cuh -- projection of a large symmetric matrix onto the PSD cone on the tensor cores.
+//
+// Replaces dsyevr + clamp + syrk of the reference (convexset.jl:163-189, 219-263) for cones with N > kPsdSmallMax:
+//
+//     Pi_+(X) = (X + sign(X) X) / 2,      sign(X) by the scaled Newton-Schulz iteration
+//     S <- gamma S;  S <- S (3 I - S^2) / 2,    gamma = alpha / u,
+//         u     = min(1, |S^2|_F^(1/2)) >= rho(S)        (rigorous, a by-product of the product S^2)
+//         alpha = (3 / (1 + l + l^2))^(1/2)              (minimax cubic for a spectrum in [l, 1]; l <- g(alpha l))
+//
+// Every step is two products of commuting symmetric matrices, evaluated by tc::OzakiGemm (int8 slices on tcgen05,
+// exact int32 accumulation in TMEM, fp64 Horner epilogue): Y = S S with fused |Y|_F^2 and |I - Y|_F^2, then
+// S' = c1 S + c0 (S Y).  The iteration keeps the sign of every eigenvalue because gamma rho(S) <= alpha < sqrt 3.
+// Eigenvalues that are numerically zero never reach +-1 and do not have to (they enter the projection with weight
+// |lambda|): once the unweighted measure delta = rms(1 - s_i^2) stalls, the weighted residual
+// |S (S X) - X|_F / |X|_F -- twice an upper bound of the projection error -- decides.
+// Anything unexpected (NaN, no convergence within the cap) returns false and the caller falls back to the
+// block-Jacobi eigensolver.
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace cosmo {
+
+// state[0..2] = coefficients of the update product, state[3] = l, state[4] = delta, state[5] = |Y|_F^2, state[6] = gamma
+template <int DUMMY = 0>
+__global__ void ns_coef_kernel(const double* __restrict__ partial, int ntiles, int N, double* __restrict__ state) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  double f = 0.0, d = 0.0;
+  for (int i = 0; i < ntiles; ++i) { f += partial[2 * i]; d += partial[2 * i + 1]; }
+  double l = state[3];
+  double gamma = 1.0;
+  if (!(f > 0.0)) {            // zero matrix (f == 0) or NaN: hand it to the host through delta
+    state[4] = (f == 0.0) ? 0.0 : f;
+  } else {
+    const double beta = sqrt(sqrt(f));                     // rho(S)^2 = rho(Y) <= |Y|_F
+    const double u = beta < 1.0 ? beta : 1.0;
+    const double alpha = sqrt(3.0 / (1.0 + l + l * l));
+    gamma = alpha / u;
+    const double y = alpha * l;
+    l = 0.5 * y * (3.0 - y * y);
+    if (l > 1.0) l = 1.0;
+    state[4] = (beta < 1.0) ? 2.0 : sqrt(d / (double)N);   // the measure is void while the bound still tightens
+  }
+  state[0] = -0.5 * gamma * gamma * gamma;
+  state[1] = 1.5 * gamma;
+  state[2] = 0.0;
+  state[3] = l;
+  state[5] = f;
+  state[6] = gamma;
+}
+
+// state[4] = |X - S W|_F / |X|_F
+template <int DUMMY = 0>
+__global__ void ns_residual_kernel(const double* __restrict__ partial, int ntiles, const double* __restrict__ x2, double* __restrict__ state) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  double r = 0.0;
+  for (int i = 0; i < ntiles; ++i) r += partial[2 * i + 1];
+  state[4] = (*x2 > 0.0) ? sqrt(r / *x2) : 0.0;
+}
+
+// S = X / |X|_F; x2[0] = |X|_F^2 (from the load kernel's partial sums)
+template <typename T>
+__global__ void __launch_bounds__(kBlock) ns_scale_kernel(int N, const T* __restrict__ X, const T* __restrict__ fro_partials, int nparts,
+                                                          T* __restrict__ S, double* __restrict__ x2) {
+  __shared__ double sc_s;
+  if (threadIdx.x == 0) {
+    double f = 0.0;
+    for (int i = 0; i < nparts; ++i) f += (double)fro_partials[i];
+    sc_s = (f > 0.0) ? 1.0 / sqrt(f) : 0.0;
+    if (blockIdx.x == 0) *x2 = f;
+  }
+  __syncthreads();
+  const double sc = sc_s;
+  const long long total = (long long)N * N;
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x)
+    S[k] = (T)((double)X[k] * sc);
+}
+
+// s[cone] = svec / square layout of the symmetric matrix P (already (X + sign(X) X) / 2)
+template <typename T>
+__global__ void __launch_bounds__(kBlock) ns_store_kernel(PsdConeDesc d, const T* __restrict__ P, T* __restrict__ s) {
+  const int N = d.N;
+  const T sqrt2 = T(1.41421356237309504880);
+  const long long total = (long long)N * N;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e % N), j = (int)(e / N);
+    if (i > j) continue;
+    const T v = P[e];
+    if (d.triangle) {
+      s[d.off + svec_pos(i, j)] = (i == j) ? v : sqrt2 * v;
+    } else {
+      s[d.off + (long long)j * N + i] = v;
+      s[d.off + (long long)i * N + j] = v;   // mirror, convexset.jl:316-318
+    }
+  }
+}
+
+// W = 2 P - X  (the candidate S X recovered from P = (X + S X) / 2)
+template <typename T>
+__global__ void __launch_bounds__(kBlock) ns_w_from_p_kernel(long long total, const T* __restrict__ P, const T* __restrict__ X, T* __restrict__ W) {
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x)
+    W[k] = T(2) * P[k] - X[k];
+}
+
+template <typename T>
+struct PsdTc {
+  tc::OzakiGemm<T> gemm;
+  tc::Sliced slS, slY, slX;
+  T *S1_d = nullptr, *U_d = nullptr;
+  double *state_d = nullptr, *partial_d = nullptr, *const_d = nullptr, *x2_d = nullptr;
+  double* state_h = nullptr;   // pinned
+  int capN = 0, shapeN = 0;
+  int last_steps = 0, last_checks = 0;
+  double last_delta = 0, last_resid = -1;
+  bool configured = false;
+  std::string err;
+
+  ~PsdTc() {
+    cudaFree(S1_d); cudaFree(U_d); cudaFree(state_d); cudaFree(partial_d); cudaFree(const_d); cudaFree(x2_d);
+    if (state_h) cudaFreeHost(state_h);
+  }
+  static int env_int(const char* name, int def) {
+    const char* e = getenv(name);
+    return (e && *e) ? atoi(e) : def;
+  }
+  static double env_double(const char* name, double def) {
+    const char* e = getenv(name);
+    return (e && *e) ? atof(e) : def;
+  }
+  // COSMO_B200_PSD_TC=0 switches the tensor-core path off (block Jacobi for every large cone)
+  static bool enabled() {
+    const char* e = getenv("COSMO_B200_PSD_TC");
+    return !(e && e[0] == '0');
+  }
+  static int min_n() { return env_int("COSMO_B200_PSD_TC_MIN_N", 192); }
+
+  bool ensure(int N, cudaStream_t st) {
+    if (!configured) {
+      const int k = env_int("COSMO_B200_TC_SLICES", sizeof(T) == 8 ? 7 : 4);
+      const int kstep = env_int("COSMO_B200_TC_KSTEP", 128);
+      const int gpb = env_int("COSMO_B200_TC_GPB", 1);
+      if (!gemm.configure(k, kstep, gpb, st)) { err = gemm.err; return false; }
+      bool ok = cudaMalloc(&state_d, 8 * sizeof(double)) == cudaSuccess && cudaMalloc(&const_d, 8 * sizeof(double)) == cudaSuccess &&
+                cudaMalloc(&x2_d, sizeof(double)) == cudaSuccess && cudaMallocHost(&state_h, 8 * sizeof(double)) == cudaSuccess;
+      if (!ok) { err = "PsdTc: cudaMalloc"; return false; }
+      const double c[8] = {1.0, 0.0, 0.0, 0.5, 0.5, 0.0, 0.0, 0.0};   // [0..2]: plain product, [3..5]: (X + S X) / 2
+      if (cudaMemcpyAsync(const_d, c, sizeof(c), cudaMemcpyHostToDevice, st) != cudaSuccess) { err = "PsdTc: copy"; return false; }
+      cudaStreamSynchronize(st);
+      configured = true;
+    }
+    if (N > capN) {
+      cudaFree(S1_d); cudaFree(U_d); cudaFree(partial_d);
+      S1_d = U_d = nullptr; partial_d = nullptr;
+      capN = 0;
+      const size_t nn = (size_t)N * N;
+      const int nt = (N + tc::kTile - 1) / tc::kTile;
+      bool ok = cudaMalloc(&S1_d, nn * sizeof(T)) == cudaSuccess && cudaMalloc(&U_d, nn * sizeof(T)) == cudaSuccess &&
+                cudaMalloc(&partial_d, (size_t)nt * (nt + 1) * sizeof(double)) == cudaSuccess;
+      const int Np = nt * tc::kTile;
+      ok = ok && slS.ensure(Np, gemm.k, st) && slY.ensure(Np, gemm.k, st) && slX.ensure(Np, gemm.k, st);
+      if (!ok) { err = "PsdTc: out of memory"; return false; }
+      capN = N;
+      shapeN = 0;
+    }
+    if (shapeN != N) {
+      if (!gemm.set_shape(N, st)) { err = gemm.err; return false; }
+      const int Np = gemm.Np;
+      // the padding rows / columns of the slices must be zero; the shape of the cone changed, so clear everything
+      if (!slS.clear(Np, gemm.k, st) || !slY.clear(Np, gemm.k, st) || !slX.clear(Np, gemm.k, st)) { err = "PsdTc: memset"; return false; }
+      slS.mapNp = slY.mapNp = slX.mapNp = 0;
+      shapeN = N;
+    }
+    return true;
+  }
+
+  // X_d: N x N symmetric (ld = N), fro_partials: partial sums of |X|_F^2, S0_d: scratch N x N.  Writes the projection
+  // in the layout of the cone into s_out.
+  bool project(const PsdConeDesc& d, const T* X_d, const T* fro_partials, int nfro, T* S0_d, T* s_out, cudaStream_t st,
+               long long& launches) {
+    const int N = d.N;
+    if (!ensure(N, st)) return false;
+    const int g = (int)std::min<long long>(((long long)N * N + kBlock - 1) / kBlock, kMaxGrid);
+    const int ntiles = gemm.ntiles;
+    const double l0 = env_double("COSMO_B200_TC_L0", 1e-7);
+    const double tol = sizeof(T) == 8 ? 1e-7 : 3e-4;     // quadratic convergence: the step after delta < tol reaches ~delta^2
+    const double rtol = sizeof(T) == 8 ? 5e-13 : 2e-5;   // accepted weighted residual
+    const int cap = env_int("COSMO_B200_TC_MAX_STEPS", 80);
+    bool ok = true;
+    ns_scale_kernel<T><<<g, kBlock, 0, st>>>(N, X_d, fro_partials, nfro, S0_d, x2_d);
+    {
+      double init[8] = {0, 0, 0, l0, 2.0, 0, 1.0, 0};
+      memcpy(state_h, init, sizeof(init));
+      ok = ok && cudaMemcpyAsync(state_d, state_h, 8 * sizeof(double), cudaMemcpyHostToDevice, st) == cudaSuccess;
+    }
+    ok = ok && gemm.slice(X_d, slX, st);
+    launches += 2;
+    T* S = S0_d;
+    T* Sn = S1_d;
+    double prev = 1e300, resid = -1.0, delta = 2.0;
+    int it = 0, next_check = -1, checks = 0;
+    bool have_P = false;
+    for (;;) {
+      ok = ok && gemm.slice(S, slS, st);
+      ok = ok && gemm.gemm(slS, slS, U_d, (const T*)nullptr, (const T*)nullptr, 1, const_d, partial_d, st);        // Y = S S
+      ns_coef_kernel<0><<<1, 32, 0, st>>>(partial_d, ntiles, N, state_d);
+      ok = ok && gemm.slice(U_d, slY, st);
+      ok = ok && gemm.gemm(slS, slY, Sn, S, (const T*)nullptr, 0, state_d, (double*)nullptr, st);                  // S' = c1 S + c0 S Y
+      launches += 5;
+      if (!ok) { err = gemm.err; return false; }
+      if (cudaMemcpyAsync(state_h, state_d, 8 * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) return false;
+      if (cudaStreamSynchronize(st) != cudaSuccess) { err = std::string("PsdTc: ") + cudaGetErrorString(cudaGetLastError()); return false; }
+      std::swap(S, Sn);
+      ++it;
+      delta = state_h[4];
+      if (!(delta == delta)) { err = "PsdTc: NaN"; return false; }
+      if (delta < tol) break;
+      // the minimax schedule has run out (l ~ 1) and delta stalls: a cluster of (numerically) zero eigenvalues
+      const bool schedule_done = state_h[3] > 0.999;
+      if (next_check < 0 && schedule_done) next_check = it + 1;
+      if ((next_check >= 0 && it >= next_check && delta > 0.9 * prev) || it >= cap) {
+        ok = ok && gemm.slice(S, slS, st);
+        ok = ok && gemm.gemm(slS, slX, U_d, X_d, (const T*)nullptr, 0, const_d + 3, (double*)nullptr, st);           // P = (X + S X) / 2
+        // residual of the candidate: W = S X = 2 P - X;  |S W - X| = |2 S P - S X - X| ... evaluated as S (2P - X) - X
+        // through one more product on the slices of W
+        ok = ok && residual_of_candidate(X_d, Sn, st, launches);
+        if (!ok) { if (err.empty()) err = gemm.err; return false; }
+        if (cudaMemcpyAsync(state_h, state_d, 8 * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) return false;
+        if (cudaStreamSynchronize(st) != cudaSuccess) return false;
+        resid = state_h[4];
+        ++checks;
+        if (!(resid == resid)) { err = "PsdTc: NaN"; return false; }
+        if (resid < rtol || (it >= cap && resid < 1e3 * rtol)) { have_P = true; break; }
+        if (it >= cap) { err = "PsdTc: no convergence"; return false; }
+        next_check = it + 4;
+      }
+      prev = delta;
+    }
+    last_steps = it; last_checks = checks; last_delta = delta; last_resid = resid;
+    if (!have_P) {
+      ok = ok && gemm.slice(S, slS, st);
+      ok = ok && gemm.gemm(slS, slX, U_d, X_d, (const T*)nullptr, 0, const_d + 3, (double*)nullptr, st);
+      launches += 2;
+      if (!ok) { err = gemm.err; return false; }
+    }
+    ns_store_kernel<T><<<g, kBlock, 0, st>>>(d, U_d, s_out);
+    ++launches;
+    if (getenv("COSMO_B200_PSD_DEBUG"))
+      fprintf(stderr, "[psd-tc] N=%d steps=%d checks=%d delta=%g resid=%g l=%g\n", N, it, checks, delta, resid, state_h[3]);
+    return cudaGetLastError() == cudaSuccess;
+  }
+
+  // state[4] <- |S W - X|_F / |X|_F with W = 2 P - X, P in U_d, S sliced in slS.  Wbuf: scratch N x N.
+  bool residual_of_candidate(const T* X_d, T* Wbuf, cudaStream_t st, long long& launches) {
+    const int N = gemm.N;
+    const int g = (int)std::min<long long>(((long long)N * N + kBlock - 1) / kBlock, kMaxGrid);
+    ns_w_from_p_kernel<T><<<g, kBlock, 0, st>>>((long long)N * N, U_d, X_d, Wbuf);
+    bool ok = gemm.slice(Wbuf, slY, st);
+    ok = ok && gemm.gemm(slS, slY, (T*)nullptr, (const T*)nullptr, X_d, 0, const_d, partial_d, st);
+    ns_residual_kernel<0><<<1, 32, 0, st>>>(partial_d, gemm.ntiles, x2_d, state_d);
+    launches += 4;
+    return ok;
+  }
+};
+
+}  // namespace cosmo

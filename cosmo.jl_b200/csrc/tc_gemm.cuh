@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(kThreads, 1) ozaki_gemm_kernel(const __grid_co
       const int N = args.N;
       if (gm < N) {
         const double sa = args.scaleA[gm];
-#pragma unroll 4
+#pragma unroll
         for (int j = 0; j < 64; ++j) {
           const int gn = gn0 + j;
           if (gn >= N || gm > gn) continue;               // upper triangle only; the mirror is written below

@@ -84,6 +84,7 @@ EXPORTS = [
     "cosmo_b200_update_rho", "cosmo_b200_reset", "cosmo_b200_solve", "cosmo_b200_project", "cosmo_b200_kkt_solve",
     "cosmo_b200_residuals", "cosmo_b200_spmv", "cosmo_b200_spmv_bench", "cosmo_b200_get_rho_vec", "cosmo_b200_get_w",
     "cosmo_b200_comm_unique_id", "cosmo_b200_comm_init", "cosmo_b200_comm_p2p_export", "cosmo_b200_comm_p2p_attach",
+    "cosmo_b200_tc_gemm_test",
 ]
 
 _lib = None
@@ -129,6 +130,8 @@ def load_library(rebuild_if_stale=True):
     lib.cosmo_b200_comm_init.argtypes = [vp, C.c_int32, C.c_int32, vp]
     lib.cosmo_b200_comm_p2p_export.argtypes = [vp, vp]
     lib.cosmo_b200_comm_p2p_attach.argtypes = [vp, vp, C.c_int32]
+    lib.cosmo_b200_tc_gemm_test.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, C.c_int32,
+                                            C.POINTER(C.c_double), C.POINTER(C.c_double)]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("cosmo_b200_destroy", "cosmo_b200_last_error"):
@@ -362,3 +365,21 @@ class Engine:
         out = np.empty(self.n + self.m, dtype=self.dtype)
         self._check(self._lib.cosmo_b200_get_w(self._h, _ptr(out)))
         return out
+
+
+def tc_gemm(A, B, slices=7, kstep=128, gpb=1, reps=0):
+    """C = A @ B for symmetric commuting fp64 matrices through the int8-sliced tcgen05 product kernel
+    (diagnostic entry `cosmo_b200_tc_gemm_test`).  Returns (C, ms_per_product, (|C|_F^2, |I - C|_F^2))."""
+    lib = load_library()
+    A = np.asfortranarray(A, dtype=np.float64)
+    B = np.asfortranarray(B, dtype=np.float64)
+    N = A.shape[0]
+    assert A.shape == (N, N) and B.shape == (N, N)
+    Cm = np.zeros((N, N), dtype=np.float64, order="F")
+    ms = C.c_double(0.0)
+    fr = (C.c_double * 2)()
+    rc = lib.cosmo_b200_tc_gemm_test(N, slices, kstep, gpb, A.ctypes.data, B.ctypes.data, Cm.ctypes.data, reps,
+                                     C.byref(ms), fr)
+    if rc != 0:
+        raise EngineError(rc, (lib.cosmo_b200_last_error(None) or b"").decode())
+    return Cm, ms.value, (fr[0], fr[1])

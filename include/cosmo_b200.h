@@ -243,6 +243,15 @@ int cosmo_b200_comm_init(cosmo_b200_handle* h, int32_t nranks, int32_t rank, con
 int cosmo_b200_comm_p2p_export(cosmo_b200_handle* h, void* blob128);
 int cosmo_b200_comm_p2p_attach(cosmo_b200_handle* h, const void* blobs, int32_t nranks);
 
+/* ---- diagnostics ---------------------------------------------------------- */
+/* The product kernel of the large-cone PSD projection on its own: C = A B for symmetric, commuting N x N fp64
+   matrices (column-major) through `k` int8 slices on tcgen05 (csrc/tc_gemm.cuh; the reference's counterpart is the
+   BLAS-3 part of project!(::PsdCone), convexset.jl:244-260).  kstep in {32, 64, 128} bytes of K per stage tile,
+   gpb in {1, 2, 4} slice groups per TMEM batch.  frob2 = {|C|_F^2, |I - C|_F^2} from the fused reductions.
+   No handle: uses the current device.  Errors through cosmo_b200_last_error(NULL). */
+int cosmo_b200_tc_gemm_test(int32_t N, int32_t k, int32_t kstep, int32_t gpb, const double* A, const double* B, double* C,
+                            int32_t reps, double* ms_per_product, double* frob2);
+
 #ifdef __cplusplus
 }
 #endif
