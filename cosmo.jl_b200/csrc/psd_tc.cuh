@@ -135,10 +135,8 @@ struct PsdTc {
 
   bool ensure(int N, cudaStream_t st) {
     if (!configured) {
-      const int k = env_int("COSMO_B200_TC_SLICES", sizeof(T) == 8 ? 7 : 4);
-      const int kstep = env_int("COSMO_B200_TC_KSTEP", 128);
-      const int gpb = env_int("COSMO_B200_TC_GPB", 1);
-      if (!gemm.configure(k, kstep, gpb, st)) { err = gemm.err; return false; }
+      const int k = env_int("COSMO_B200_TC_SLICES", sizeof(T) == 8 ? 8 : 4);
+      if (!gemm.configure(k, st)) { err = gemm.err; return false; }
       bool ok = cudaMalloc(&state_d, 8 * sizeof(double)) == cudaSuccess && cudaMalloc(&const_d, 8 * sizeof(double)) == cudaSuccess &&
                 cudaMalloc(&x2_d, sizeof(double)) == cudaSuccess && cudaMallocHost(&state_h, 8 * sizeof(double)) == cudaSuccess;
       if (!ok) { err = "PsdTc: cudaMalloc"; return false; }
@@ -156,7 +154,7 @@ struct PsdTc {
       bool ok = cudaMalloc(&S1_d, nn * sizeof(T)) == cudaSuccess && cudaMalloc(&U_d, nn * sizeof(T)) == cudaSuccess &&
                 cudaMalloc(&partial_d, (size_t)nt * (nt + 1) * sizeof(double)) == cudaSuccess;
       const int Np = nt * tc::kTile;
-      ok = ok && slS.ensure(Np, gemm.k, st) && slY.ensure(Np, gemm.k, st) && slX.ensure(Np, gemm.k, st);
+      ok = ok && slS.ensure(Np) && slY.ensure(Np) && slX.ensure(Np);
       if (!ok) { err = "PsdTc: out of memory"; return false; }
       capN = N;
       shapeN = 0;
@@ -165,8 +163,7 @@ struct PsdTc {
       if (!gemm.set_shape(N, st)) { err = gemm.err; return false; }
       const int Np = gemm.Np;
       // the padding rows / columns of the slices must be zero; the shape of the cone changed, so clear everything
-      if (!slS.clear(Np, gemm.k, st) || !slY.clear(Np, gemm.k, st) || !slX.clear(Np, gemm.k, st)) { err = "PsdTc: memset"; return false; }
-      slS.mapNp = slY.mapNp = slX.mapNp = 0;
+      if (!slS.clear(Np, st) || !slY.clear(Np, st) || !slX.clear(Np, st)) { err = "PsdTc: memset"; return false; }
       shapeN = N;
     }
     return true;

@@ -8,23 +8,26 @@
 //     M[r, :] = 2^(e_r - 6) * sum_p D_p[r, :] * 128^-(p-1),   D_p int8 digits in [-64, 64]   (slice_rows_kernel)
 //     (A B)[m, n] = sA[m] sB[n] * sum_s 128^-(s-2) G_s[m, n],  G_s = sum_{p+q=s} A_p B_q^T     (int32, EXACT)
 //
-// G_s is accumulated by tcgen05.mma.kind::i8 in TMEM (|G_s| <= 8 * K * 64^2 < 2^31 for K <= 65536), the sum over s is
-// a Horner recurrence in fp64 registers of the epilogue warps (acc <- acc / 128 + G_s, least significant group first),
-// so the only rounding errors are the truncation of the slices (2^-7k relative to the row maximum) and one fp64
-// rounding per group.  k = 7 slices reproduce dgemm to ~1e-15 relative to |A|_row |B|_col.
+// G_s is accumulated by tcgen05.mma.kind::i8 in TMEM (|G_s| <= 8 * K * 64^2 < 2^31 for K <= 65536), the sum over s
+// runs in fp64 registers of the epilogue warps (acc += 128^-(s-2) G_s, least significant groups first), so the only
+// rounding errors are the truncation of the slices (2^-7k relative to the row maximum) and one fp64 rounding per group.
+// Measured against numpy dgemm (N = 2000, profiles/tc_gemm_bringup_r2_*.log): k = 8 -> 1e-15, k = 7 -> 1e-13 relative
+// to |A| |B|.
 //
 // Kernel anatomy (one persistent CTA per SM, 10 warps):
-//   warp 0      TMA producer: cp.async.bulk.tensor (3-d maps over the [slice][row][k] int8 arrays, 128 x KSTEP byte
-//               boxes, hardware swizzle) into a ring of shared-memory stages, mbarrier complete_tx
-//   warp 1      MMA issuer: one elected lane walks the pass list of the plan and issues tcgen05.mma (M = N = 128,
-//               K = 32 bytes) from shared-memory descriptors into up to four 128-column TMEM accumulators;
-//               tcgen05.commit releases the stage / publishes the accumulators
-//   warps 2..9  epilogue: tcgen05.ld 32x32b, int32 -> fp64 Horner accumulation, scaling, fused
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d, 128-row x 128-byte boxes (= the tiles of 4 slices for one K step
+//               of 32, see the layout note at MmaOp), 128-byte hardware swizzle, into a ring of 64 KB stages
+//               {A slices 0-3, A 4-7, B 0-3, B 4-7}, mbarrier complete_tx
+//   warp 1      MMA issuer: one elected lane walks the pass list of the plan and issues tcgen05.mma.kind::i8 (M = N = 128,
+//               K = 32) from shared-memory descriptors into four 128-column TMEM accumulators -- up to 26 slice-pair
+//               products per stage; tcgen05.commit releases the stage / publishes the accumulators
+//   warps 2..9  epilogue: tcgen05.ld 32x32b, exact int32 -> fp64 accumulation over the groups, scaling, fused
 //               out = c0 * (A B) + c1 * D + c2 * I, mirrored store (the product of commuting symmetric matrices is
 //               symmetric: only tiles of the upper triangle are computed) and two fused Frobenius reductions.
-// The "plan" (built on the host, copied to shared memory) says which slices a stage holds and which (A slice, B slice,
-// accumulator) products are issued per stage, so that operand tiles are re-used across the slice pairs of several
-// groups while they sit in shared memory (L2 -> SM traffic is what bounds an int8 product of this shape).
+// The "plan" (built on the host, copied to shared memory) lists the (A slice, B slice, accumulator) products of a pass.
+// Operand tiles are re-used by all slice pairs of four groups while they sit in shared memory: L2 -> SM traffic is
+// what bounds an int8 product of this shape (the first version, one slice pair per stage, ran at 11 TB/s of L2 reads
+// and 28 % of the int8 peak -- profiles/tc_gemm_bringup_r2_v1.log).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -37,84 +40,67 @@
 namespace cosmo {
 namespace tc {
 
-constexpr int kTile = 128;         // output tile side = rows of one operand tile = UMMA M = UMMA N
-constexpr int kMaxSlices = 8;
+constexpr int kTile = 128;         // output tile side = rows of one operand box = UMMA M = UMMA N
+constexpr int kSlices = 8;         // slices stored per matrix (unused ones are zero)
+constexpr int kKStep = 32;         // K per stage = K of one tcgen05.mma.kind::i8
+constexpr int kBoxBytes = kTile * 128;   // one TMA box: 128 rows x (4 slices x 32 K-bytes), 128-byte swizzle
+constexpr int kStageBytes = 4 * kBoxBytes;   // A slices 0-3, A slices 4-7, B slices 0-3, B slices 4-7
+constexpr int kStages = 3;
 constexpr int kMaxOps = 32;        // products per stage
-constexpr int kMaxPasses = 36;
+constexpr int kMaxPasses = 4;
 constexpr int kThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kEpiWarps = 8;
-constexpr int kSmemBudget = 200 * 1024;   // ring of operand stages (the rest: plan, barriers, reduction scratch)
 
-struct MmaOp { uint8_t a, b, acc, first; };   // stage slot of the A / B tile, accumulator 0..3, 1: first write of acc in its batch
+// Layout of a sliced operand: int8 [row][K / 32][slice 0..7][32], i.e. a row of Np * 8 bytes in which the 8 slices of
+// the same 32 K-values are adjacent.  One 128-byte TMA row therefore carries 4 slices of one K step, a 128 x 128-byte
+// box is the operand tile of 4 slices at once, and the tile of slice j inside the box is addressed like the j-th
+// K sub-step of an ordinary 128-byte-swizzled K-major tile (descriptor start address + 32 j bytes).
+struct MmaOp { uint16_t a_off, b_off; uint8_t acc, first, pad0, pad1; };   // descriptor offsets (16-byte units) inside a stage
 struct Pass {
-  uint8_t nA, nB, nops, flags;     // flags: 1 = first pass of a batch (wait for the TMEM slots), 2 = last (publish them)
-  uint8_t slot_mask, ngroups, pad0, pad1;   // TMEM halves used by the batch: bit 0 -> accumulators 0,1; bit 1 -> 2,3
-  uint8_t sliceA[kMaxSlices], sliceB[kMaxSlices];
-  uint8_t acc_order[4];            // last pass only: accumulators of the batch in Horner order (descending s)
+  uint8_t box_mask, nops, ngroups, pad;    // box_mask: bit 0 A slices 0-3, 1 A slices 4-7, 2 B slices 0-3, 3 B slices 4-7
+  uint8_t acc_order[4];                    // accumulators in the order the epilogue folds them
+  double group_scale[4];                   // 128^-(s-2) of each of them
   MmaOp ops[kMaxOps];
 };
 struct Plan {
-  int npasses, stage_tiles, nstages, kstep;
+  int npasses, k;
   Pass p[kMaxPasses];
 };
 
-// Host: the pass list for k slices.  `gpb` groups per batch (1, 2 or 4): the accumulators of a batch live in TMEM
-// together, so a stage's tiles serve the slice pairs of all of them.
-inline bool make_plan(Plan& pl, int k, int gpb, int kstep, std::string& err) {
+// Host: the pass list for k slices.  A pass owns the four TMEM accumulators: it covers up to four groups s = p + q and
+// issues every slice pair of them per K step from one stage, so an operand tile fetched once serves up to 26 products.
+inline bool make_plan(Plan& pl, int k, std::string& err) {
   memset(&pl, 0, sizeof(pl));
-  if (k < 1 || k > kMaxSlices || (gpb != 1 && gpb != 2 && gpb != 4) || (kstep != 32 && kstep != 64 && kstep != 128)) {
-    err = "tc::make_plan: bad parameters";
-    return false;
-  }
-  const int tile_bytes = kTile * kstep;
-  const int max_tiles = std::min(2 * kMaxSlices, kSmemBudget / (2 * tile_bytes));   // at least two stages
-  pl.kstep = kstep;
-  int stage_tiles = 0, batch = 0;
-  for (int s_hi = k + 1; s_hi >= 2; s_hi -= gpb, ++batch) {
-    const int ng = std::min(gpb, s_hi - 1);
-    const int slot_mask = (gpb == 4) ? 3 : (1 << (batch & 1));
-    const int acc0 = (gpb == 4) ? 0 : 2 * (batch & 1);
-    // pairs of the batch, ordered by A slice so that a pass holds few A tiles and many B tiles
-    struct Pr { int p, q, acc; };
-    std::vector<Pr> prs;
-    for (int p = 1; p <= k; ++p)
-      for (int g = 0; g < ng; ++g) {
-        const int s = s_hi - g, q = s - p;
-        if (q >= 1 && q <= k) prs.push_back({p, q, acc0 + g});
-      }
+  if (k < 1 || k > kSlices) { err = "tc::make_plan: 1 <= slices <= 8"; return false; }
+  pl.k = k;
+  for (int s_hi = k + 1; s_hi >= 2; s_hi -= 4) {
+    if (pl.npasses >= kMaxPasses) { err = "tc::make_plan: too many passes"; return false; }
+    Pass& ps = pl.p[pl.npasses++];
+    const int ng = std::min(4, s_hi - 1);
+    ps.ngroups = (uint8_t)ng;
     bool first_write[4] = {true, true, true, true};
-    size_t i = 0;
-    bool first_pass = true;
-    while (i < prs.size()) {
-      if (pl.npasses >= kMaxPasses) { err = "tc::make_plan: too many passes"; return false; }
-      Pass& ps = pl.p[pl.npasses++];
-      ps.flags = first_pass ? 1 : 0;
-      first_pass = false;
-      ps.slot_mask = (uint8_t)slot_mask;
-      int ia[kMaxSlices + 1], ib[kMaxSlices + 1];
-      for (int t = 0; t <= kMaxSlices; ++t) ia[t] = ib[t] = -1;
-      while (i < prs.size() && ps.nops < kMaxOps) {
-        const Pr& pr = prs[i];
-        const int needA = ia[pr.p] < 0, needB = ib[pr.q] < 0;
-        if (ps.nA + ps.nB + needA + needB > max_tiles) break;
-        if (needA) { ia[pr.p] = ps.nA; ps.sliceA[ps.nA++] = (uint8_t)(pr.p - 1); }
-        if (needB) { ib[pr.q] = ps.nB; ps.sliceB[ps.nB++] = (uint8_t)(pr.q - 1); }
-        ps.ops[ps.nops++] = MmaOp{(uint8_t)ia[pr.p], (uint8_t)ib[pr.q], (uint8_t)pr.acc, (uint8_t)(first_write[pr.acc] ? 1 : 0)};
-        first_write[pr.acc] = false;
-        ++i;
-      }
-      if (ps.nops == 0) { err = "tc::make_plan: stage too small"; return false; }
-      stage_tiles = std::max(stage_tiles, (int)ps.nA + ps.nB);
-      if (i == prs.size()) {
-        ps.flags |= 2;
-        ps.ngroups = (uint8_t)ng;
-        for (int g = 0; g < ng; ++g) ps.acc_order[g] = (uint8_t)(acc0 + g);   // s_hi first: least significant group
-      }
+    for (int g = 0; g < ng; ++g) {
+      ps.acc_order[g] = (uint8_t)g;
+      ps.group_scale[g] = std::ldexp(1.0, -7 * (s_hi - g - 2));
     }
+    for (int p = 1; p <= k; ++p)           // ordered by A slice: consecutive products share the A tile
+      for (int g = 0; g < ng; ++g) {
+        const int q = s_hi - g - p;
+        if (q < 1 || q > k) continue;
+        if (ps.nops >= kMaxOps) { err = "tc::make_plan: too many products per stage"; return false; }
+        const int ja = p - 1, jb = q - 1;
+        ps.box_mask |= (uint8_t)(1 << (ja / 4));
+        ps.box_mask |= (uint8_t)(4 << (jb / 4));
+        MmaOp op;
+        op.a_off = (uint16_t)(((ja / 4) * kBoxBytes + (ja % 4) * 32) >> 4);
+        op.b_off = (uint16_t)(((2 + jb / 4) * kBoxBytes + (jb % 4) * 32) >> 4);
+        op.acc = (uint8_t)g;
+        op.first = first_write[g] ? 1 : 0;
+        op.pad0 = op.pad1 = 0;
+        first_write[g] = false;
+        ps.ops[ps.nops++] = op;
+      }
   }
-  pl.stage_tiles = stage_tiles;
-  pl.nstages = std::min(8, kSmemBudget / (stage_tiles * tile_bytes));
-  if (pl.nstages < 2) { err = "tc::make_plan: fewer than two stages fit"; return false; }
   return true;
 }
 
@@ -141,10 +127,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "LAB_DONE:\n\t}\n" ::"r"(smem_u32(bar)), "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -157,17 +143,13 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint6
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate));
 }
-// shared-memory matrix descriptor, K-major tile of 128 rows x KSTEP bytes written by TMA with a KSTEP-byte swizzle
-// (atoms of 8 rows x KSTEP bytes, stride between atoms along M/N = 8 * KSTEP)
-template <int KSTEP>
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
-  constexpr uint64_t layout = KSTEP == 128 ? 2 : (KSTEP == 64 ? 4 : 6);   // SWIZZLE_128B / 64B / 32B
-  constexpr uint64_t sbo = (8 * KSTEP) >> 4;
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (sbo << 32) | (1ull << 46) | (layout << 61);
-}
+// shared-memory matrix descriptor of a K-major operand tile inside a 128-row x 128-byte box written by TMA with the
+// 128-byte swizzle (atoms of 8 rows x 128 bytes: stride between atoms along M / N = 1024 bytes); `saddr16` is the
+// shared-memory byte address >> 4 of the first row + 32 * (slice within the box)
+constexpr uint64_t kDescHi = ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);   // SBO, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr16) { return kDescHi | (uint64_t)(saddr16 & 0x3FFFu); }
 // instruction descriptor: S32 accumulate, signed 8-bit A and B, both K-major, N = 128, M = 128
 constexpr uint32_t kIdescI8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTile >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
 
@@ -182,9 +164,14 @@ constexpr uint32_t kIdescI8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(k
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                        \
       : "r"(taddr))
 
+// (double)v for an int32 v without the conversion unit: 2^52 + 2^31 + v is exactly representable, its bit pattern is
+// {0x43300000, v ^ 0x80000000}
+__device__ __forceinline__ double biased_double(uint32_t v) { return __hiloint2double(0x43300000, (int)(v ^ 0x80000000u)); }
+constexpr double kBias = 4503599627370496.0 + 2147483648.0;
+
 // ---------------------------------------------------------------------------------------------------------------
 // Slicing: one CTA per row.  scale[r] = 2^(e_r - 6) with 2^e_r > max |M[r, :]|; digits by round-to-nearest so that
-// every digit is in [-64, 64]; all operations are exact in fp64.
+// every digit is in [-64, 64]; all operations are exact in fp64.  Output layout: see MmaOp above.
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) slice_rows_kernel(const T* __restrict__ M, int N, int Np, int k, int8_t* __restrict__ slices,
@@ -203,11 +190,12 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const T* __restrict__ M
   if (mx > 0.0 && mx < 1.0e300) frexp(mx, &e);   // mx = f 2^e, f in [0.5, 1)  =>  |x| < 2^e
   if (threadIdx.x == 0) scale[r] = ldexp(1.0, e - 6);
   const double inv = ldexp(1.0, 6 - e);
-  const size_t plane = (size_t)Np * Np;
+  int8_t* out_row = slices + (size_t)r * Np * kSlices;
   for (int c0 = threadIdx.x * 8; c0 < N; c0 += blockDim.x * 8) {
     double t[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) t[j] = (c0 + j < N) ? (double)row[c0 + j] * inv : 0.0;
+    int8_t* dst = out_row + (size_t)(c0 >> 5) * (kSlices * 32) + (c0 & 31);
     for (int p = 0; p < k; ++p) {
       uint32_t lo = 0, hi = 0;
 #pragma unroll
@@ -217,7 +205,7 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const T* __restrict__ M
         const uint32_t b = (uint32_t)(uint8_t)(int8_t)(int)d;
         if (j < 4) lo |= b << (8 * j); else hi |= b << (8 * (j - 4));
       }
-      *reinterpret_cast<uint2*>(slices + (size_t)p * plane + (size_t)r * Np + c0) = make_uint2(lo, hi);
+      *reinterpret_cast<uint2*>(dst + p * 32) = make_uint2(lo, hi);
     }
   }
 }
@@ -239,16 +227,14 @@ struct GemmArgs {
   double* partial;                   // 2 per tile: sum w out^2, sum w (E - out)^2   (w: 1 on the diagonal, 2 above it)
 };
 
-template <typename T, int KSTEP>
+template <typename T>
 __global__ void __launch_bounds__(kThreads, 1) ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmapA,
                                                                  const __grid_constant__ CUtensorMap tmapB,
                                                                  const Plan* __restrict__ plan_g, const GemmArgs<T> args) {
-  constexpr int kTileBytes = kTile * KSTEP;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [ring of stages (1024-aligned)] [plan] [barriers] [tmem base] [reduction scratch]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ Plan plan;
-  __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2];
+  __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], tfull_bar, tempty_bar;
   __shared__ uint32_t tmem_base_s;
   __shared__ double red[kEpiWarps][2];
 
@@ -258,14 +244,10 @@ __global__ void __launch_bounds__(kThreads, 1) ozaki_gemm_kernel(const __grid_co
     uint32_t* dst = reinterpret_cast<uint32_t*>(&plan);
     for (int i = threadIdx.x; i < (int)(sizeof(Plan) / 4); i += blockDim.x) dst[i] = src[i];
   }
-  __syncthreads();
-  const int nstages = plan.nstages;
-  const int stage_bytes = plan.stage_tiles * kTileBytes;
-  const int nk = args.Np / KSTEP;
-
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < nstages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kEpiWarps); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&tfull_bar, 1);
+    mbar_init(&tempty_bar, kEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // the allocating warp also frees
@@ -276,6 +258,8 @@ __global__ void __launch_bounds__(kThreads, 1) ozaki_gemm_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  const int nk = args.Np / kKStep;
+  const int npasses = plan.npasses;
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -285,17 +269,19 @@ __global__ void __launch_bounds__(kThreads, 1) ozaki_gemm_kernel(const __grid_co
       for (int t = blockIdx.x; t < args.ntiles; t += gridDim.x) {
         const int2 tl = args.tiles[t];
         const int m0 = tl.x * kTile, n0 = tl.y * kTile;
-        for (int pi = 0; pi < plan.npasses; ++pi) {
-          const Pass& ps = plan.p[pi];
-          const uint32_t bytes = (uint32_t)(ps.nA + ps.nB) * kTileBytes;
+        for (int pi = 0; pi < npasses; ++pi) {
+          const uint32_t mask = plan.p[pi].box_mask;
+          const uint32_t bytes = (uint32_t)__popc(mask) * kBoxBytes;
           for (int ks = 0; ks < nk; ++ks) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             mbar_expect_tx(&full_bar[stage], bytes);
-            uint8_t* dst = smem + (size_t)stage * stage_bytes;
-            for (int i = 0; i < ps.nA; ++i) tma_load_3d(dst + i * kTileBytes, &tmapA, &full_bar[stage], ks * KSTEP, m0, ps.sliceA[i]);
-            for (int i = 0; i < ps.nB; ++i)
-              tma_load_3d(dst + (ps.nA + i) * kTileBytes, &tmapB, &full_bar[stage], ks * KSTEP, n0, ps.sliceB[i]);
-            if (++stage == nstages) { stage = 0; phase ^= 1; }
+            const uint32_t dst = smem_u32(smem) + (uint32_t)stage * kStageBytes;
+            const int c0 = ks * (kSlices * 32);
+            if (mask & 1) tma_load_2d(dst, &tmapA, &full_bar[stage], c0, m0);
+            if (mask & 2) tma_load_2d(dst + kBoxBytes, &tmapA, &full_bar[stage], c0 + 128, m0);
+            if (mask & 4) tma_load_2d(dst + 2 * kBoxBytes, &tmapB, &full_bar[stage], c0, n0);
+            if (mask & 8) tma_load_2d(dst + 3 * kBoxBytes, &tmapB, &full_bar[stage], c0 + 128, n0);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -304,35 +290,28 @@ __global__ void __launch_bounds__(kThreads, 1) ozaki_gemm_kernel(const __grid_co
     // ===== MMA issuer =====
     if (lane == 0) {
       int stage = 0;
-      uint32_t phase = 0, tphase[2] = {0, 0};
+      uint32_t phase = 0, tphase = 0;
       for (int t = blockIdx.x; t < args.ntiles; t += gridDim.x) {
-        for (int pi = 0; pi < plan.npasses; ++pi) {
+        for (int pi = 0; pi < npasses; ++pi) {
           const Pass& ps = plan.p[pi];
-          if (ps.flags & 1) {
-            for (int h = 0; h < 2; ++h)
-              if (ps.slot_mask & (1 << h)) mbar_wait(&tempty_bar[h], tphase[h] ^ 1);
-            tc_fence_after();
-          }
+          const int nops = ps.nops;
+          mbar_wait(&tempty_bar, tphase ^ 1);      // the epilogue has drained the accumulators of the previous pass
+          tc_fence_after();
           for (int ks = 0; ks < nk; ++ks) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            const uint32_t sbase = smem_u32(smem + (size_t)stage * stage_bytes);
-            for (int o = 0; o < ps.nops; ++o) {
+            const uint32_t sbase16 = (smem_u32(smem) + (uint32_t)stage * kStageBytes) >> 4;
+#pragma unroll 2
+            for (int o = 0; o < nops; ++o) {
               const MmaOp op = ps.ops[o];
-              const uint64_t ad = smem_desc<KSTEP>(sbase + op.a * kTileBytes);
-              const uint64_t bd = smem_desc<KSTEP>(sbase + (ps.nA + op.b) * kTileBytes);
-              const uint32_t d = tmem_base + (uint32_t)op.acc * kTile;
-#pragma unroll
-              for (int kk = 0; kk < KSTEP / 32; ++kk)
-                tc_mma_i8(d, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), kIdescI8, (ks | kk | (op.first ^ 1)) ? 1u : 0u);
+              tc_mma_i8(tmem_base + (uint32_t)op.acc * kTile, smem_desc(sbase16 + op.a_off), smem_desc(sbase16 + op.b_off),
+                        kIdescI8, (ks | (op.first ^ 1)) ? 1u : 0u);
             }
             tc_commit(&empty_bar[stage]);
-            if (++stage == nstages) { stage = 0; phase ^= 1; }
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
-          if (ps.flags & 2) {
-            for (int h = 0; h < 2; ++h)
-              if (ps.slot_mask & (1 << h)) { tc_commit(&tfull_bar[h]); tphase[h] ^= 1; }
-          }
+          tc_commit(&tfull_bar);
+          tphase ^= 1;
         }
       }
     }
@@ -342,7 +321,7 @@ __global__ void __launch_bounds__(kThreads, 1) ozaki_gemm_kernel(const __grid_co
     const int quad = warp & 3;            // TMEM lanes [32 quad, 32 quad + 32) are the ones this warp may read
     const int half = ew >> 2;             // columns [64 half, 64 half + 64) of the tile
     const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 64);
-    uint32_t tphase[2] = {0, 0};
+    uint32_t tphase = 0;
     const double c0 = args.coef[0], c1 = args.coef[1], c2 = args.coef[2];
     for (int t = blockIdx.x; t < args.ntiles; t += gridDim.x) {
       const int2 tl = args.tiles[t];
@@ -351,28 +330,28 @@ __global__ void __launch_bounds__(kThreads, 1) ozaki_gemm_kernel(const __grid_co
       double acc[64];
 #pragma unroll
       for (int j = 0; j < 64; ++j) acc[j] = 0.0;
-      for (int pi = 0; pi < plan.npasses; ++pi) {
+      for (int pi = 0; pi < npasses; ++pi) {
         const Pass& ps = plan.p[pi];
-        if (!(ps.flags & 2)) continue;
-        for (int h = 0; h < 2; ++h)
-          if (ps.slot_mask & (1 << h)) { mbar_wait(&tfull_bar[h], tphase[h]); tphase[h] ^= 1; }
+        mbar_wait(&tfull_bar, tphase);
+        tphase ^= 1;
         tc_fence_after();
-        for (int g = 0; g < ps.ngroups; ++g) {
+        const int ng = ps.ngroups;
+        for (int g = 0; g < ng; ++g) {
           const uint32_t ta = tlane + (uint32_t)ps.acc_order[g] * kTile;
+          const double sc = ps.group_scale[g];
+          const double nb = -kBias * sc;
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             uint32_t v[32];
             COSMO_TC_LD32(ta + c * 32, v);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[c * 32 + j] = fma(acc[c * 32 + j], 0.0078125, (double)(int)v[j]);
+            for (int j = 0; j < 32; ++j) acc[c * 32 + j] += fma(biased_double(v[j]), sc, nb);   // exact: sc is a power of two
           }
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0)
-          for (int h = 0; h < 2; ++h)
-            if (ps.slot_mask & (1 << h)) mbar_arrive(&tempty_bar[h]);
+        if (lane == 0) mbar_arrive(&tempty_bar);
       }
       // ---- final epilogue of the tile ----
       double r0 = 0.0, r1 = 0.0;
@@ -443,41 +422,39 @@ inline EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// One sliced operand: int8 [k][Np][Np] + Np scales, and its tensor map for the current (Np, kstep).
+// One sliced operand: int8 [Np][Np / 32][8][32] + Np scales, and its tensor map for the current Np.
 struct Sliced {
   int8_t* d = nullptr;
   double* scale = nullptr;
   CUtensorMap map;
-  int capNp = 0, capK = 0, mapNp = 0, mapKstep = 0;
+  int capNp = 0, mapNp = 0;
   ~Sliced() { cudaFree(d); cudaFree(scale); }
-  bool ensure(int Np, int k, cudaStream_t st) {
-    if (Np <= capNp && k <= capK) return true;
+  bool ensure(int Np) {
+    if (Np <= capNp) return true;
     cudaFree(d); cudaFree(scale);
-    d = nullptr; scale = nullptr; capNp = capK = 0; mapNp = 0;
-    const size_t bytes = (size_t)k * Np * Np;
-    if (cudaMalloc(&d, bytes) != cudaSuccess || cudaMalloc(&scale, (size_t)Np * sizeof(double)) != cudaSuccess) return false;
-    capNp = Np; capK = k;
-    (void)st;
+    d = nullptr; scale = nullptr; capNp = 0; mapNp = 0;
+    if (cudaMalloc(&d, (size_t)kSlices * Np * Np) != cudaSuccess || cudaMalloc(&scale, (size_t)Np * sizeof(double)) != cudaSuccess) return false;
+    capNp = Np;
     return true;
   }
-  // zero padding rows / columns (and everything else) for a new (N, Np): called when the shape changes
-  bool clear(int Np, int k, cudaStream_t st) {
-    return cudaMemsetAsync(d, 0, (size_t)k * Np * Np, st) == cudaSuccess &&
+  // zero padding rows / columns and unused slices: called when the shape of the cone changes
+  bool clear(int Np, cudaStream_t st) {
+    mapNp = 0;
+    return cudaMemsetAsync(d, 0, (size_t)kSlices * Np * Np, st) == cudaSuccess &&
            cudaMemsetAsync(scale, 0, (size_t)Np * sizeof(double), st) == cudaSuccess;
   }
-  bool make_map(int Np, int k, int kstep) {
-    if (mapNp == Np && mapKstep == kstep) return true;
+  bool make_map(int Np) {
+    if (mapNp == Np) return true;
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return false;
-    const cuuint64_t dims[3] = {(cuuint64_t)Np, (cuuint64_t)Np, (cuuint64_t)k};
-    const cuuint64_t strides[2] = {(cuuint64_t)Np, (cuuint64_t)Np * Np};
-    const cuuint32_t box[3] = {(cuuint32_t)kstep, (cuuint32_t)kTile, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUtensorMapSwizzle sw = kstep == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (kstep == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-    if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, d, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    const cuuint64_t dims[2] = {(cuuint64_t)Np * kSlices, (cuuint64_t)Np};
+    const cuuint64_t strides[1] = {(cuuint64_t)Np * kSlices};
+    const cuuint32_t box[2] = {128, (cuuint32_t)kTile};
+    const cuuint32_t estr[2] = {1, 1};
+    if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, d, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return false;
-    mapNp = Np; mapKstep = kstep;
+    mapNp = Np;
     return true;
   }
 };
@@ -488,34 +465,29 @@ struct OzakiGemm {
   Plan* plan_d = nullptr;
   int2* tiles_d = nullptr;
   int tilesNp = 0, ntiles = 0;
-  int k = 7, kstep = 128, gpb = 1, num_sms = 148;
+  int k = 8, num_sms = 148;
   int N = 0, Np = 0;
   bool ready = false;
   std::string err;
   ~OzakiGemm() { cudaFree(plan_d); cudaFree(tiles_d); }
 
-  static int env_int(const char* name, int def) {
-    const char* e = getenv(name);
-    return (e && *e) ? atoi(e) : def;
-  }
-  bool configure(int k_, int kstep_, int gpb_, cudaStream_t st) {
-    k = k_; kstep = kstep_; gpb = gpb_;
-    if (!make_plan(plan_h, k, gpb, kstep, err)) return false;
+  static constexpr int smem_bytes() { return kStages * kStageBytes + 1024; }
+  bool configure(int k_, cudaStream_t st) {
+    k = k_;
+    if (!make_plan(plan_h, k, err)) return false;
     if (!plan_d && cudaMalloc(&plan_d, sizeof(Plan)) != cudaSuccess) { err = "cudaMalloc plan"; return false; }
     if (cudaMemcpyAsync(plan_d, &plan_h, sizeof(Plan), cudaMemcpyHostToDevice, st) != cudaSuccess) { err = "copy plan"; return false; }
-    cudaStreamSynchronize(st);   // plan_h may change before the copy is consumed otherwise
+    cudaStreamSynchronize(st);
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    const int smem = smem_bytes();
-    cudaError_t e1 = cudaFuncSetAttribute(ozaki_gemm_kernel<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaError_t e2 = cudaFuncSetAttribute(ozaki_gemm_kernel<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaError_t e3 = cudaFuncSetAttribute(ozaki_gemm_kernel<T, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { err = "cudaFuncSetAttribute(ozaki_gemm_kernel)"; return false; }
+    if (cudaFuncSetAttribute(ozaki_gemm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes()) != cudaSuccess) {
+      err = "cudaFuncSetAttribute(ozaki_gemm_kernel)";
+      return false;
+    }
     ready = true;
     return true;
   }
-  int smem_bytes() const { return plan_h.nstages * plan_h.stage_tiles * kTile * kstep + 1024; }
   bool set_shape(int N_, cudaStream_t st) {
     N = N_;
     Np = (N + kTile - 1) / kTile * kTile;
@@ -524,8 +496,6 @@ struct OzakiGemm {
       std::vector<int2> tl;
       for (int bj = 0; bj < nt; ++bj)
         for (int bi = 0; bi <= bj; ++bi) tl.push_back(make_int2(bi, bj));
-      // long tiles first would not matter (all tiles cost the same); diagonal-major order keeps A/B tiles of
-      // concurrently running CTAs close in L2
       cudaFree(tiles_d);
       tiles_d = nullptr;
       if (cudaMalloc(&tiles_d, tl.size() * sizeof(int2)) != cudaSuccess) { err = "cudaMalloc tiles"; return false; }
@@ -544,16 +514,13 @@ struct OzakiGemm {
   // out = c0 (A B) + c1 D + c2 I   (+ reductions into partial[2 * ntiles])
   bool gemm(Sliced& A, Sliced& B, T* out, const T* D, const T* E, int e_identity, const double* coef_d, double* partial,
             cudaStream_t st) {
-    if (!A.make_map(Np, k, kstep) || !B.make_map(Np, k, kstep)) { err = "cuTensorMapEncodeTiled failed"; return false; }
+    if (!A.make_map(Np) || !B.make_map(Np)) { err = "cuTensorMapEncodeTiled failed"; return false; }
     GemmArgs<T> a;
     a.N = N; a.Np = Np; a.ntiles = ntiles; a.store = out ? 1 : 0;
     a.tiles = tiles_d; a.scaleA = A.scale; a.scaleB = B.scale; a.out = out; a.D = D; a.E = E; a.e_identity = e_identity;
     a.coef = coef_d; a.partial = partial;
     const int grid = std::min(ntiles, num_sms);
-    const int smem = smem_bytes();
-    if (kstep == 128) ozaki_gemm_kernel<T, 128><<<grid, kThreads, smem, st>>>(A.map, B.map, plan_d, a);
-    else if (kstep == 64) ozaki_gemm_kernel<T, 64><<<grid, kThreads, smem, st>>>(A.map, B.map, plan_d, a);
-    else ozaki_gemm_kernel<T, 32><<<grid, kThreads, smem, st>>>(A.map, B.map, plan_d, a);
+    ozaki_gemm_kernel<T><<<grid, kThreads, smem_bytes(), st>>>(A.map, B.map, plan_d, a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("ozaki_gemm_kernel launch: ") + cudaGetErrorString(e); return false; }
     return true;

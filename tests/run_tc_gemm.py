@@ -13,7 +13,7 @@ import cosmo_b200  # noqa: E402
 from cosmo_b200 import engine as E  # noqa: E402
 
 Ns = [int(a) for a in sys.argv[1:]] or [128, 200, 256, 1000, 2000]
-variants = [(7, 128, 1), (7, 64, 2), (7, 32, 4), (7, 32, 2), (7, 64, 1), (8, 128, 1), (4, 128, 1)]
+variants = [(8, 0, 0), (7, 0, 0), (6, 0, 0), (4, 0, 0)]
 if os.environ.get("TC_VARIANTS"):
     variants = [tuple(int(x) for x in v.split(",")) for v in os.environ["TC_VARIANTS"].split(";")]
 for N in Ns:
