@@ -24,7 +24,6 @@
 //   warps 2..9  epilogue: tcgen05.ld 32x32b, exact int32 -> fp64 accumulation over the groups, scaling, fused
 //               out = c0 * (A B) + c1 * D + c2 * I, mirrored store (the product of commuting symmetric matrices is
 //               symmetric: only tiles of the upper triangle are computed) and two fused Frobenius reductions.
-// The "plan" (built on the host, copied to shared memory) lists the (A slice, B slice, accumulator) products of a pass.
 // Operand tiles are re-used by all slice pairs of four groups while they sit in shared memory: L2 -> SM traffic is
 // what bounds an int8 product of this shape (the first version, one slice pair per stage, ran at 11 TB/s of L2 reads
 // and 28 % of the int8 peak -- profiles/tc_gemm_bringup_r2_v1.log).
@@ -46,8 +45,6 @@ constexpr int kKStep = 32;         // K per stage = K of one tcgen05.mma.kind::i
 constexpr int kBoxBytes = kTile * 128;   // one TMA box: 128 rows x (4 slices x 32 K-bytes), 128-byte swizzle
 constexpr int kStageBytes = 4 * kBoxBytes;   // A slices 0-3, A slices 4-7, B slices 0-3, B slices 4-7
 constexpr int kStages = 3;
-constexpr int kMaxOps = 32;        // products per stage
-constexpr int kMaxPasses = 4;
 constexpr int kThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kEpiWarps = 8;
 
@@ -55,53 +52,33 @@ constexpr int kEpiWarps = 8;
 // the same 32 K-values are adjacent.  One 128-byte TMA row therefore carries 4 slices of one K step, a 128 x 128-byte
 // box is the operand tile of 4 slices at once, and the tile of slice j inside the box is addressed like the j-th
 // K sub-step of an ordinary 128-byte-swizzled K-major tile (descriptor start address + 32 j bytes).
-struct MmaOp { uint16_t a_off, b_off; uint8_t acc, first, pad0, pad1; };   // descriptor offsets (16-byte units) inside a stage
-struct Pass {
-  uint8_t box_mask, nops, ngroups, pad;    // box_mask: bit 0 A slices 0-3, 1 A slices 4-7, 2 B slices 0-3, 3 B slices 4-7
-  uint8_t acc_order[4];                    // accumulators in the order the epilogue folds them
-  double group_scale[4];                   // 128^-(s-2) of each of them
-  MmaOp ops[kMaxOps];
-};
-struct Plan {
-  int npasses, k;
-  Pass p[kMaxPasses];
-};
-
-// Host: the pass list for k slices.  A pass owns the four TMEM accumulators: it covers up to four groups s = p + q and
-// issues every slice pair of them per K step from one stage, so an operand tile fetched once serves up to 26 products.
-inline bool make_plan(Plan& pl, int k, std::string& err) {
-  memset(&pl, 0, sizeof(pl));
-  if (k < 1 || k > kSlices) { err = "tc::make_plan: 1 <= slices <= 8"; return false; }
-  pl.k = k;
-  for (int s_hi = k + 1; s_hi >= 2; s_hi -= 4) {
-    if (pl.npasses >= kMaxPasses) { err = "tc::make_plan: too many passes"; return false; }
-    Pass& ps = pl.p[pl.npasses++];
-    const int ng = std::min(4, s_hi - 1);
-    ps.ngroups = (uint8_t)ng;
-    bool first_write[4] = {true, true, true, true};
-    for (int g = 0; g < ng; ++g) {
-      ps.acc_order[g] = (uint8_t)g;
-      ps.group_scale[g] = std::ldexp(1.0, -7 * (s_hi - g - 2));
+//
+// The product list is static.  With k slices the groups s = p + q run from k + 1 down to 2; a PASS owns the four TMEM
+// accumulators and covers the groups s_hi, s_hi - 1, s_hi - 2, s_hi - 3: pass 0 starts at k + 1, pass 1 at k - 3.
+// Every slice pair of a pass is issued per K step from one 64 KB stage, so an operand tile fetched once serves up
+// to 26 products.  Everything below is resolved at compile time (template parameter K): the issuing thread executes
+// two uniform adds and one UTCIMMA per product.
+__host__ __device__ constexpr int pass_s_hi(int k, int pass) { return k + 1 - 4 * pass; }
+__host__ __device__ constexpr int num_passes(int k) { return k <= 4 ? 1 : 2; }
+__host__ __device__ constexpr int pass_groups(int k, int pass) { return pass_s_hi(k, pass) - 1 < 4 ? pass_s_hi(k, pass) - 1 : 4; }
+// bit 0: A slices 0-3, bit 1: A slices 4-7, bit 2: B slices 0-3, bit 3: B slices 4-7 (the same set for A and B by symmetry)
+__host__ __device__ constexpr int pass_box_mask(int k, int pass) {
+  int m = 0;
+  for (int g = 0; g < pass_groups(k, pass); ++g)
+    for (int p = 1; p <= k; ++p) {
+      const int q = pass_s_hi(k, pass) - g - p;
+      if (q >= 1 && q <= k) m |= (1 << ((p - 1) / 4)) | (4 << ((q - 1) / 4));
     }
-    for (int p = 1; p <= k; ++p)           // ordered by A slice: consecutive products share the A tile
-      for (int g = 0; g < ng; ++g) {
-        const int q = s_hi - g - p;
-        if (q < 1 || q > k) continue;
-        if (ps.nops >= kMaxOps) { err = "tc::make_plan: too many products per stage"; return false; }
-        const int ja = p - 1, jb = q - 1;
-        ps.box_mask |= (uint8_t)(1 << (ja / 4));
-        ps.box_mask |= (uint8_t)(4 << (jb / 4));
-        MmaOp op;
-        op.a_off = (uint16_t)(((ja / 4) * kBoxBytes + (ja % 4) * 32) >> 4);
-        op.b_off = (uint16_t)(((2 + jb / 4) * kBoxBytes + (jb % 4) * 32) >> 4);
-        op.acc = (uint8_t)g;
-        op.first = first_write[g] ? 1 : 0;
-        op.pad0 = op.pad1 = 0;
-        first_write[g] = false;
-        ps.ops[ps.nops++] = op;
-      }
-  }
-  return true;
+  return m;
+}
+__host__ __device__ constexpr int pass_products(int k, int pass) {
+  int n = 0;
+  for (int g = 0; g < pass_groups(k, pass); ++g)
+    for (int p = 1; p <= k; ++p) {
+      const int q = pass_s_hi(k, pass) - g - p;
+      if (q >= 1 && q <= k) ++n;
+    }
+  return n;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -137,6 +114,11 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.b32 %0, 1, 0, P1;\n\t}\n" : "=r"(pred));
+  return pred != 0;
 }
 // D[tmem] (+)= A[smem] * B[smem]^T, int8 x int8 -> int32, M = N = 128, K = 32
 __device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -227,23 +209,107 @@ struct GemmArgs {
   double* partial;                   // 2 per tile: sum w out^2, sum w (E - out)^2   (w: 1 on the diagonal, 2 above it)
 };
 
-template <typename T>
+// all slice-pair products of one pass for one K step (compile-time list)
+template <int K, int PASS>
+__device__ __forceinline__ void issue_pass_products(uint32_t sbase16, uint32_t tmem_base, int ks) {
+  constexpr int S_HI = pass_s_hi(K, PASS);
+  constexpr int NG = pass_groups(K, PASS);
+#pragma unroll
+  for (int p = 1; p <= K; ++p) {       // ordered by A slice: consecutive products share the A tile
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      const int s = S_HI - g, q = s - p;
+      if (q >= 1 && q <= K) {
+        const uint32_t a_off = (uint32_t)((((p - 1) / 4) * kBoxBytes + ((p - 1) % 4) * 32) >> 4);
+        const uint32_t b_off = (uint32_t)(((2 + (q - 1) / 4) * kBoxBytes + ((q - 1) % 4) * 32) >> 4);
+        const bool first = (p == ((s - K) > 1 ? (s - K) : 1));      // first write of this accumulator in the pass
+        tc_mma_i8(tmem_base + (uint32_t)(g * kTile), smem_desc(sbase16 + a_off), smem_desc(sbase16 + b_off), kIdescI8,
+                  first ? (ks != 0 ? 1u : 0u) : 1u);
+      }
+    }
+  }
+}
+
+struct PipeState { int stage; uint32_t phase; };
+
+template <int K, int PASS>
+__device__ __forceinline__ void producer_pass(const CUtensorMap* tmapA, const CUtensorMap* tmapB, uint8_t* smem, uint64_t* full_bar,
+                                              uint64_t* empty_bar, int nk, int m0, int n0, PipeState& st) {
+  constexpr uint32_t mask = (uint32_t)pass_box_mask(K, PASS);
+  constexpr uint32_t bytes = (uint32_t)(((mask & 1) + ((mask >> 1) & 1) + ((mask >> 2) & 1) + ((mask >> 3) & 1)) * kBoxBytes);
+  for (int ks = 0; ks < nk; ++ks) {
+    mbar_wait(&empty_bar[st.stage], st.phase ^ 1);
+    if (elect_one()) {
+      mbar_expect_tx(&full_bar[st.stage], bytes);
+      const uint32_t dst = smem_u32(smem) + (uint32_t)st.stage * kStageBytes;
+      const int c0 = ks * (kSlices * 32);
+      if (mask & 1) tma_load_2d(dst, tmapA, &full_bar[st.stage], c0, m0);
+      if (mask & 2) tma_load_2d(dst + kBoxBytes, tmapA, &full_bar[st.stage], c0 + 128, m0);
+      if (mask & 4) tma_load_2d(dst + 2 * kBoxBytes, tmapB, &full_bar[st.stage], c0, n0);
+      if (mask & 8) tma_load_2d(dst + 3 * kBoxBytes, tmapB, &full_bar[st.stage], c0 + 128, n0);
+    }
+    __syncwarp();
+    if (++st.stage == kStages) { st.stage = 0; st.phase ^= 1; }
+  }
+}
+
+template <int K, int PASS>
+__device__ __forceinline__ void mma_pass(uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar, uint64_t* tfull_bar, uint64_t* tempty_bar,
+                                         uint32_t tmem_base, int nk, PipeState& st, uint32_t& tphase) {
+  mbar_wait(tempty_bar, tphase ^ 1);      // the epilogue has drained the accumulators of the previous pass
+  tc_fence_after();
+  for (int ks = 0; ks < nk; ++ks) {
+    mbar_wait(&full_bar[st.stage], st.phase);
+    tc_fence_after();
+    if (elect_one()) {
+      const uint32_t sbase16 = (smem_u32(smem) + (uint32_t)st.stage * kStageBytes) >> 4;
+      issue_pass_products<K, PASS>(sbase16, tmem_base, ks);
+      tc_commit(&empty_bar[st.stage]);
+      if (ks == nk - 1) tc_commit(tfull_bar);
+    }
+    __syncwarp();
+    if (++st.stage == kStages) { st.stage = 0; st.phase ^= 1; }
+  }
+  tphase ^= 1;
+}
+
+// fold the accumulators of one pass into the fp64 registers: acc += 128^-(s-2) G_s, exactly converted
+template <int K, int PASS>
+__device__ __forceinline__ void epilogue_pass(double (&acc)[64], uint32_t tlane, uint64_t* tfull_bar, uint64_t* tempty_bar, uint32_t& tphase,
+                                              int lane) {
+  constexpr int S_HI = pass_s_hi(K, PASS);
+  constexpr int NG = pass_groups(K, PASS);
+  mbar_wait(tfull_bar, tphase);
+  tphase ^= 1;
+  tc_fence_after();
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    const double sc = 1.0 / (double)(1ull << (7 * (S_HI - g - 2)));     // 128^-(s-2), a power of two
+    const double nb = -kBias * sc;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      COSMO_TC_LD32(tlane + (uint32_t)(g * kTile + c * 32), v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[c * 32 + j] += fma(biased_double(v[j]), sc, nb);   // fma is exact: v * sc
+    }
+  }
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(tempty_bar);
+}
+
+template <typename T, int K>
 __global__ void __launch_bounds__(kThreads, 1) ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmapA,
-                                                                 const __grid_constant__ CUtensorMap tmapB,
-                                                                 const Plan* __restrict__ plan_g, const GemmArgs<T> args) {
+                                                                 const __grid_constant__ CUtensorMap tmapB, const GemmArgs<T> args) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ Plan plan;
   __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], tfull_bar, tempty_bar;
   __shared__ uint32_t tmem_base_s;
   __shared__ double red[kEpiWarps][2];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(plan_g);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&plan);
-    for (int i = threadIdx.x; i < (int)(sizeof(Plan) / 4); i += blockDim.x) dst[i] = src[i];
-  }
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(&tfull_bar, 1);
@@ -259,61 +325,23 @@ __global__ void __launch_bounds__(kThreads, 1) ozaki_gemm_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   const int nk = args.Np / kKStep;
-  const int npasses = plan.npasses;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = blockIdx.x; t < args.ntiles; t += gridDim.x) {
-        const int2 tl = args.tiles[t];
-        const int m0 = tl.x * kTile, n0 = tl.y * kTile;
-        for (int pi = 0; pi < npasses; ++pi) {
-          const uint32_t mask = plan.p[pi].box_mask;
-          const uint32_t bytes = (uint32_t)__popc(mask) * kBoxBytes;
-          for (int ks = 0; ks < nk; ++ks) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_expect_tx(&full_bar[stage], bytes);
-            const uint32_t dst = smem_u32(smem) + (uint32_t)stage * kStageBytes;
-            const int c0 = ks * (kSlices * 32);
-            if (mask & 1) tma_load_2d(dst, &tmapA, &full_bar[stage], c0, m0);
-            if (mask & 2) tma_load_2d(dst + kBoxBytes, &tmapA, &full_bar[stage], c0 + 128, m0);
-            if (mask & 4) tma_load_2d(dst + 2 * kBoxBytes, &tmapB, &full_bar[stage], c0, n0);
-            if (mask & 8) tma_load_2d(dst + 3 * kBoxBytes, &tmapB, &full_bar[stage], c0 + 128, n0);
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
-          }
-        }
-      }
+    // ===== TMA producer (warp-uniform loop, one elected lane issues) =====
+    PipeState st{0, 0};
+    for (int t = blockIdx.x; t < args.ntiles; t += gridDim.x) {
+      const int2 tl = args.tiles[t];
+      const int m0 = tl.x * kTile, n0 = tl.y * kTile;
+      producer_pass<K, 0>(&tmapA, &tmapB, smem, full_bar, empty_bar, nk, m0, n0, st);
+      if (num_passes(K) > 1) producer_pass<K, (num_passes(K) > 1 ? 1 : 0)>(&tmapA, &tmapB, smem, full_bar, empty_bar, nk, m0, n0, st);
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0, tphase = 0;
-      for (int t = blockIdx.x; t < args.ntiles; t += gridDim.x) {
-        for (int pi = 0; pi < npasses; ++pi) {
-          const Pass& ps = plan.p[pi];
-          const int nops = ps.nops;
-          mbar_wait(&tempty_bar, tphase ^ 1);      // the epilogue has drained the accumulators of the previous pass
-          tc_fence_after();
-          for (int ks = 0; ks < nk; ++ks) {
-            mbar_wait(&full_bar[stage], phase);
-            tc_fence_after();
-            const uint32_t sbase16 = (smem_u32(smem) + (uint32_t)stage * kStageBytes) >> 4;
-#pragma unroll 2
-            for (int o = 0; o < nops; ++o) {
-              const MmaOp op = ps.ops[o];
-              tc_mma_i8(tmem_base + (uint32_t)op.acc * kTile, smem_desc(sbase16 + op.a_off), smem_desc(sbase16 + op.b_off),
-                        kIdescI8, (ks | (op.first ^ 1)) ? 1u : 0u);
-            }
-            tc_commit(&empty_bar[stage]);
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
-          }
-          tc_commit(&tfull_bar);
-          tphase ^= 1;
-        }
-      }
+    PipeState st{0, 0};
+    uint32_t tphase = 0;
+    for (int t = blockIdx.x; t < args.ntiles; t += gridDim.x) {
+      mma_pass<K, 0>(smem, full_bar, empty_bar, &tfull_bar, &tempty_bar, tmem_base, nk, st, tphase);
+      if (num_passes(K) > 1) mma_pass<K, (num_passes(K) > 1 ? 1 : 0)>(smem, full_bar, empty_bar, &tfull_bar, &tempty_bar, tmem_base, nk, st, tphase);
     }
   } else {
     // ===== epilogue warps =====
@@ -330,29 +358,8 @@ __global__ void __launch_bounds__(kThreads, 1) ozaki_gemm_kernel(const __grid_co
       double acc[64];
 #pragma unroll
       for (int j = 0; j < 64; ++j) acc[j] = 0.0;
-      for (int pi = 0; pi < npasses; ++pi) {
-        const Pass& ps = plan.p[pi];
-        mbar_wait(&tfull_bar, tphase);
-        tphase ^= 1;
-        tc_fence_after();
-        const int ng = ps.ngroups;
-        for (int g = 0; g < ng; ++g) {
-          const uint32_t ta = tlane + (uint32_t)ps.acc_order[g] * kTile;
-          const double sc = ps.group_scale[g];
-          const double nb = -kBias * sc;
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t v[32];
-            COSMO_TC_LD32(ta + c * 32, v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int j = 0; j < 32; ++j) acc[c * 32 + j] += fma(biased_double(v[j]), sc, nb);   // exact: sc is a power of two
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar);
-      }
+      epilogue_pass<K, 0>(acc, tlane, &tfull_bar, &tempty_bar, tphase, lane);
+      if (num_passes(K) > 1) epilogue_pass<K, (num_passes(K) > 1 ? 1 : 0)>(acc, tlane, &tfull_bar, &tempty_bar, tphase, lane);
       // ---- final epilogue of the tile ----
       double r0 = 0.0, r1 = 0.0;
       const int N = args.N;
@@ -461,27 +468,28 @@ struct Sliced {
 
 template <typename T>
 struct OzakiGemm {
-  Plan plan_h;
-  Plan* plan_d = nullptr;
   int2* tiles_d = nullptr;
   int tilesNp = 0, ntiles = 0;
   int k = 8, num_sms = 148;
   int N = 0, Np = 0;
   bool ready = false;
   std::string err;
-  ~OzakiGemm() { cudaFree(plan_d); cudaFree(tiles_d); }
+  ~OzakiGemm() { cudaFree(tiles_d); }
 
   static constexpr int smem_bytes() { return kStages * kStageBytes + 1024; }
+  template <int K>
+  static bool set_attr() {
+    return cudaFuncSetAttribute(ozaki_gemm_kernel<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes()) == cudaSuccess;
+  }
   bool configure(int k_, cudaStream_t st) {
+    (void)st;
     k = k_;
-    if (!make_plan(plan_h, k, err)) return false;
-    if (!plan_d && cudaMalloc(&plan_d, sizeof(Plan)) != cudaSuccess) { err = "cudaMalloc plan"; return false; }
-    if (cudaMemcpyAsync(plan_d, &plan_h, sizeof(Plan), cudaMemcpyHostToDevice, st) != cudaSuccess) { err = "copy plan"; return false; }
-    cudaStreamSynchronize(st);
+    if (k < 3 || k > kSlices) { err = "tc::OzakiGemm: 3 <= slices <= 8"; return false; }
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaFuncSetAttribute(ozaki_gemm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes()) != cudaSuccess) {
+    // per device, every time: function attributes are per device and cheap to set
+    if (!(set_attr<3>() && set_attr<4>() && set_attr<5>() && set_attr<6>() && set_attr<7>() && set_attr<8>())) {
       err = "cudaFuncSetAttribute(ozaki_gemm_kernel)";
       return false;
     }
@@ -520,7 +528,14 @@ struct OzakiGemm {
     a.tiles = tiles_d; a.scaleA = A.scale; a.scaleB = B.scale; a.out = out; a.D = D; a.E = E; a.e_identity = e_identity;
     a.coef = coef_d; a.partial = partial;
     const int grid = std::min(ntiles, num_sms);
-    ozaki_gemm_kernel<T><<<grid, kThreads, smem_bytes(), st>>>(A.map, B.map, plan_d, a);
+    switch (k) {
+      case 3: ozaki_gemm_kernel<T, 3><<<grid, kThreads, smem_bytes(), st>>>(A.map, B.map, a); break;
+      case 4: ozaki_gemm_kernel<T, 4><<<grid, kThreads, smem_bytes(), st>>>(A.map, B.map, a); break;
+      case 5: ozaki_gemm_kernel<T, 5><<<grid, kThreads, smem_bytes(), st>>>(A.map, B.map, a); break;
+      case 6: ozaki_gemm_kernel<T, 6><<<grid, kThreads, smem_bytes(), st>>>(A.map, B.map, a); break;
+      case 7: ozaki_gemm_kernel<T, 7><<<grid, kThreads, smem_bytes(), st>>>(A.map, B.map, a); break;
+      default: ozaki_gemm_kernel<T, 8><<<grid, kThreads, smem_bytes(), st>>>(A.map, B.map, a); break;
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("ozaki_gemm_kernel launch: ") + cudaGetErrorString(e); return false; }
     return true;
