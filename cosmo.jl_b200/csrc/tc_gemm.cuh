@@ -14,14 +14,14 @@
 // Measured against numpy dgemm (N = 2000, profiles/tc_gemm_bringup_r2_*.log): k = 8 -> 1e-15, k = 7 -> 1e-13 relative
 // to |A| |B|.
 //
-// Kernel anatomy (one persistent CTA per SM, 10 warps):
+// Kernel anatomy (one persistent CTA per SM, 12 warps):
 //   warp 0      TMA producer: cp.async.bulk.tensor.2d, 128-row x 128-byte boxes (= the tiles of 4 slices for one K step
-//               of 32, see the layout note at MmaOp), 128-byte hardware swizzle, into a ring of 64 KB stages
-//               {A slices 0-3, A 4-7, B 0-3, B 4-7}, mbarrier complete_tx
+//               of 32, see the layout note below), 128-byte hardware swizzle, into a ring of six 32 KB units
+//               {A box, B box}, mbarrier complete_tx
 //   warp 1      MMA issuer: one elected lane walks the pass list of the plan and issues tcgen05.mma.kind::i8 (M = N = 128,
 //               K = 32) from shared-memory descriptors into four 128-column TMEM accumulators -- up to 26 slice-pair
 //               products per stage; tcgen05.commit releases the stage / publishes the accumulators
-//   warps 2..9  epilogue: tcgen05.ld 32x32b, exact int32 -> fp64 accumulation over the groups, scaling, fused
+//   warps 4..11 epilogue: tcgen05.ld 32x32b, exact int32 -> fp64 accumulation over the groups, scaling, fused
 //               out = c0 * (A B) + c1 * D + c2 * I, mirrored store (the product of commuting symmetric matrices is
 //               symmetric: only tiles of the upper triangle are computed) and two fused Frobenius reductions.
 // Operand tiles are re-used by all slice pairs of four groups while they sit in shared memory: L2 -> SM traffic is
@@ -43,9 +43,9 @@ constexpr int kTile = 128;         // output tile side = rows of one operand box
 constexpr int kSlices = 8;         // slices stored per matrix (unused ones are zero)
 constexpr int kKStep = 32;         // K per stage = K of one tcgen05.mma.kind::i8
 constexpr int kBoxBytes = kTile * 128;   // one TMA box: 128 rows x (4 slices x 32 K-bytes), 128-byte swizzle
-constexpr int kStageBytes = 4 * kBoxBytes;   // A slices 0-3, A slices 4-7, B slices 0-3, B slices 4-7
-constexpr int kStages = 3;
-constexpr int kThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kUnitBytes = 2 * kBoxBytes;    // ring unit: {A box, B box} of slices 0-3 (or of slices 4-7)
+constexpr int kUnits = 6;                    // 192 KB ring: 3 K steps in flight when a pass needs both halves, 6 otherwise
+constexpr int kThreads = 384;      // warpgroup 0: warp 0 TMA, warp 1 MMA (2, 3 idle); warpgroups 1, 2: epilogue
 constexpr int kEpiWarps = 8;
 
 // Layout of a sliced operand: int8 [row][K / 32][slice 0..7][32], i.e. a row of Np * 8 bytes in which the 8 slices of
@@ -153,7 +153,7 @@ constexpr double kBias = 4503599627370496.0 + 2147483648.0;
 
 // ---------------------------------------------------------------------------------------------------------------
 // Slicing: one CTA per row.  scale[r] = 2^(e_r - 6) with 2^e_r > max |M[r, :]|; digits by round-to-nearest so that
-// every digit is in [-64, 64]; all operations are exact in fp64.  Output layout: see MmaOp above.
+// every digit is in [-64, 64]; all operations are exact in fp64.  Output layout: see the note above.
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) slice_rows_kernel(const T* __restrict__ M, int N, int Np, int k, int8_t* __restrict__ slices,
@@ -220,8 +220,8 @@ __device__ __forceinline__ void issue_pass_products(uint32_t sbase16, uint32_t t
     for (int g = 0; g < NG; ++g) {
       const int s = S_HI - g, q = s - p;
       if (q >= 1 && q <= K) {
-        const uint32_t a_off = (uint32_t)((((p - 1) / 4) * kBoxBytes + ((p - 1) % 4) * 32) >> 4);
-        const uint32_t b_off = (uint32_t)(((2 + (q - 1) / 4) * kBoxBytes + ((q - 1) % 4) * 32) >> 4);
+        const uint32_t a_off = (uint32_t)((((p - 1) / 4) * kUnitBytes + ((p - 1) % 4) * 32) >> 4);
+        const uint32_t b_off = (uint32_t)((((q - 1) / 4) * kUnitBytes + kBoxBytes + ((q - 1) % 4) * 32) >> 4);
         const bool first = (p == ((s - K) > 1 ? (s - K) : 1));      // first write of this accumulator in the pass
         tc_mma_i8(tmem_base + (uint32_t)(g * kTile), smem_desc(sbase16 + a_off), smem_desc(sbase16 + b_off), kIdescI8,
                   first ? (ks != 0 ? 1u : 0u) : 1u);
@@ -230,45 +230,53 @@ __device__ __forceinline__ void issue_pass_products(uint32_t sbase16, uint32_t t
   }
 }
 
-struct PipeState { int stage; uint32_t phase; };
+struct PipeState { int unit; uint32_t phase; };   // position in the ring of kUnits units
+
+// a pass needs the slices 4-7 of either operand <=> it occupies two ring units per K step (kUnits is even and the
+// number of K steps is even, so a two-unit step never wraps inside)
+__host__ __device__ constexpr int pass_units(int k, int pass) { return (pass_box_mask(k, pass) & 0xA) ? 2 : 1; }
 
 template <int K, int PASS>
 __device__ __forceinline__ void producer_pass(const CUtensorMap* tmapA, const CUtensorMap* tmapB, uint8_t* smem, uint64_t* full_bar,
                                               uint64_t* empty_bar, int nk, int m0, int n0, PipeState& st) {
-  constexpr uint32_t mask = (uint32_t)pass_box_mask(K, PASS);
-  constexpr uint32_t bytes = (uint32_t)(((mask & 1) + ((mask >> 1) & 1) + ((mask >> 2) & 1) + ((mask >> 3) & 1)) * kBoxBytes);
+  constexpr int NU = pass_units(K, PASS);
   for (int ks = 0; ks < nk; ++ks) {
-    mbar_wait(&empty_bar[st.stage], st.phase ^ 1);
-    if (elect_one()) {
-      mbar_expect_tx(&full_bar[st.stage], bytes);
-      const uint32_t dst = smem_u32(smem) + (uint32_t)st.stage * kStageBytes;
-      const int c0 = ks * (kSlices * 32);
-      if (mask & 1) tma_load_2d(dst, tmapA, &full_bar[st.stage], c0, m0);
-      if (mask & 2) tma_load_2d(dst + kBoxBytes, tmapA, &full_bar[st.stage], c0 + 128, m0);
-      if (mask & 4) tma_load_2d(dst + 2 * kBoxBytes, tmapB, &full_bar[st.stage], c0, n0);
-      if (mask & 8) tma_load_2d(dst + 3 * kBoxBytes, tmapB, &full_bar[st.stage], c0 + 128, n0);
+#pragma unroll
+    for (int h = 0; h < NU; ++h) {
+      mbar_wait(&empty_bar[st.unit], st.phase ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&full_bar[st.unit], (uint32_t)kUnitBytes);
+        const uint32_t dst = smem_u32(smem) + (uint32_t)st.unit * kUnitBytes;
+        const int c0 = ks * (kSlices * 32) + h * 128;
+        tma_load_2d(dst, tmapA, &full_bar[st.unit], c0, m0);
+        tma_load_2d(dst + kBoxBytes, tmapB, &full_bar[st.unit], c0, n0);
+      }
+      __syncwarp();
+      if (++st.unit == kUnits) { st.unit = 0; st.phase ^= 1; }
     }
-    __syncwarp();
-    if (++st.stage == kStages) { st.stage = 0; st.phase ^= 1; }
   }
 }
 
 template <int K, int PASS>
 __device__ __forceinline__ void mma_pass(uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar, uint64_t* tfull_bar, uint64_t* tempty_bar,
                                          uint32_t tmem_base, int nk, PipeState& st, uint32_t& tphase) {
+  constexpr int NU = pass_units(K, PASS);
   mbar_wait(tempty_bar, tphase ^ 1);      // the epilogue has drained the accumulators of the previous pass
   tc_fence_after();
   for (int ks = 0; ks < nk; ++ks) {
-    mbar_wait(&full_bar[st.stage], st.phase);
+    mbar_wait(&full_bar[st.unit], st.phase);
+    if (NU == 2) mbar_wait(&full_bar[st.unit + 1], st.phase);
     tc_fence_after();
     if (elect_one()) {
-      const uint32_t sbase16 = (smem_u32(smem) + (uint32_t)st.stage * kStageBytes) >> 4;
+      const uint32_t sbase16 = (smem_u32(smem) + (uint32_t)st.unit * kUnitBytes) >> 4;
       issue_pass_products<K, PASS>(sbase16, tmem_base, ks);
-      tc_commit(&empty_bar[st.stage]);
+      tc_commit(&empty_bar[st.unit]);
+      if (NU == 2) tc_commit(&empty_bar[st.unit + 1]);
       if (ks == nk - 1) tc_commit(tfull_bar);
     }
     __syncwarp();
-    if (++st.stage == kStages) { st.stage = 0; st.phase ^= 1; }
+    st.unit += NU;
+    if (st.unit == kUnits) { st.unit = 0; st.phase ^= 1; }
   }
   tphase ^= 1;
 }
@@ -305,13 +313,13 @@ __global__ void __launch_bounds__(kThreads, 1) ozaki_gemm_kernel(const __grid_co
                                                                  const __grid_constant__ CUtensorMap tmapB, const GemmArgs<T> args) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], tfull_bar, tempty_bar;
+  __shared__ __align__(8) uint64_t full_bar[kUnits], empty_bar[kUnits], tfull_bar, tempty_bar;
   __shared__ uint32_t tmem_base_s;
   __shared__ double red[kEpiWarps][2];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < kUnits; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(&tfull_bar, 1);
     mbar_init(&tempty_bar, kEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -326,8 +334,11 @@ __global__ void __launch_bounds__(kThreads, 1) ozaki_gemm_kernel(const __grid_co
   const uint32_t tmem_base = tmem_base_s;
   const int nk = args.Np / kKStep;
 
+  // register re-distribution (setmaxnreg is per warpgroup): the TMA / MMA warps need few registers, the epilogue
+  // threads hold a 64-element fp64 accumulator row each plus the 32 freshly loaded TMEM words
   if (warp == 0) {
     // ===== TMA producer (warp-uniform loop, one elected lane issues) =====
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     PipeState st{0, 0};
     for (int t = blockIdx.x; t < args.ntiles; t += gridDim.x) {
       const int2 tl = args.tiles[t];
@@ -337,15 +348,19 @@ __global__ void __launch_bounds__(kThreads, 1) ozaki_gemm_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     PipeState st{0, 0};
     uint32_t tphase = 0;
     for (int t = blockIdx.x; t < args.ntiles; t += gridDim.x) {
       mma_pass<K, 0>(smem, full_bar, empty_bar, &tfull_bar, &tempty_bar, tmem_base, nk, st, tphase);
       if (num_passes(K) > 1) mma_pass<K, (num_passes(K) > 1 ? 1 : 0)>(smem, full_bar, empty_bar, &tfull_bar, &tempty_bar, tmem_base, nk, st, tphase);
     }
+  } else if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   } else {
     // ===== epilogue warps =====
-    const int ew = warp - 2;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int ew = warp - 4;
     const int quad = warp & 3;            // TMEM lanes [32 quad, 32 quad + 32) are the ones this warp may read
     const int half = ew >> 2;             // columns [64 half, 64 half + 64) of the tile
     const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 64);
@@ -476,7 +491,7 @@ struct OzakiGemm {
   std::string err;
   ~OzakiGemm() { cudaFree(tiles_d); }
 
-  static constexpr int smem_bytes() { return kStages * kStageBytes + 1024; }
+  static constexpr int smem_bytes() { return kUnits * kUnitBytes + 1024; }
   template <int K>
   static bool set_attr() {
     return cudaFuncSetAttribute(ozaki_gemm_kernel<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes()) == cudaSuccess;
