@@ -166,6 +166,7 @@ class EngineBase {
   virtual void spmv_bench(int which, int reps, double* ms, double* bytes) = 0;
   virtual void get_rho_vec(void* out) = 0;
   virtual void get_w(void* out) = 0;
+  virtual void psd_stats(int64_t* out8) = 0;
   virtual void comm_init(int nranks, int rank, const void* id128) = 0;
   virtual void p2p_export(void* blob128) = 0;
   virtual void p2p_attach(const void* blobs, int nranks) = 0;
@@ -192,6 +193,7 @@ class Engine : public EngineBase {
   void spmv_bench(int which, int reps, double* ms, double* bytes) override;
   void get_rho_vec(void* out) override;
   void get_w(void* out) override;
+  void psd_stats(int64_t* out8) override;
   void comm_init(int nranks, int rank, const void* id128) override;
   void p2p_export(void* blob128) override;
   void p2p_attach(const void* blobs, int nranks) override;
@@ -1801,6 +1803,11 @@ void Engine<T>::spmv_bench(int which, int reps, double* ms, double* bytes) {
 template <typename T>
 void Engine<T>::get_rho_vec(void* out) { download_vec(out, rho_vec_.p, m_); sync(); }
 template <typename T>
+void Engine<T>::psd_stats(int64_t* o) {
+  o[0] = psd_.tc_projections; o[1] = psd_.tc_fallbacks; o[2] = psd_.tc_.last_steps; o[3] = psd_.tc_.last_checks;
+  o[4] = psd_.sign_projections; o[5] = psd_.sign_fallbacks; o[6] = psd_.last_sweeps; o[7] = psd_.tc_.gemm.k;
+}
+template <typename T>
 void Engine<T>::get_w(void* out) { download_vec(out, W_[cur_].p, (size_t)n_ + m_); sync(); }
 
 }  // namespace cosmo
@@ -1906,6 +1913,10 @@ int cosmo_b200_get_rho_vec(cosmo_b200_handle* h, void* out) {
 int cosmo_b200_get_w(cosmo_b200_handle* h, void* out) {
   if (!out) return COSMO_B200_ERR_INVALID;
   ABI_GUARD(h, h->impl->get_w(out));
+}
+int cosmo_b200_psd_stats(cosmo_b200_handle* h, int64_t out[8]) {
+  if (!out) return COSMO_B200_ERR_INVALID;
+  ABI_GUARD(h, h->impl->psd_stats(out));
 }
 int cosmo_b200_comm_unique_id(void* id128) {
   if (!id128) return COSMO_B200_ERR_INVALID;

@@ -84,7 +84,7 @@ EXPORTS = [
     "cosmo_b200_update_rho", "cosmo_b200_reset", "cosmo_b200_solve", "cosmo_b200_project", "cosmo_b200_kkt_solve",
     "cosmo_b200_residuals", "cosmo_b200_spmv", "cosmo_b200_spmv_bench", "cosmo_b200_get_rho_vec", "cosmo_b200_get_w",
     "cosmo_b200_comm_unique_id", "cosmo_b200_comm_init", "cosmo_b200_comm_p2p_export", "cosmo_b200_comm_p2p_attach",
-    "cosmo_b200_tc_gemm_test",
+    "cosmo_b200_tc_gemm_test", "cosmo_b200_psd_stats",
 ]
 
 _lib = None
@@ -130,6 +130,7 @@ def load_library(rebuild_if_stale=True):
     lib.cosmo_b200_comm_init.argtypes = [vp, C.c_int32, C.c_int32, vp]
     lib.cosmo_b200_comm_p2p_export.argtypes = [vp, vp]
     lib.cosmo_b200_comm_p2p_attach.argtypes = [vp, vp, C.c_int32]
+    lib.cosmo_b200_psd_stats.argtypes = [vp, C.POINTER(C.c_int64)]
     lib.cosmo_b200_tc_gemm_test.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, C.c_int32,
                                             C.POINTER(C.c_double), C.POINTER(C.c_double)]
     for name in EXPORTS:
@@ -366,8 +367,16 @@ class Engine:
         self._check(self._lib.cosmo_b200_get_w(self._h, _ptr(out)))
         return out
 
+    def psd_stats(self):
+        """Which path projected the large PSD cones so far (cosmo_b200_psd_stats)."""
+        out = (C.c_int64 * 8)()
+        self._check(self._lib.cosmo_b200_psd_stats(self._h, out))
+        keys = ("tc_projections", "tc_fallbacks", "tc_last_steps", "tc_last_checks", "sign_projections", "sign_fallbacks",
+                "jacobi_last_sweeps", "tc_slices")
+        return dict(zip(keys, [int(v) for v in out]))
 
-def tc_gemm(A, B, slices=7, kstep=128, gpb=1, reps=0):
+
+def tc_gemm(A, B, slices=8, kstep=0, gpb=0, reps=0):
     """C = A @ B for symmetric commuting fp64 matrices through the int8-sliced tcgen05 product kernel
     (diagnostic entry `cosmo_b200_tc_gemm_test`).  Returns (C, ms_per_product, (|C|_F^2, |I - C|_F^2))."""
     lib = load_library()

@@ -244,6 +244,10 @@ int cosmo_b200_comm_p2p_export(cosmo_b200_handle* h, void* blob128);
 int cosmo_b200_comm_p2p_attach(cosmo_b200_handle* h, const void* blobs, int32_t nranks);
 
 /* ---- diagnostics ---------------------------------------------------------- */
+/* Which path projected the large PSD cones (N > 96) so far: out = {tensor-core projections, tensor-core fallbacks to
+   block Jacobi, Newton-Schulz steps of the last one, weighted-residual checks of the last one, FP64-FMA sign
+   projections, their fallbacks, block-Jacobi sweeps of the last eigensolve, int8 slices per operand}. */
+int cosmo_b200_psd_stats(cosmo_b200_handle* h, int64_t out[8]);
 /* The product kernel of the large-cone PSD projection on its own: C = A B for symmetric, commuting N x N fp64
    matrices (column-major) through `k` int8 slices on tcgen05 (csrc/tc_gemm.cuh; the reference's counterpart is the
    BLAS-3 part of project!(::PsdCone), convexset.jl:244-260).  kstep in {32, 64, 128} bytes of K per stage tile,

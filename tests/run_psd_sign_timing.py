@@ -1,5 +1,5 @@
-"""Measurement helper for round 2 (not a test): the experimental GEMM-only PSD projection (csrc/psd_sign.cuh,
-COSMO_B200_PSD_SIGN=1) against the block-Jacobi path on the same matrices -- accuracy vs the CPU oracle, wall time
+"""Measurement helper (not a test): the GEMM-only PSD projections (csrc/psd_tc.cuh on the tensor cores -- the default
+for N >= 192 -- and csrc/psd_sign.cuh on the FP64 FMA pipe) against the block-Jacobi path on the same matrices -- accuracy vs the CPU oracle, wall time
 of `Engine.project` (includes the host <-> device copies of the N(N+1)/2 vector) and the step counts printed by
 COSMO_B200_PSD_DEBUG=1.
 
@@ -52,15 +52,17 @@ for N in [int(a) for a in sys.argv[1:]] or [300, 1000, 2000]:
         O.project(ref, to_oracle_cones(sets))
         t_cpu = time.time() - t0
         row = {"N": N, "matrix": name, "cpu_dsyevr_s": round(t_cpu, 4)}
-        for mode in ("0", "1", "2"):      # block Jacobi / hand-written symmetric products / cuBLAS comparator
-            os.environ["COSMO_B200_PSD_SIGN"] = mode
+        for mode in ("0", "1", "tc"):     # block Jacobi (cold) / Newton-Schulz on the FP64 FMA pipe / on tcgen05 int8 slices
+            os.environ["COSMO_B200_PSD_SIGN"] = "1" if mode == "1" else "0"
+            os.environ["COSMO_B200_PSD_TC"] = "1" if mode == "tc" else "0"
+            os.environ["COSMO_B200_PSD_WARM"] = "0"
             eng = E.Engine(sp.identity(1, format="csc"), np.zeros(1), sp.csc_matrix((d, 1)), np.zeros(d),
                            [cosmo_b200.model.set_tuple(S) for S in sets], cosmo_b200.Settings(scaling=0).to_struct())
             eng.project(ws)                      # warm-up (allocations, first launches)
             t0 = time.time()
             got = eng.project(ws)
             dt = time.time() - t0
-            key = {"0": "jacobi", "1": "sign", "2": "sign_cublas"}[mode]
+            key = {"0": "jacobi_cold", "1": "sign_fp64fma", "tc": "sign_tc"}[mode]
             row[key + "_s"] = round(dt, 4)
             row[key + "_relerr"] = float(np.linalg.norm(got - ref) / (np.linalg.norm(ws) + 1e-300))
             eng.close()

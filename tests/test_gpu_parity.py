@@ -221,9 +221,6 @@ def test_project_psd_large_path(N):
     assert np.linalg.norm(got - ref) / np.linalg.norm(ws) < 1e-12
 
 
-@pytest.mark.skipif(os.environ.get("COSMO_B200_TEST_EXPERIMENTAL") != "1",
-                    reason="experimental GEMM-only PSD projection (csrc/psd_sign.cuh), written after the round-1 GPU budget was "
-                           "spent and not yet validated: run with COSMO_B200_TEST_EXPERIMENTAL=1")
 @pytest.mark.parametrize("kind", ["wigner", "rank_deficient", "shifted", "zero"])
 def test_project_psd_sign_function_path(kind, monkeypatch):
     # Pi_+(X) = (X + sign(X) X) / 2 with sign(X) by Newton-Schulz products; same bar as the eigensolver path
@@ -250,10 +247,87 @@ def test_project_psd_sign_function_path(kind, monkeypatch):
     assert np.linalg.norm(got - ref) / nrm < 1e-12
 
 
-@pytest.mark.skipif(os.environ.get("COSMO_B200_TEST_EXPERIMENTAL") != "1",
-                    reason="complex Hermitian PSD cones (real 2N x 2N embedding inside psd_small_kernel) were added after the "
-                           "round-1 GPU budget was spent; index maps validated by emulation only: run with "
-                           "COSMO_B200_TEST_EXPERIMENTAL=1")
+# ---------------------------------------------------------------------------
+# Tensor-core PSD path (csrc/tc_gemm.cuh, csrc/psd_tc.cuh): int8-sliced tcgen05 products + scaled Newton-Schulz
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("N,slices,bound", [(128, 8, 5e-15), (200, 8, 5e-15), (333, 8, 5e-15), (333, 7, 1e-12), (200, 4, 2e-6)])
+def test_tc_gemm_matches_dgemm(N, slices, bound):
+    # C = A B for commuting symmetric matrices; error measured against |A| |B| elementwise (the natural bound of a
+    # row-scaled fixed-point product); one row is 1000x smaller than the rest (per-row exponents)
+    rng = np.random.default_rng(N)
+    Gm = rng.standard_normal((N, N))
+    A = (Gm + Gm.T) / np.sqrt(2.0 * N)
+    A[0, :] *= 1e-3
+    A[:, 0] *= 1e-3
+    B = A @ A
+    B = (B + B.T) / 2
+    got, _, fr = E.tc_gemm(A, B, slices=slices)
+    ref = A @ B
+    assert np.max(np.abs(got - ref) / (np.abs(A) @ np.abs(B))) < bound
+    assert np.array_equal(got, got.T)                                   # mirrored store: exactly symmetric
+    assert abs(fr[0] - np.sum(got * got)) <= 1e-12 * np.sum(got * got)  # fused |C|_F^2
+    assert abs(fr[1] - np.sum((np.eye(N) - got) ** 2)) <= 1e-12 * np.sum((np.eye(N) - got) ** 2)
+
+
+def _psd_test_matrix(kind, N, rng):
+    B = rng.standard_normal((N, N))
+    if kind == "wigner":
+        return (B + B.T) / 2
+    if kind == "rank_deficient":
+        k = max(N // 10, 2)
+        return B[:, :k] @ B[:, :k].T - B[:, k:2 * k] @ B[:, k:2 * k].T
+    if kind == "shifted":
+        return (B + B.T) / 2 + 3.0 * np.sqrt(N) * np.eye(N)
+    if kind == "zero":
+        return np.zeros((N, N))
+    if kind == "admm_like":      # w_s = s - mu / rho near a solution: PSD part, scaled negative part, a cluster near zero
+        Q, _ = np.linalg.qr(B)
+        lam = np.concatenate([np.abs(rng.standard_normal(N // 3)), -10.0 * np.abs(rng.standard_normal(N // 3)),
+                              1e-7 * rng.standard_normal(N - 2 * (N // 3))])
+        return (Q * lam) @ Q.T
+    if kind == "graded":         # eigenvalues spread over 12 orders of magnitude, both signs
+        Q, _ = np.linalg.qr(B)
+        lam = np.logspace(0, -12, N) * np.where(np.arange(N) % 2 == 0, 1.0, -1.0)
+        return (Q * lam) @ Q.T
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind", ["wigner", "rank_deficient", "shifted", "zero", "admm_like", "graded"])
+@pytest.mark.parametrize("N", [200, 385])
+def test_project_psd_tensor_core_path(kind, N):
+    # same bar as the eigensolver path (|Pi_gpu - Pi_lapack|_F / |X|_F <= 1e-12), triangle and square cone,
+    # and the projection must really have come from the tensor-core path (no silent fallback)
+    rng = np.random.default_rng(1000 + N)
+    X = _psd_test_matrix(kind, N, rng)
+    sets = [cosmo_b200.PsdConeTriangle(N * (N + 1) // 2), cosmo_b200.PsdCone(N * N)]
+    ws = np.concatenate([G._svec(X), X.reshape(-1, order="F")])
+    m = ws.size
+    eng = _engine(sp.identity(1, format="csc"), np.zeros(1), sp.csc_matrix((m, 1)), np.zeros(m), sets)
+    ref = ws.copy()
+    O.project(ref, to_oracle_cones(sets))
+    got = eng.project(ws)
+    st = eng.psd_stats()
+    assert st["tc_projections"] == 2 and st["tc_fallbacks"] == 0, st
+    assert np.linalg.norm(got - ref) / (np.linalg.norm(ws) + 1e-300) < 1e-12, st
+
+
+def test_project_psd_tensor_core_path_float32():
+    # Model{Float32}: the oracle runs ssyevr (convexset.jl:163-165); 4 slices carry 2^-28, the bar is the fp32 one (1e-5)
+    rng = np.random.default_rng(77)
+    N = 256
+    X = _psd_test_matrix("wigner", N, rng).astype(np.float32)
+    sets = [cosmo_b200.PsdConeTriangle(N * (N + 1) // 2)]
+    ws = G._svec(X.astype(np.float64)).astype(np.float32)
+    m = ws.size
+    eng = _engine(sp.identity(1, format="csc"), np.zeros(1), sp.csc_matrix((m, 1)), np.zeros(m), sets, dtype=np.float32)
+    ref = ws.copy()
+    O.project(ref, to_oracle_cones(sets))
+    got = eng.project(ws)
+    st = eng.psd_stats()
+    assert st["tc_projections"] == 1 and st["tc_fallbacks"] == 0, st
+    assert np.linalg.norm(got.astype(np.float64) - ref) / np.linalg.norm(ws) < 1e-5
+
+
 def test_complex_psd_cone_projection_and_least_eigenvalue():
     # PsdConeTriangle{T, Complex{T}} (convexset.jl:344-360, 444-490): projection vs the Hermitian eigendecomposition of
     # the oracle at the real-PSD bar (1e-12), then least_eigenvalue.jl:33-39 (obj = 1 - sqrt 2 at 1e-4)
