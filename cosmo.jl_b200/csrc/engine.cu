@@ -1956,8 +1956,8 @@ int cosmo_b200_tc_gemm_test(int32_t N, int32_t k, int32_t kstep, int32_t gpb, co
     cosmo::tc::Sliced sa, sb;
     const size_t nn = (size_t)N * N;
     const double coef[3] = {1.0, 0.0, 0.0};
-    (void)kstep; (void)gpb;
-    bool ok = g.configure(k, st) && g.set_shape(N, st);
+    (void)gpb;
+    bool ok = g.configure(k, kstep > 0 ? kstep : (k == 8 ? 10 : (k == 7 ? 7 : k + 2)), st) && g.set_shape(N, st);
     ok = ok && cudaMalloc(&A_d, nn * 8) == cudaSuccess && cudaMalloc(&B_d, nn * 8) == cudaSuccess && cudaMalloc(&C_d, nn * 8) == cudaSuccess &&
          cudaMalloc(&coef_d, 3 * 8) == cudaSuccess && cudaMalloc(&part_d, (size_t)2 * (g.ntiles + 1) * 8) == cudaSuccess;
     ok = ok && sa.ensure(g.Np) && sb.ensure(g.Np) && sa.clear(g.Np, st) && sb.clear(g.Np, st);

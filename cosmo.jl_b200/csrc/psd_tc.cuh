@@ -5,7 +5,11 @@
 //     Pi_+(X) = (X + sign(X) X) / 2,      sign(X) by the scaled Newton-Schulz iteration
 //     S <- gamma S;  S <- S (3 I - S^2) / 2,    gamma = alpha / u,
 //         u     = min(1, |S^2|_F^(1/2)) >= rho(S)        (rigorous, a by-product of the product S^2)
-//         alpha = (3 / (1 + l + l^2))^(1/2)              (minimax cubic for a spectrum in [l, 1]; l <- g(alpha l))
+//         alpha = min(alpha_max, (3 / (1 + l + l^2))^(1/2))   (minimax cubic for a spectrum in [l, 1]; l <- g(alpha l))
+//     alpha_max = 1.5: the uncapped minimax scaling (alpha -> sqrt 3) folds the top of the spectrum down onto the
+//     bottom, which brings eigenvalues of opposite sign and large weight close together and amplifies the rounding
+//     errors of the products by 1 / l; with the cap the top never drops below g(1.5) = 0.56 while small eigenvalues
+//     still grow by 2.25 per step (plain Newton-Schulz: 1.5) -- measured: two more steps, 10x smaller error.
 //
 // Every step is two products of commuting symmetric matrices, evaluated by tc::OzakiGemm (int8 slices on tcgen05,
 // exact int32 accumulation in TMEM, fp64 Horner epilogue): Y = S S with fused |Y|_F^2 and |I - Y|_F^2, then
@@ -20,7 +24,8 @@
 
 namespace cosmo {
 
-// state[0..2] = coefficients of the update product, state[3] = l, state[4] = delta, state[5] = |Y|_F^2, state[6] = gamma
+// state[0..2] = coefficients of the update product, state[3] = l, state[4] = delta, state[5] = |Y|_F^2, state[6] = gamma,
+// state[7] = alpha_max
 template <int DUMMY = 0>
 __global__ void ns_coef_kernel(const double* __restrict__ partial, int ntiles, int N, double* __restrict__ state) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
@@ -33,10 +38,12 @@ __global__ void ns_coef_kernel(const double* __restrict__ partial, int ntiles, i
   } else {
     const double beta = sqrt(sqrt(f));                     // rho(S)^2 = rho(Y) <= |Y|_F
     const double u = beta < 1.0 ? beta : 1.0;
-    const double alpha = sqrt(3.0 / (1.0 + l + l * l));
+    double alpha = sqrt(3.0 / (1.0 + l + l * l));          // minimax cubic for a spectrum in [l, 1] ...
+    if (alpha > state[7]) alpha = state[7];                // ... capped: see the header
     gamma = alpha / u;
-    const double y = alpha * l;
-    l = 0.5 * y * (3.0 - y * y);
+    const double y = alpha * l, ya = alpha;
+    const double gl = 0.5 * y * (3.0 - y * y), gu = 0.5 * ya * (3.0 - ya * ya);
+    l = gl < gu ? gl : gu;
     if (l > 1.0) l = 1.0;
     state[4] = (beta < 1.0) ? 2.0 : sqrt(d / (double)N);   // the measure is void while the bound still tightens
   }
@@ -57,10 +64,11 @@ __global__ void ns_residual_kernel(const double* __restrict__ partial, int ntile
   state[4] = (*x2 > 0.0) ? sqrt(r / *x2) : 0.0;
 }
 
-// S = X / |X|_F; x2[0] = |X|_F^2 (from the load kernel's partial sums)
+// S = X / |X|_F (fp64, whatever the model type); x2[0] = |X|_F^2 (from the load kernel's partial sums); Xd: fp64 copy of
+// X when the model type is not fp64
 template <typename T>
 __global__ void __launch_bounds__(kBlock) ns_scale_kernel(int N, const T* __restrict__ X, const T* __restrict__ fro_partials, int nparts,
-                                                          T* __restrict__ S, double* __restrict__ x2) {
+                                                          double* __restrict__ S, double* __restrict__ Xd, double* __restrict__ x2) {
   __shared__ double sc_s;
   if (threadIdx.x == 0) {
     double f = 0.0;
@@ -71,41 +79,45 @@ __global__ void __launch_bounds__(kBlock) ns_scale_kernel(int N, const T* __rest
   __syncthreads();
   const double sc = sc_s;
   const long long total = (long long)N * N;
-  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x)
-    S[k] = (T)((double)X[k] * sc);
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+    const double x = (double)X[k];
+    S[k] = x * sc;
+    if (Xd) Xd[k] = x;
+  }
 }
 
 // s[cone] = svec / square layout of the symmetric matrix P (already (X + sign(X) X) / 2)
 template <typename T>
-__global__ void __launch_bounds__(kBlock) ns_store_kernel(PsdConeDesc d, const T* __restrict__ P, T* __restrict__ s) {
+__global__ void __launch_bounds__(kBlock) ns_store_kernel(PsdConeDesc d, const double* __restrict__ P, T* __restrict__ s) {
   const int N = d.N;
-  const T sqrt2 = T(1.41421356237309504880);
+  const double sqrt2 = 1.41421356237309504880;
   const long long total = (long long)N * N;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int i = (int)(e % N), j = (int)(e / N);
     if (i > j) continue;
-    const T v = P[e];
+    const double v = P[e];
     if (d.triangle) {
-      s[d.off + svec_pos(i, j)] = (i == j) ? v : sqrt2 * v;
+      s[d.off + svec_pos(i, j)] = (T)((i == j) ? v : sqrt2 * v);
     } else {
-      s[d.off + (long long)j * N + i] = v;
-      s[d.off + (long long)i * N + j] = v;   // mirror, convexset.jl:316-318
+      s[d.off + (long long)j * N + i] = (T)v;
+      s[d.off + (long long)i * N + j] = (T)v;   // mirror, convexset.jl:316-318
     }
   }
 }
 
 // W = 2 P - X  (the candidate S X recovered from P = (X + S X) / 2)
-template <typename T>
-__global__ void __launch_bounds__(kBlock) ns_w_from_p_kernel(long long total, const T* __restrict__ P, const T* __restrict__ X, T* __restrict__ W) {
+template <int DUMMY = 0>
+__global__ void __launch_bounds__(kBlock) ns_w_from_p_kernel(long long total, const double* __restrict__ P, const double* __restrict__ X,
+                                                             double* __restrict__ W) {
   for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x)
-    W[k] = T(2) * P[k] - X[k];
+    W[k] = 2.0 * P[k] - X[k];
 }
 
 template <typename T>
 struct PsdTc {
-  tc::OzakiGemm<T> gemm;
+  tc::OzakiGemm<double> gemm;     // the iteration runs in fp64 for every model type (fp32 iterates would cost accuracy, not time)
   tc::Sliced slS, slY, slX;
-  T *S1_d = nullptr, *U_d = nullptr;
+  double *S0_d = nullptr, *S1_d = nullptr, *U_d = nullptr, *Xd_d = nullptr;
   double *state_d = nullptr, *partial_d = nullptr, *const_d = nullptr, *x2_d = nullptr;
   double* state_h = nullptr;   // pinned
   int capN = 0, shapeN = 0;
@@ -115,7 +127,7 @@ struct PsdTc {
   std::string err;
 
   ~PsdTc() {
-    cudaFree(S1_d); cudaFree(U_d); cudaFree(state_d); cudaFree(partial_d); cudaFree(const_d); cudaFree(x2_d);
+    cudaFree(S0_d); cudaFree(S1_d); cudaFree(U_d); cudaFree(Xd_d); cudaFree(state_d); cudaFree(partial_d); cudaFree(const_d); cudaFree(x2_d);
     if (state_h) cudaFreeHost(state_h);
   }
   static int env_int(const char* name, int def) {
@@ -135,8 +147,10 @@ struct PsdTc {
 
   bool ensure(int N, cudaStream_t st) {
     if (!configured) {
-      const int k = env_int("COSMO_B200_TC_SLICES", sizeof(T) == 8 ? 8 : 4);
-      if (!gemm.configure(k, st)) { err = gemm.err; return false; }
+      // fp64 model: 8 slices, 10 groups (products exact to ~2^-56 of the row maxima); fp32 model: 6 slices, 8 groups (2^-42)
+      const int k = env_int("COSMO_B200_TC_SLICES", sizeof(T) == 8 ? 8 : 6);
+      const int g = env_int("COSMO_B200_TC_GROUPS", k == 8 ? 10 : (k == 7 ? 7 : k + 2));
+      if (!gemm.configure(k, g, st)) { err = gemm.err; return false; }
       bool ok = cudaMalloc(&state_d, 8 * sizeof(double)) == cudaSuccess && cudaMalloc(&const_d, 8 * sizeof(double)) == cudaSuccess &&
                 cudaMalloc(&x2_d, sizeof(double)) == cudaSuccess && cudaMallocHost(&state_h, 8 * sizeof(double)) == cudaSuccess;
       if (!ok) { err = "PsdTc: cudaMalloc"; return false; }
@@ -146,13 +160,15 @@ struct PsdTc {
       configured = true;
     }
     if (N > capN) {
-      cudaFree(S1_d); cudaFree(U_d); cudaFree(partial_d);
-      S1_d = U_d = nullptr; partial_d = nullptr;
+      cudaFree(S0_d); cudaFree(S1_d); cudaFree(U_d); cudaFree(Xd_d); cudaFree(partial_d);
+      S0_d = S1_d = U_d = Xd_d = nullptr; partial_d = nullptr;
       capN = 0;
       const size_t nn = (size_t)N * N;
       const int nt = (N + tc::kTile - 1) / tc::kTile;
-      bool ok = cudaMalloc(&S1_d, nn * sizeof(T)) == cudaSuccess && cudaMalloc(&U_d, nn * sizeof(T)) == cudaSuccess &&
+      bool ok = cudaMalloc(&S0_d, nn * sizeof(double)) == cudaSuccess && cudaMalloc(&S1_d, nn * sizeof(double)) == cudaSuccess &&
+                cudaMalloc(&U_d, nn * sizeof(double)) == cudaSuccess &&
                 cudaMalloc(&partial_d, (size_t)nt * (nt + 1) * sizeof(double)) == cudaSuccess;
+      if (sizeof(T) != 8) ok = ok && cudaMalloc(&Xd_d, nn * sizeof(double)) == cudaSuccess;
       const int Np = nt * tc::kTile;
       ok = ok && slS.ensure(Np) && slY.ensure(Np) && slX.ensure(Np);
       if (!ok) { err = "PsdTc: out of memory"; return false; }
@@ -169,38 +185,46 @@ struct PsdTc {
     return true;
   }
 
-  // X_d: N x N symmetric (ld = N), fro_partials: partial sums of |X|_F^2, S0_d: scratch N x N.  Writes the projection
-  // in the layout of the cone into s_out.
-  bool project(const PsdConeDesc& d, const T* X_d, const T* fro_partials, int nfro, T* S0_d, T* s_out, cudaStream_t st,
+  // X_in: N x N symmetric (ld = N) of the model type, fro_partials: partial sums of |X|_F^2.  Writes the projection in
+  // the layout of the cone into s_out.
+  bool project(const PsdConeDesc& d, const T* X_in, const T* fro_partials, int nfro, T* /*scratch*/, T* s_out, cudaStream_t st,
                long long& launches) {
     const int N = d.N;
     if (!ensure(N, st)) return false;
     const int g = (int)std::min<long long>(((long long)N * N + kBlock - 1) / kBlock, kMaxGrid);
     const int ntiles = gemm.ntiles;
     const double l0 = env_double("COSMO_B200_TC_L0", 1e-7);
-    const double tol = sizeof(T) == 8 ? 1e-7 : 3e-4;     // quadratic convergence: the step after delta < tol reaches ~delta^2
-    const double rtol = sizeof(T) == 8 ? 5e-13 : 2e-5;   // accepted weighted residual
+    const double alpha_max = env_double("COSMO_B200_TC_ALPHA_MAX", 1.5);
+    const double tol = 1e-7;                              // quadratic convergence: the step after delta < tol reaches ~delta^2
+    const double rtol = sizeof(T) == 8 ? 5e-13 : 1e-7;    // accepted weighted residual
     const int cap = env_int("COSMO_B200_TC_MAX_STEPS", 80);
     bool ok = true;
-    ns_scale_kernel<T><<<g, kBlock, 0, st>>>(N, X_d, fro_partials, nfro, S0_d, x2_d);
+    const double* X_d;
+    if (sizeof(T) == 8) {
+      X_d = reinterpret_cast<const double*>(X_in);
+      ns_scale_kernel<T><<<g, kBlock, 0, st>>>(N, X_in, fro_partials, nfro, S0_d, (double*)nullptr, x2_d);
+    } else {
+      X_d = Xd_d;
+      ns_scale_kernel<T><<<g, kBlock, 0, st>>>(N, X_in, fro_partials, nfro, S0_d, Xd_d, x2_d);
+    }
     {
-      double init[8] = {0, 0, 0, l0, 2.0, 0, 1.0, 0};
+      double init[8] = {0, 0, 0, l0, 2.0, 0, 1.0, alpha_max};
       memcpy(state_h, init, sizeof(init));
       ok = ok && cudaMemcpyAsync(state_d, state_h, 8 * sizeof(double), cudaMemcpyHostToDevice, st) == cudaSuccess;
     }
     ok = ok && gemm.slice(X_d, slX, st);
     launches += 2;
-    T* S = S0_d;
-    T* Sn = S1_d;
-    double prev = 1e300, resid = -1.0, delta = 2.0;
+    double* S = S0_d;
+    double* Sn = S1_d;
+    double prev = 1e300, resid = -1.0, prev_resid = 1e300, delta = 2.0;
     int it = 0, next_check = -1, checks = 0;
     bool have_P = false;
     for (;;) {
       ok = ok && gemm.slice(S, slS, st);
-      ok = ok && gemm.gemm(slS, slS, U_d, (const T*)nullptr, (const T*)nullptr, 1, const_d, partial_d, st);        // Y = S S
+      ok = ok && gemm.gemm(slS, slS, U_d, nullptr, nullptr, 1, const_d, partial_d, st);        // Y = S S
       ns_coef_kernel<0><<<1, 32, 0, st>>>(partial_d, ntiles, N, state_d);
       ok = ok && gemm.slice(U_d, slY, st);
-      ok = ok && gemm.gemm(slS, slY, Sn, S, (const T*)nullptr, 0, state_d, (double*)nullptr, st);                  // S' = c1 S + c0 S Y
+      ok = ok && gemm.gemm(slS, slY, Sn, S, nullptr, 0, state_d, nullptr, st);                  // S' = c1 S + c0 S Y
       launches += 5;
       if (!ok) { err = gemm.err; return false; }
       if (cudaMemcpyAsync(state_h, state_d, 8 * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) return false;
@@ -210,31 +234,32 @@ struct PsdTc {
       delta = state_h[4];
       if (!(delta == delta)) { err = "PsdTc: NaN"; return false; }
       if (delta < tol) break;
-      // the minimax schedule has run out (l ~ 1) and delta stalls: a cluster of (numerically) zero eigenvalues
+      // the scaling schedule has run out (l ~ 1) and delta stalls: a cluster of (numerically) zero eigenvalues
       const bool schedule_done = state_h[3] > 0.999;
       if (next_check < 0 && schedule_done) next_check = it + 1;
       if ((next_check >= 0 && it >= next_check && delta > 0.9 * prev) || it >= cap) {
         ok = ok && gemm.slice(S, slS, st);
-        ok = ok && gemm.gemm(slS, slX, U_d, X_d, (const T*)nullptr, 0, const_d + 3, (double*)nullptr, st);           // P = (X + S X) / 2
-        // residual of the candidate: W = S X = 2 P - X;  |S W - X| = |2 S P - S X - X| ... evaluated as S (2P - X) - X
-        // through one more product on the slices of W
+        ok = ok && gemm.gemm(slS, slX, U_d, X_d, nullptr, 0, const_d + 3, nullptr, st);           // P = (X + S X) / 2
         ok = ok && residual_of_candidate(X_d, Sn, st, launches);
+        launches += 2;
         if (!ok) { if (err.empty()) err = gemm.err; return false; }
         if (cudaMemcpyAsync(state_h, state_d, 8 * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) return false;
         if (cudaStreamSynchronize(st) != cudaSuccess) return false;
         resid = state_h[4];
         ++checks;
         if (!(resid == resid)) { err = "PsdTc: NaN"; return false; }
-        if (resid < rtol || (it >= cap && resid < 1e3 * rtol)) { have_P = true; break; }
+        // accept: below the tolerance, or within 100x of it and no longer improving (the floor of the arithmetic)
+        if (resid < rtol || (resid < 1e2 * rtol && resid > 0.5 * prev_resid)) { have_P = true; break; }
         if (it >= cap) { err = "PsdTc: no convergence"; return false; }
-        next_check = it + 4;
+        prev_resid = resid;
+        next_check = it + 3;
       }
       prev = delta;
     }
     last_steps = it; last_checks = checks; last_delta = delta; last_resid = resid;
     if (!have_P) {
       ok = ok && gemm.slice(S, slS, st);
-      ok = ok && gemm.gemm(slS, slX, U_d, X_d, (const T*)nullptr, 0, const_d + 3, (double*)nullptr, st);
+      ok = ok && gemm.gemm(slS, slX, U_d, X_d, nullptr, 0, const_d + 3, nullptr, st);
       launches += 2;
       if (!ok) { err = gemm.err; return false; }
     }
@@ -246,12 +271,12 @@ struct PsdTc {
   }
 
   // state[4] <- |S W - X|_F / |X|_F with W = 2 P - X, P in U_d, S sliced in slS.  Wbuf: scratch N x N.
-  bool residual_of_candidate(const T* X_d, T* Wbuf, cudaStream_t st, long long& launches) {
+  bool residual_of_candidate(const double* X_d, double* Wbuf, cudaStream_t st, long long& launches) {
     const int N = gemm.N;
     const int g = (int)std::min<long long>(((long long)N * N + kBlock - 1) / kBlock, kMaxGrid);
-    ns_w_from_p_kernel<T><<<g, kBlock, 0, st>>>((long long)N * N, U_d, X_d, Wbuf);
+    ns_w_from_p_kernel<0><<<g, kBlock, 0, st>>>((long long)N * N, U_d, X_d, Wbuf);
     bool ok = gemm.slice(Wbuf, slY, st);
-    ok = ok && gemm.gemm(slS, slY, (T*)nullptr, (const T*)nullptr, X_d, 0, const_d, partial_d, st);
+    ok = ok && gemm.gemm(slS, slY, nullptr, nullptr, X_d, 0, const_d, partial_d, st);
     ns_residual_kernel<0><<<1, 32, 0, st>>>(partial_d, gemm.ntiles, x2_d, state_d);
     launches += 4;
     return ok;

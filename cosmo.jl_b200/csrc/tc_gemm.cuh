@@ -53,31 +53,32 @@ constexpr int kEpiWarps = 8;
 // box is the operand tile of 4 slices at once, and the tile of slice j inside the box is addressed like the j-th
 // K sub-step of an ordinary 128-byte-swizzled K-major tile (descriptor start address + 32 j bytes).
 //
-// The product list is static.  With k slices the groups s = p + q run from k + 1 down to 2; a PASS owns the four TMEM
-// accumulators and covers the groups s_hi, s_hi - 1, s_hi - 2, s_hi - 3: pass 0 starts at k + 1, pass 1 at k - 3.
-// Every slice pair of a pass is issued per K step from one 64 KB stage, so an operand tile fetched once serves up
-// to 26 products.  Everything below is resolved at compile time (template parameter K): the issuing thread executes
-// two uniform adds and one UTCIMMA per product.
-__host__ __device__ constexpr int pass_s_hi(int k, int pass) { return k + 1 - 4 * pass; }
-__host__ __device__ constexpr int num_passes(int k) { return k <= 4 ? 1 : 2; }
-__host__ __device__ constexpr int pass_groups(int k, int pass) { return pass_s_hi(k, pass) - 1 < 4 ? pass_s_hi(k, pass) - 1 : 4; }
+// The product list is static.  With K slices and G groups the groups s = p + q run from G + 1 down to 2; a PASS owns
+// the four TMEM accumulators and covers the groups s_hi, s_hi - 1, s_hi - 2, s_hi - 3: pass 0 starts at G + 1, pass 1
+// at G - 3, ...  Every slice pair of a pass is issued per K step from the same operand boxes, so a tile fetched once
+// serves up to 28 products.  Everything below is resolved at compile time (template parameters K, G): the issuing
+// thread executes two uniform adds and one UTCIMMA per product.
+// G >= K is the number of groups kept: G = K is the classical truncation (error ~ K 2^-7K relative to the row maxima),
+// every further group gains 7 bits; G = K + 2 leaves only the truncation of the operands themselves (2^-7K per
+// element): with K = 8 the product is then more accurate than dgemm.
+__host__ __device__ constexpr int pass_s_hi(int g, int pass) { return g + 1 - 4 * pass; }
+__host__ __device__ constexpr int num_passes(int g) { return (g + 3) / 4; }
+__host__ __device__ constexpr int pass_groups(int g, int pass) { return pass_s_hi(g, pass) - 1 < 4 ? pass_s_hi(g, pass) - 1 : 4; }
 // bit 0: A slices 0-3, bit 1: A slices 4-7, bit 2: B slices 0-3, bit 3: B slices 4-7 (the same set for A and B by symmetry)
-__host__ __device__ constexpr int pass_box_mask(int k, int pass) {
+__host__ __device__ constexpr int pass_box_mask(int k, int g, int pass) {
   int m = 0;
-  for (int g = 0; g < pass_groups(k, pass); ++g)
+  for (int gi = 0; gi < pass_groups(g, pass); ++gi)
     for (int p = 1; p <= k; ++p) {
-      const int q = pass_s_hi(k, pass) - g - p;
+      const int q = pass_s_hi(g, pass) - gi - p;
       if (q >= 1 && q <= k) m |= (1 << ((p - 1) / 4)) | (4 << ((q - 1) / 4));
     }
   return m;
 }
-__host__ __device__ constexpr int pass_products(int k, int pass) {
+__host__ __device__ constexpr int total_products(int k, int g) {
   int n = 0;
-  for (int g = 0; g < pass_groups(k, pass); ++g)
-    for (int p = 1; p <= k; ++p) {
-      const int q = pass_s_hi(k, pass) - g - p;
-      if (q >= 1 && q <= k) ++n;
-    }
+  for (int s = 2; s <= g + 1; ++s)
+    for (int p = 1; p <= k; ++p)
+      if (s - p >= 1 && s - p <= k) ++n;
   return n;
 }
 
@@ -210,10 +211,10 @@ struct GemmArgs {
 };
 
 // all slice-pair products of one pass for one K step (compile-time list)
-template <int K, int PASS>
+template <int K, int G, int PASS>
 __device__ __forceinline__ void issue_pass_products(uint32_t sbase16, uint32_t tmem_base, int ks) {
-  constexpr int S_HI = pass_s_hi(K, PASS);
-  constexpr int NG = pass_groups(K, PASS);
+  constexpr int S_HI = pass_s_hi(G, PASS);
+  constexpr int NG = pass_groups(G, PASS);
 #pragma unroll
   for (int p = 1; p <= K; ++p) {       // ordered by A slice: consecutive products share the A tile
 #pragma unroll
@@ -234,12 +235,12 @@ struct PipeState { int unit; uint32_t phase; };   // position in the ring of kUn
 
 // a pass needs the slices 4-7 of either operand <=> it occupies two ring units per K step (kUnits is even and the
 // number of K steps is even, so a two-unit step never wraps inside)
-__host__ __device__ constexpr int pass_units(int k, int pass) { return (pass_box_mask(k, pass) & 0xA) ? 2 : 1; }
+__host__ __device__ constexpr int pass_units(int k, int g, int pass) { return (pass_box_mask(k, g, pass) & 0xA) ? 2 : 1; }
 
-template <int K, int PASS>
+template <int K, int G, int PASS>
 __device__ __forceinline__ void producer_pass(const CUtensorMap* tmapA, const CUtensorMap* tmapB, uint8_t* smem, uint64_t* full_bar,
                                               uint64_t* empty_bar, int nk, int m0, int n0, PipeState& st) {
-  constexpr int NU = pass_units(K, PASS);
+  constexpr int NU = pass_units(K, G, PASS);
   for (int ks = 0; ks < nk; ++ks) {
 #pragma unroll
     for (int h = 0; h < NU; ++h) {
@@ -257,10 +258,10 @@ __device__ __forceinline__ void producer_pass(const CUtensorMap* tmapA, const CU
   }
 }
 
-template <int K, int PASS>
+template <int K, int G, int PASS>
 __device__ __forceinline__ void mma_pass(uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar, uint64_t* tfull_bar, uint64_t* tempty_bar,
                                          uint32_t tmem_base, int nk, PipeState& st, uint32_t& tphase) {
-  constexpr int NU = pass_units(K, PASS);
+  constexpr int NU = pass_units(K, G, PASS);
   mbar_wait(tempty_bar, tphase ^ 1);      // the epilogue has drained the accumulators of the previous pass
   tc_fence_after();
   for (int ks = 0; ks < nk; ++ks) {
@@ -269,7 +270,7 @@ __device__ __forceinline__ void mma_pass(uint8_t* smem, uint64_t* full_bar, uint
     tc_fence_after();
     if (elect_one()) {
       const uint32_t sbase16 = (smem_u32(smem) + (uint32_t)st.unit * kUnitBytes) >> 4;
-      issue_pass_products<K, PASS>(sbase16, tmem_base, ks);
+      issue_pass_products<K, G, PASS>(sbase16, tmem_base, ks);
       tc_commit(&empty_bar[st.unit]);
       if (NU == 2) tc_commit(&empty_bar[st.unit + 1]);
       if (ks == nk - 1) tc_commit(tfull_bar);
@@ -282,11 +283,11 @@ __device__ __forceinline__ void mma_pass(uint8_t* smem, uint64_t* full_bar, uint
 }
 
 // fold the accumulators of one pass into the fp64 registers: acc += 128^-(s-2) G_s, exactly converted
-template <int K, int PASS>
+template <int G, int PASS>
 __device__ __forceinline__ void epilogue_pass(double (&acc)[64], uint32_t tlane, uint64_t* tfull_bar, uint64_t* tempty_bar, uint32_t& tphase,
                                               int lane) {
-  constexpr int S_HI = pass_s_hi(K, PASS);
-  constexpr int NG = pass_groups(K, PASS);
+  constexpr int S_HI = pass_s_hi(G, PASS);
+  constexpr int NG = pass_groups(G, PASS);
   mbar_wait(tfull_bar, tphase);
   tphase ^= 1;
   tc_fence_after();
@@ -308,7 +309,7 @@ __device__ __forceinline__ void epilogue_pass(double (&acc)[64], uint32_t tlane,
   if (lane == 0) mbar_arrive(tempty_bar);
 }
 
-template <typename T, int K>
+template <typename T, int K, int G>
 __global__ void __launch_bounds__(kThreads, 1) ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmapA,
                                                                  const __grid_constant__ CUtensorMap tmapB, const GemmArgs<T> args) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -343,8 +344,9 @@ __global__ void __launch_bounds__(kThreads, 1) ozaki_gemm_kernel(const __grid_co
     for (int t = blockIdx.x; t < args.ntiles; t += gridDim.x) {
       const int2 tl = args.tiles[t];
       const int m0 = tl.x * kTile, n0 = tl.y * kTile;
-      producer_pass<K, 0>(&tmapA, &tmapB, smem, full_bar, empty_bar, nk, m0, n0, st);
-      if (num_passes(K) > 1) producer_pass<K, (num_passes(K) > 1 ? 1 : 0)>(&tmapA, &tmapB, smem, full_bar, empty_bar, nk, m0, n0, st);
+      producer_pass<K, G, 0>(&tmapA, &tmapB, smem, full_bar, empty_bar, nk, m0, n0, st);
+      if (num_passes(G) > 1) producer_pass<K, G, (num_passes(G) > 1 ? 1 : 0)>(&tmapA, &tmapB, smem, full_bar, empty_bar, nk, m0, n0, st);
+      if (num_passes(G) > 2) producer_pass<K, G, (num_passes(G) > 2 ? 2 : 0)>(&tmapA, &tmapB, smem, full_bar, empty_bar, nk, m0, n0, st);
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
@@ -352,8 +354,9 @@ __global__ void __launch_bounds__(kThreads, 1) ozaki_gemm_kernel(const __grid_co
     PipeState st{0, 0};
     uint32_t tphase = 0;
     for (int t = blockIdx.x; t < args.ntiles; t += gridDim.x) {
-      mma_pass<K, 0>(smem, full_bar, empty_bar, &tfull_bar, &tempty_bar, tmem_base, nk, st, tphase);
-      if (num_passes(K) > 1) mma_pass<K, (num_passes(K) > 1 ? 1 : 0)>(smem, full_bar, empty_bar, &tfull_bar, &tempty_bar, tmem_base, nk, st, tphase);
+      mma_pass<K, G, 0>(smem, full_bar, empty_bar, &tfull_bar, &tempty_bar, tmem_base, nk, st, tphase);
+      if (num_passes(G) > 1) mma_pass<K, G, (num_passes(G) > 1 ? 1 : 0)>(smem, full_bar, empty_bar, &tfull_bar, &tempty_bar, tmem_base, nk, st, tphase);
+      if (num_passes(G) > 2) mma_pass<K, G, (num_passes(G) > 2 ? 2 : 0)>(smem, full_bar, empty_bar, &tfull_bar, &tempty_bar, tmem_base, nk, st, tphase);
     }
   } else if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -373,8 +376,9 @@ __global__ void __launch_bounds__(kThreads, 1) ozaki_gemm_kernel(const __grid_co
       double acc[64];
 #pragma unroll
       for (int j = 0; j < 64; ++j) acc[j] = 0.0;
-      epilogue_pass<K, 0>(acc, tlane, &tfull_bar, &tempty_bar, tphase, lane);
-      if (num_passes(K) > 1) epilogue_pass<K, (num_passes(K) > 1 ? 1 : 0)>(acc, tlane, &tfull_bar, &tempty_bar, tphase, lane);
+      epilogue_pass<G, 0>(acc, tlane, &tfull_bar, &tempty_bar, tphase, lane);
+      if (num_passes(G) > 1) epilogue_pass<G, (num_passes(G) > 1 ? 1 : 0)>(acc, tlane, &tfull_bar, &tempty_bar, tphase, lane);
+      if (num_passes(G) > 2) epilogue_pass<G, (num_passes(G) > 2 ? 2 : 0)>(acc, tlane, &tfull_bar, &tempty_bar, tphase, lane);
       // ---- final epilogue of the tile ----
       double r0 = 0.0, r1 = 0.0;
       const int N = args.N;
@@ -485,26 +489,31 @@ template <typename T>
 struct OzakiGemm {
   int2* tiles_d = nullptr;
   int tilesNp = 0, ntiles = 0;
-  int k = 8, num_sms = 148;
+  int k = 8, g = 10, num_sms = 148;
   int N = 0, Np = 0;
   bool ready = false;
   std::string err;
   ~OzakiGemm() { cudaFree(tiles_d); }
 
   static constexpr int smem_bytes() { return kUnits * kUnitBytes + 1024; }
-  template <int K>
+  // supported (slices, groups): (8, 10) exact-fp64 default, (8, 8) and (7, 7) classical truncations, (6, 8) and (4, 6)
+  // for the fp32 model type
+  template <int K, int G>
   static bool set_attr() {
-    return cudaFuncSetAttribute(ozaki_gemm_kernel<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes()) == cudaSuccess;
+    return cudaFuncSetAttribute(ozaki_gemm_kernel<T, K, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes()) == cudaSuccess;
   }
-  bool configure(int k_, cudaStream_t st) {
+  static bool supported(int k_, int g_) {
+    return (k_ == 8 && (g_ == 10 || g_ == 8)) || (k_ == 7 && g_ == 7) || (k_ == 6 && g_ == 8) || (k_ == 4 && g_ == 6);
+  }
+  bool configure(int k_, int g_, cudaStream_t st) {
     (void)st;
-    k = k_;
-    if (k < 3 || k > kSlices) { err = "tc::OzakiGemm: 3 <= slices <= 8"; return false; }
+    if (!supported(k_, g_)) { err = "tc::OzakiGemm: unsupported (slices, groups)"; return false; }
+    k = k_; g = g_;
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     // per device, every time: function attributes are per device and cheap to set
-    if (!(set_attr<3>() && set_attr<4>() && set_attr<5>() && set_attr<6>() && set_attr<7>() && set_attr<8>())) {
+    if (!(set_attr<8, 10>() && set_attr<8, 8>() && set_attr<7, 7>() && set_attr<6, 8>() && set_attr<4, 6>())) {
       err = "cudaFuncSetAttribute(ozaki_gemm_kernel)";
       return false;
     }
@@ -543,14 +552,11 @@ struct OzakiGemm {
     a.tiles = tiles_d; a.scaleA = A.scale; a.scaleB = B.scale; a.out = out; a.D = D; a.E = E; a.e_identity = e_identity;
     a.coef = coef_d; a.partial = partial;
     const int grid = std::min(ntiles, num_sms);
-    switch (k) {
-      case 3: ozaki_gemm_kernel<T, 3><<<grid, kThreads, smem_bytes(), st>>>(A.map, B.map, a); break;
-      case 4: ozaki_gemm_kernel<T, 4><<<grid, kThreads, smem_bytes(), st>>>(A.map, B.map, a); break;
-      case 5: ozaki_gemm_kernel<T, 5><<<grid, kThreads, smem_bytes(), st>>>(A.map, B.map, a); break;
-      case 6: ozaki_gemm_kernel<T, 6><<<grid, kThreads, smem_bytes(), st>>>(A.map, B.map, a); break;
-      case 7: ozaki_gemm_kernel<T, 7><<<grid, kThreads, smem_bytes(), st>>>(A.map, B.map, a); break;
-      default: ozaki_gemm_kernel<T, 8><<<grid, kThreads, smem_bytes(), st>>>(A.map, B.map, a); break;
-    }
+    if (k == 8 && g == 10) ozaki_gemm_kernel<T, 8, 10><<<grid, kThreads, smem_bytes(), st>>>(A.map, B.map, a);
+    else if (k == 8) ozaki_gemm_kernel<T, 8, 8><<<grid, kThreads, smem_bytes(), st>>>(A.map, B.map, a);
+    else if (k == 7) ozaki_gemm_kernel<T, 7, 7><<<grid, kThreads, smem_bytes(), st>>>(A.map, B.map, a);
+    else if (k == 6) ozaki_gemm_kernel<T, 6, 8><<<grid, kThreads, smem_bytes(), st>>>(A.map, B.map, a);
+    else ozaki_gemm_kernel<T, 4, 6><<<grid, kThreads, smem_bytes(), st>>>(A.map, B.map, a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("ozaki_gemm_kernel launch: ") + cudaGetErrorString(e); return false; }
     return true;

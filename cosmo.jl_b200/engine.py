@@ -376,7 +376,7 @@ class Engine:
         return dict(zip(keys, [int(v) for v in out]))
 
 
-def tc_gemm(A, B, slices=8, kstep=0, gpb=0, reps=0):
+def tc_gemm(A, B, slices=8, groups=0, reps=0):
     """C = A @ B for symmetric commuting fp64 matrices through the int8-sliced tcgen05 product kernel
     (diagnostic entry `cosmo_b200_tc_gemm_test`).  Returns (C, ms_per_product, (|C|_F^2, |I - C|_F^2))."""
     lib = load_library()
@@ -387,7 +387,7 @@ def tc_gemm(A, B, slices=8, kstep=0, gpb=0, reps=0):
     Cm = np.zeros((N, N), dtype=np.float64, order="F")
     ms = C.c_double(0.0)
     fr = (C.c_double * 2)()
-    rc = lib.cosmo_b200_tc_gemm_test(N, slices, kstep, gpb, A.ctypes.data, B.ctypes.data, Cm.ctypes.data, reps,
+    rc = lib.cosmo_b200_tc_gemm_test(N, slices, groups, 0, A.ctypes.data, B.ctypes.data, Cm.ctypes.data, reps,
                                      C.byref(ms), fr)
     if rc != 0:
         raise EngineError(rc, (lib.cosmo_b200_last_error(None) or b"").decode())

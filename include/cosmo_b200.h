@@ -250,10 +250,11 @@ int cosmo_b200_comm_p2p_attach(cosmo_b200_handle* h, const void* blobs, int32_t 
 int cosmo_b200_psd_stats(cosmo_b200_handle* h, int64_t out[8]);
 /* The product kernel of the large-cone PSD projection on its own: C = A B for symmetric, commuting N x N fp64
    matrices (column-major) through `k` int8 slices on tcgen05 (csrc/tc_gemm.cuh; the reference's counterpart is the
-   BLAS-3 part of project!(::PsdCone), convexset.jl:244-260).  kstep in {32, 64, 128} bytes of K per stage tile,
-   gpb in {1, 2, 4} slice groups per TMEM batch.  frob2 = {|C|_F^2, |I - C|_F^2} from the fused reductions.
+   BLAS-3 part of project!(::PsdCone), convexset.jl:244-260).  `groups` = number of slice-pair groups kept
+   (0: the default of `k`); supported (k, groups): (8,10) (8,8) (7,7) (6,8) (4,6); `reserved` must be 0.
+   frob2 = {|C|_F^2, |I - C|_F^2} from the fused reductions.
    No handle: uses the current device.  Errors through cosmo_b200_last_error(NULL). */
-int cosmo_b200_tc_gemm_test(int32_t N, int32_t k, int32_t kstep, int32_t gpb, const double* A, const double* B, double* C,
+int cosmo_b200_tc_gemm_test(int32_t N, int32_t k, int32_t groups, int32_t reserved, const double* A, const double* B, double* C,
                             int32_t reps, double* ms_per_product, double* frob2);
 
 #ifdef __cplusplus

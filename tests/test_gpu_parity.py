@@ -250,8 +250,9 @@ def test_project_psd_sign_function_path(kind, monkeypatch):
 # ---------------------------------------------------------------------------
 # Tensor-core PSD path (csrc/tc_gemm.cuh, csrc/psd_tc.cuh): int8-sliced tcgen05 products + scaled Newton-Schulz
 # ---------------------------------------------------------------------------
-@pytest.mark.parametrize("N,slices,bound", [(128, 8, 5e-15), (200, 8, 5e-15), (333, 8, 5e-15), (333, 7, 1e-12), (200, 4, 2e-6)])
-def test_tc_gemm_matches_dgemm(N, slices, bound):
+@pytest.mark.parametrize("N,slices,groups,bound", [(128, 8, 10, 2e-15), (200, 8, 10, 2e-15), (333, 8, 10, 2e-15), (333, 8, 8, 5e-15),
+                                                   (333, 7, 7, 1e-12), (200, 6, 8, 1e-11), (200, 4, 6, 2e-7)])
+def test_tc_gemm_matches_dgemm(N, slices, groups, bound):
     # C = A B for commuting symmetric matrices; error measured against |A| |B| elementwise (the natural bound of a
     # row-scaled fixed-point product); one row is 1000x smaller than the rest (per-row exponents)
     rng = np.random.default_rng(N)
@@ -261,7 +262,7 @@ def test_tc_gemm_matches_dgemm(N, slices, bound):
     A[:, 0] *= 1e-3
     B = A @ A
     B = (B + B.T) / 2
-    got, _, fr = E.tc_gemm(A, B, slices=slices)
+    got, _, fr = E.tc_gemm(A, B, slices=slices, groups=groups)
     ref = A @ B
     assert np.max(np.abs(got - ref) / (np.abs(A) @ np.abs(B))) < bound
     assert np.array_equal(got, got.T)                                   # mirrored store: exactly symmetric
@@ -312,7 +313,9 @@ def test_project_psd_tensor_core_path(kind, N):
 
 
 def test_project_psd_tensor_core_path_float32():
-    # Model{Float32}: the oracle runs ssyevr (convexset.jl:163-165); 4 slices carry 2^-28, the bar is the fp32 one (1e-5)
+    # Model{Float32}: the oracle runs ssyevr (convexset.jl:163-165); the bar is the fp32 one of SURVEY 8c-i (1e-5).  The
+    # reference's own fp32 path is only ~N eps32 accurate, so the engine (fp64 iterates inside) is also held against the
+    # fp64 projection: it must not be worse than the reference's fp32 path.
     rng = np.random.default_rng(77)
     N = 256
     X = _psd_test_matrix("wigner", N, rng).astype(np.float32)
@@ -325,7 +328,13 @@ def test_project_psd_tensor_core_path_float32():
     got = eng.project(ws)
     st = eng.psd_stats()
     assert st["tc_projections"] == 1 and st["tc_fallbacks"] == 0, st
-    assert np.linalg.norm(got.astype(np.float64) - ref) / np.linalg.norm(ws) < 1e-5
+    truth = ws.astype(np.float64)
+    O.project(truth, to_oracle_cones(sets))
+    nrm = np.linalg.norm(ws.astype(np.float64))
+    err_engine = np.linalg.norm(got.astype(np.float64) - truth) / nrm
+    err_ref32 = np.linalg.norm(ref.astype(np.float64) - truth) / nrm
+    assert err_engine <= max(err_ref32, 2e-7), (err_engine, err_ref32)
+    assert np.linalg.norm(got.astype(np.float64) - ref) / nrm < 1e-5 + err_ref32
 
 
 def test_complex_psd_cone_projection_and_least_eigenvalue():
