@@ -14,10 +14,13 @@ CG reduced-KKT solver, scaling=0, fixed rho, EmptyAccelerator.
             (times.iter_time / iter) excludes as well; it is reported as setup_s.
   roofline  dominant kernel = the CSR SpMV t = rho.*(A u): algorithmic bytes
             (12 B/nnz + vectors) / CUDA-event time per launch.
-  cpu_baseline  the oracle port (oracle/cosmo_oracle.py) on this box's host cores,
-            bounded sample of the same workload.
+  cpu_baseline  the oracle port (oracle/cosmo_oracle.py) on this box's host cores (sparse products of
+            the KKT operator on all OpenMP threads), bounded sample of the same workload, setup excluded.
+  parity    the engine's operator variable w against the oracle's after the same iterations on the
+            identical arrays at full size (bound 1e-8).
 
-`--impl reference` times the oracle port (the reference cannot run here: no Julia).
+`--impl reference` times the oracle port for the same K steps / W warm-up (the reference itself cannot run
+here: no Julia; it has no C sources to compile).
 """
 import argparse
 import json
@@ -110,26 +113,32 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def oracle_iterations(P, q, A, b, sets, iters, warm):
-    """Time `iters` ADMM iterations of the oracle port after `warm` untimed ones (same settings)."""
-    import cosmo_b200
+def oracle_iterations(P, q, A, b, sets, iters, warm, keep_w_at=None):
+    """Time `iters` ADMM iterations of the oracle port after `warm` >= 1 untimed ones (same settings as the engine).
+    setup() (the reference's setup!, excluded from its own iter_time too) runs before the clock starts; the sparse
+    products of the KKT operator run on all host threads (oracle/fast_matvec.py), everything else is the oracle as is.
+    Returns (seconds, iterations, mean CG iterations, host threads, w after `keep_w_at` iterations or None)."""
     from oracle import cosmo_oracle as O
+    from oracle import fast_matvec as F
     from oracle.bridge import to_oracle_cones
     cones = to_oracle_cones(sets)
-    marks = {}
+    warm = max(1, warm)
+    marks, kept = {}, {}
 
     def cb(it, ws):
         marks[it] = time.perf_counter()
+        if keep_w_at is not None and it == keep_w_at:
+            kept["w"] = ws.w.copy()
 
     st = O.Settings(kkt_solver="cg", scaling=0, adaptive_rho=False, max_iter=warm + iters, eps_abs=0.0, eps_rel=0.0,
                     check_termination=25, check_infeasibility=40)
     ws = O.Workspace(P, q, A, b, cones, st)
-    t0 = time.perf_counter()
+    ws.setup()
+    F.threaded(ws)
     res = ws.optimize(iter_callback=cb)
-    tstart = marks[warm] if warm >= 1 else t0
-    dt = marks[warm + iters] - tstart
+    dt = marks[warm + iters] - marks[warm]
     inner = res.kkt.inner_iterations
-    return dt, iters, float(np.mean(inner)) if inner else 0.0
+    return dt, iters, float(np.mean(inner)) if inner else 0.0, F.max_threads(), kept.get("w")
 
 
 def host_cores():
@@ -144,21 +153,29 @@ def run_reference(a, rank, world):
         return
     import cosmo_b200
     P, q, A, b, sets = cosmo_b200.problems.random_sparse_qp(a.n, a.m, a.density, a.seed)
-    # bounded sample: SciPy's compiled single-threaded CSC mat-vec, like Julia's SparseArrays.mul!
-    scale = (a.n * a.m * a.density) / 5e7
-    cap = max(2, int(8 / max(scale, 1e-3))) if scale > 0.2 else 200
-    iters = max(1, min(a.steps, cap))
-    warm = max(0, min(a.warmup, 1 if scale > 0.2 else a.warmup))
-    dt, iters, cg = oracle_iterations(P, q, A, b, sets, iters, warm)
+    # Same K steps and W warm-up iterations as the engine arm.  One ADMM iteration of C2 is ~110 sparse products of
+    # 5e7 nonzeros: ~0.5 s on the host threads of a GPU box; the budget guard below only bites on small hosts.
+    iters, warm = max(1, a.steps), max(1, a.warmup)
+    budget_s = float(os.environ.get("COSMO_B200_REF_BUDGET_S", "420"))
+    t0 = time.perf_counter()
+    dt1, _, _, _, _ = oracle_iterations(P, q, A, b, sets, 1, 1)          # probe: one timed iteration after one warm-up
+    probe_s = time.perf_counter() - t0
+    capped = False
+    if (iters + warm) * dt1 > budget_s:
+        iters = max(1, int(budget_s / dt1) - warm)
+        capped = True
+    dt, iters, cg, threads, _ = oracle_iterations(P, q, A, b, sets, iters, warm)
     val = iters / dt
-    sample = "%d ADMM iterations after %d warm-up (of the requested %d/%d), oracle port: SciPy CSC mat-vec, 1 thread" % (
-        iters, warm, a.steps, a.warmup)
+    sample = ("%d ADMM iterations after %d warm-up iterations (requested %d/%d%s), the reference loop restated in "
+              "NumPy (oracle/cosmo_oracle.py) with the sparse products of the KKT operator on %d OpenMP threads "
+              "(oracle/spmv_omp.c); setup excluded like in the reference's iter_time" % (
+                  iters, warm, a.steps, a.warmup, ", capped by the %.0f s budget" % budget_s if capped else "", threads))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": iters,
             "warmup": warm, "ms_per_step": 1e3 * dt / iters, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(a, {"cg_iters_per_admm_iter": cg}),
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
-                             "host_cores_available": host_cores()},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                             "host_cores_available": host_cores(), "probe_s": probe_s},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -265,11 +282,14 @@ def main():
             peak = 6650.0
         ach_A = bytes_A / (ms_A * 1e-3) / 1e9
         ach_At = bytes_At / (ms_At * 1e-3) / 1e9
+        # dram__bytes_read + dram__bytes_write of this kernel from the committed `ncu --set full` capture of the same
+        # single-GPU command (profiles/): meaningful only for the unsharded matrix, null otherwise
         traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "spmv_traffic.json"))).get("dram_bytes_per_launch")
-        except Exception:
-            pass
+        if world == 1 and (a.n, a.m, a.density) == (50_000, 100_000, 0.01):
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "spmv_traffic.json"))).get("dram_bytes_per_launch")
+            except Exception:
+                pass
         cg = out.kkt_inner_iterations / max(out.iter, 1)
         line = {"metric": METRIC, "value": a.steps / dev_s, "unit": UNIT, "n_gpus": world, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": 1e3 * dev_s / a.steps, "higher_is_better": True,
@@ -280,7 +300,10 @@ def main():
                         "h2d_bytes_per_step": 8.0 * (n + m_loc + n + 2 * m_loc) / a.steps,
                         "d2h_bytes_per_step": 8.0 * (n + 2 * m_loc) / a.steps,
                         "note": "update_qb + warm_start + solve(K iterations) + result download, host pinned buffers; "
-                                "model upload (setup!) excluded like in the reference's iter_time"},
+                                "model upload (setup!) excluded like in the reference's iter_time",
+                        "with_setup": {"value": a.steps / (e2e_s + setup_s), "unit": UNIT, "setup_s": setup_s,
+                                       "note": "time to solution of a cold model: engine creation (CSC->CSR, slabs, "
+                                               "upload) + the K iterations"}},
                 "gpu_launches": int(out.kernel_launches),
                 "clocks": clocks,
                 "roofline": {"bound": "hbm", "kernel": "spmv_win_kernel<double,EpiScale> (t = rho.*(A u), x staged in smem by TMA bulk copy)",
@@ -293,11 +316,24 @@ def main():
         if not a.no_cpu_baseline and world == 1:
             scale = (a.n * a.m * a.density) / 5e7
             it_cpu = a.cpu_sample_iters if scale > 0.2 else 50
-            dt, iters, cgc = oracle_iterations(P, q, A, b, sets, it_cpu, 0)
-            line["cpu_baseline"] = {"value": iters / dt, "unit": UNIT, "cores": 1, "kind": "port",
-                                    "sample": "first %d ADMM iterations of the same workload (cold start, %.1f CG its/iter), "
-                                              "oracle port: SciPy CSC mat-vec single thread like SparseArrays.mul!" % (iters, cgc),
+            k_par = 1 + it_cpu                      # compare w after the oracle's warm-up + sampled iterations
+            dt, iters, cgc, threads, w_ref = oracle_iterations(P, q, A, b, sets, it_cpu, 1, keep_w_at=k_par)
+            line["cpu_baseline"] = {"value": iters / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "%d ADMM iterations of the same workload after 1 warm-up iteration (setup "
+                                              "excluded, %.1f CG its/iter), oracle port with the KKT operator's sparse "
+                                              "products on %d OpenMP threads" % (iters, cgc, threads),
                                     "host_cores_available": host_cores()}
+            # parity on the identical arrays at full size: operator variable w after the same number of iterations
+            st = cosmo_b200.Settings(scaling=0, adaptive_rho=False, max_iter=k_par, eps_abs=0.0, eps_rel=0.0).to_struct()
+            eng.update_settings(st)
+            eng.reset()
+            eng.warm_start(hx0, hs0, hmu0)
+            eng.solve(ox, os_, omu)
+            w_gpu = eng.w()
+            rel = float(np.max(np.abs(w_gpu - w_ref)) / max(np.max(np.abs(w_ref)), 1e-300)) if w_ref is not None else None
+            line["parity"] = {"what": "max |w_engine - w_oracle| / max |w_oracle| after %d ADMM iterations on the identical "
+                                      "(P, q, A, b, K) at full size" % k_par,
+                              "value": rel, "bound": 1e-8, "ok": bool(rel is not None and rel <= 1e-8)}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -978,10 +978,12 @@ void Engine<T>::launch_spmv(const DevCsr<T>& M1, const T* x1, const DevCsr<T>* M
   const CsrView<T> v2 = M2 ? M2->view() : CsrView<T>{nullptr, nullptr, nullptr};
   if (M1.windowed) {
     const size_t smem = (size_t)M1.W * sizeof(T);
-    static bool configured = false;   // one flag per (T, Epi) instantiation
-    if (!configured) {
+    // function attributes are per device: one flag per (T, Epi) instantiation AND device ordinal
+    static bool configured[64] = {false};
+    const int dev_slot = device_ & 63;
+    if (!configured[dev_slot] || device_ >= 64) {
       CUDA_TRY(cudaFuncSetAttribute(spmv_win_kernel<T, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204800));
-      configured = true;
+      configured[dev_slot] = true;
     }
     spmv_win_kernel<T, Epi><<<M1.nctas, kWinThreads, smem, stream_>>>(M1.wview(), x1, v2, x2, epi, rb, ypart_.p,
                                                                       chunk_ticket_.p);

@@ -800,7 +800,10 @@ struct PsdBatch {
       ck(cudaMalloc(&small_d, small_h.size() * sizeof(PsdConeDesc)), "cudaMalloc psd descs");
       ck(cudaMemcpyAsync(small_d, small_h.data(), small_h.size() * sizeof(PsdConeDesc), cudaMemcpyHostToDevice, st), "copy psd descs");
       ck(cudaMalloc(&lam_small_d, small_h.size() * sizeof(T)), "cudaMalloc lam");
-      const size_t smem = small_smem();
+      // the attribute belongs to the function on the device, not to this engine: always raise it to the worst case
+      // of kPsdSmallMax, or a second engine with smaller cones would lower the limit under a live one
+      const size_t ld_max = (size_t)(kPsdSmallMax | 1);
+      const size_t smem = (2 * ld_max * kPsdSmallMax + 2 * (size_t)(kPsdSmallMax / 2 + 2)) * sizeof(T);
       ck(cudaFuncSetAttribute(psd_small_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
     }
     ck(cudaMalloc(&fail_d, sizeof(int)), "cudaMalloc fail flag");

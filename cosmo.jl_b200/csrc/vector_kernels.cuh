@@ -536,8 +536,8 @@ __global__ void __launch_bounds__(kBlock) minres_update_kernel(int L, int it_hos
 //   s_tl = 2 s - w_s - nu ./ rho ; w_s += alpha (s_tl - s)         (solver.jl:55,64)
 template <typename T>
 __global__ void __launch_bounds__(kBlock) admm_tail_kernel(int m, const T* __restrict__ nu, const T* __restrict__ rho,
-                                                           const T* __restrict__ s, const T* __restrict__ ws_in,
-                                                           T* __restrict__ ws_out, T alpha) {
+                                                           const T* __restrict__ s, const T* ws_in,
+                                                           T* ws_out, T alpha) {   // ws_in may alias ws_out (after a rho adaptation)
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
     const T sr = s[i], w = ws_in[i];
     const T s_tl = T(2) * sr - w - nu[i] / rho[i];

@@ -1,0 +1,69 @@
+"""Multi-threaded sparse mat-vec for the CPU reference arm -- TEST / BENCH INFRASTRUCTURE, NOT THE PRODUCT.
+
+``threaded(ws)`` swaps the sparse operators of an oracle ``Workspace`` (after ``setup()``) for row-parallel CSR
+kernels (oracle/spmv_omp.c, OpenMP): the oracle's arithmetic is unchanged per row, rows run on all host threads.
+Only bench.py (``--impl reference`` and ``cpu_baseline``) and tests/ may import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import scipy.sparse as sp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "spmv_omp.c")
+LIB = os.path.join(HERE, "_build", "liboracle_spmv.so")
+_lib = None
+
+
+def build(force=False):
+    """gcc -O3 -fopenmp the C restatement (called by __graft_entry__.build())."""
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(SRC):
+        return LIB
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    subprocess.check_call(["gcc", "-O3", "-march=x86-64-v2", "-fopenmp", "-shared", "-fPIC", "-o", LIB, SRC])
+    return LIB
+
+
+def load():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB)
+        _lib.oracle_csr_matvec.argtypes = [C.c_int64] + [C.c_void_p] * 5
+        _lib.oracle_csr_matvec.restype = None
+        _lib.oracle_spmv_max_threads.restype = C.c_int
+    return _lib
+
+
+def max_threads():
+    return int(load().oracle_spmv_max_threads())
+
+
+class ThreadedCsr:
+    """Duck-types the two things the oracle does with a sparse matrix: ``M @ x`` and ``M.shape``."""
+
+    def __init__(self, M):
+        M = sp.csr_matrix(M)
+        M.sort_indices()
+        self.shape = M.shape
+        self.indptr = np.ascontiguousarray(M.indptr, dtype=np.int32)
+        self.indices = np.ascontiguousarray(M.indices, dtype=np.int32)
+        self.data = np.ascontiguousarray(M.data, dtype=np.float64)
+        self._lib = load()
+
+    def __matmul__(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty(self.shape[0], dtype=np.float64)
+        self._lib.oracle_csr_matvec(self.shape[0], self.indptr.ctypes.data, self.indices.ctypes.data, self.data.ctypes.data,
+                                    x.ctypes.data, y.ctypes.data)
+        return y
+
+
+def threaded(ws):
+    """Replace the operators of the KKT solver of an oracle Workspace (call after ws.setup())."""
+    k = ws.kkt
+    A = k.A
+    k.A, k.At, k.P = ThreadedCsr(A), ThreadedCsr(sp.csr_matrix(A.T)), ThreadedCsr(k.P)
+    return ws
