@@ -85,6 +85,40 @@ struct NcclApi {
 static NcclApi g_nccl;
 constexpr int kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2;
 
+// ---- phase timers (ResultTimes.proj_time / kkt_time, types.jl:26-41) ------------
+// CUDA events on the engine stream around a phase; elapsed times are harvested in batches so that the loop never
+// waits for a timer (one event synchronisation per kCap phases).
+struct PhaseTimer {
+  static constexpr int kCap = 64;
+  cudaEvent_t a[kCap], b[kCap];
+  int n = 0;
+  bool created = false, on = false;
+  double total_ms = 0.0;
+  ~PhaseTimer() {
+    if (created) for (int i = 0; i < kCap; ++i) { cudaEventDestroy(a[i]); cudaEventDestroy(b[i]); }
+  }
+  void enable(bool e) {
+    on = e;
+    if (on && !created) {
+      for (int i = 0; i < kCap; ++i) { cudaEventCreate(&a[i]); cudaEventCreate(&b[i]); }
+      created = true;
+    }
+    n = 0; total_ms = 0.0;
+  }
+  void begin(cudaStream_t st) { if (on) cudaEventRecord(a[n], st); }
+  void end(cudaStream_t st) {
+    if (!on) return;
+    cudaEventRecord(b[n], st);
+    if (++n == kCap) harvest();
+  }
+  void harvest() {
+    if (!on || n == 0) return;
+    cudaEventSynchronize(b[n - 1]);
+    for (int i = 0; i < n; ++i) { float ms = 0.f; cudaEventElapsedTime(&ms, a[i], b[i]); total_ms += ms; }
+    n = 0;
+  }
+};
+
 // ---- device buffer -----------------------------------------------------------
 template <typename U>
 struct DevBuf {
@@ -201,6 +235,8 @@ class Engine : public EngineBase {
  private:
   // ---- problem ----
   int n_ = 0, m_ = 0, device_ = 0;
+  double create_time_ = 0.0;      // engine construction (the device part of setup!)
+  int auto_rho_interval_ = 0;     // adaptive_rho_interval chosen by the automatic rule (kept across solves like settings)
   cosmo_b200_settings st_;
   bool scaled_ = false;
   double c_ = 1.0;
@@ -218,6 +254,7 @@ class Engine : public EngineBase {
   DevBuf<int> soc_off_, soc_dim_, soc_chunk_start_, soc_chunk_len_, soc_cone_chunk_ptr_;
   DevBuf<T> soc_norm_, soc_chunk_sum_, soc_norm2_;
   PsdBatch<T> psd_;
+  PhaseTimer t_proj_, t_kkt_;
   int n_c3_ = 0;             // exponential / power cones and their duals (cone3.cuh)
   DevBuf<int> c3_off_, c3_maxit_;
   DevBuf<unsigned char> c3_kind_;
@@ -597,8 +634,8 @@ Engine<T>::Engine(const cosmo_b200_problem& p, const cosmo_b200_settings& st) : 
   n_ = (int)p.n; m_ = (int)p.m; device_ = p.device;
   if (p.A.nrows != p.m || p.A.ncols != p.n) throw EngineError{COSMO_B200_ERR_INVALID, "A must be m x n"};
   if (p.P.nrows != p.n || p.P.ncols != p.n) throw EngineError{COSMO_B200_ERR_INVALID, "P must be n x n"};
-  if (st.adaptive_rho && st.adaptive_rho_interval <= 0)
-    throw EngineError{COSMO_B200_ERR_UNSUPPORTED, "adaptive_rho_interval = 0 (wall-clock rule) is decided on the host; pass an interval > 0"};
+  if (st.adaptive_rho && st.adaptive_rho_interval < 0) throw EngineError{COSMO_B200_ERR_INVALID, "adaptive_rho_interval < 0"};
+  const double t_ctor0 = now_s();
   int ndev = 0;
   cudaError_t de = cudaGetDeviceCount(&ndev);
   if (de != cudaSuccess || ndev == 0)
@@ -796,6 +833,8 @@ Engine<T>::Engine(const cosmo_b200_problem& p, const cosmo_b200_settings& st) : 
   rho_ = st_.rho;
   classify_and_set_rho(true);
   sync();
+  create_time_ = now_s() - t_ctor0;
+  auto_rho_interval_ = 0;
 }
 
 template <typename T>
@@ -1541,15 +1580,26 @@ void Engine<T>::solve(cosmo_b200_result* out) {
   ws_from_mu_kernel<T><<<vgrid(m), kBlock, 0, stream_>>>(m, rho_vec_.p, mu_.p, s_.p, W_[cur_].p + n);
   check_launch("ws_from_mu");
   is_optimized_ = true;
+  // phase timers: on request (verbose & 2 = settings.verbose_timing) and for every problem that is not latency-bound
+  {
+    const bool timers = (st_.verbose & 2) != 0 || (long long)n + m >= 20000 || !psd_.large_h.empty();
+    t_proj_.enable(timers);
+    t_kkt_.enable(timers);
+  }
   CUDA_TRY(cudaEventRecord(ev0_, stream_));
   const double iter_start = now_s();
+  // setup time as the reference counts it (ws.times.setup_time): the host's figure when it reports one (it then includes
+  // the creation of this engine), else the engine's own creation time
+  const double setup_time_total = st_.setup_time > 0.0 ? st_.setup_time : create_time_;
 
   // x-step + w-step reading W[src], writing W[dst]
   auto xw_step = [&](int src, int dst, bool do_proj, const T* ws_override) {
     const T* w = W_[src].p;
     const T* ws_rhs = ws_override ? ws_override : w + n;
     if (do_proj) {
-      project_device(w, true, ws_rhs);
+      t_proj_.begin(stream_);
+      project_device(w, true, ws_rhs);      // admm_z! fused with the right-hand side of admm_x! (one pass over w)
+      t_proj_.end(stream_);
     } else {
       ProjRhsArgs<T> a;
       a.n = n; a.m = m; a.w = w; a.ws_rhs = ws_rhs; a.q = q_.p; a.b = b_.p; a.rho = rho_vec_.p;
@@ -1561,7 +1611,9 @@ void Engine<T>::solve(cosmo_b200_result* out) {
     }
     // the tail reads w_s from ws_rhs's buffer and writes W[dst] (elementwise, may alias)
     T* wd = W_[dst].p;
+    t_kkt_.begin(stream_);
     kkt_core(true, ws_override ? (ws_override - n) : w, wd);
+    t_kkt_.end(stream_);
     wx_update_kernel<T><<<vgrid(n), kBlock, 0, stream_>>>(n, w, xsol_.p, (T)st_.alpha, wd);
     check_launch("wx_update");
   };
@@ -1595,12 +1647,24 @@ void Engine<T>::solve(cosmo_b200_result* out) {
     // w_prev = w (solver.jl:151): the current buffer becomes w_prev, the other one receives w_{k+1}
     const int src = cur_, dst = 1 - cur_;
     // rho adaptation rules (solver.jl:242-282)
-    if (st_.adaptive_rho && st_.adaptive_rho_interval > 0 && (iter % st_.adaptive_rho_interval) == 0 &&
+    // automatic interval (solver.jl:244-256): once the loop has run for adaptive_rho_fraction * setup_time, fix the
+    // interval at the current iteration count rounded to a multiple of check_termination (at least one multiple)
+    if (st_.adaptive_rho && st_.adaptive_rho_interval == 0 && auto_rho_interval_ == 0 &&
+        (now_s() - iter_start) > st_.adaptive_rho_fraction * setup_time_total) {
+      const long long N = st_.check_termination > 0 ? st_.check_termination : 25;
+      const double xr = (double)iter + 0.5 * (double)N;            // round_multiple, algebra.jl:245-247
+      const long long rm = (long long)floor(xr - fmod(xr, (double)N));
+      auto_rho_interval_ = (int)std::max<long long>(rm, N);
+    }
+    const int rho_interval = st_.adaptive_rho_interval > 0 ? st_.adaptive_rho_interval : auto_rho_interval_;
+    if (st_.adaptive_rho && rho_interval > 0 && (iter % rho_interval) == 0 &&
         (long long)(rho_updates_.size() - 1) < st_.adaptive_rho_max_adaptions)
       rho_update_due = true;
     if (suggested(rho_update_due)) {
       rho_update_due = false;
+      t_proj_.begin(stream_);
       project_device(W_[src].p, false, nullptr);          // admm_z!
+      t_proj_.end(stream_);
       recover_mu(W_[src].p);                               // w_prev == w here
       const double t0 = now_s();
       const bool adapted = adapt_rho(W_[src].p);
@@ -1644,7 +1708,7 @@ void Engine<T>::solve(cosmo_b200_result* out) {
       res_time += now_s() - t0;
       cost = info[4];
       if (fabs(cost) > 1e20) { status = COSMO_B200_UNSOLVED; break; }
-      if (st_.verbose) printf("%lld\t%.4e\t%.4e\t%.4e\t%.4e\n", iter, cost, info[0], info[1], rho_);
+      if (st_.verbose & 1) printf("%lld\t%.4e\t%.4e\t%.4e\t%.4e\n", iter, cost, info[0], info[1], rho_);
       if (info[0] < st_.eps_abs + st_.eps_rel * info[2] && info[1] < st_.eps_abs + st_.eps_rel * info[3]) {
         status = COSMO_B200_SOLVED;
         break;
@@ -1662,7 +1726,8 @@ void Engine<T>::solve(cosmo_b200_result* out) {
       if (primal_infeasible()) { status = COSMO_B200_PRIMAL_INFEASIBLE; cost = INFINITY; break; }
       if (dual_infeasible()) { status = COSMO_B200_DUAL_INFEASIBLE; cost = -INFINITY; break; }
     }
-    if (st_.time_limit != 0 && (now_s() - iter_start) > st_.time_limit) {
+    // the reference's clock starts before setup! (time_limit_start, solver.jl:119,349)
+    if (st_.time_limit != 0 && (now_s() - iter_start) + setup_time_total > st_.time_limit) {
       recover_mu(W_[prev_].p);
       compute_residuals(W_[prev_].p, s_.p, mu_.p, false, info);
       status = COSMO_B200_TIME_LIMIT_REACHED;
@@ -1701,11 +1766,13 @@ void Engine<T>::solve(cosmo_b200_result* out) {
     out->n_rho_updates = (int64_t)rho_updates_.size();
     if (out->rho_updates)
       for (int64_t i = 0; i < std::min<int64_t>(out->rho_updates_cap, out->n_rho_updates); ++i) out->rho_updates[i] = rho_updates_[i];
-    out->setup_time = 0.0;
+    out->setup_time = create_time_;   // the device part of setup!; the host adds its own
     out->iter_time = iter_time;
     out->iter_time_device = dev_ms * 1e-3;
-    out->proj_time = 0.0;
-    out->kkt_time = 0.0;
+    t_proj_.harvest();
+    t_kkt_.harvest();
+    out->proj_time = t_proj_.total_ms * 1e-3;   // device time of admm_z! (+ the fused rhs pass); 0 when the timers are off
+    out->kkt_time = t_kkt_.total_ms * 1e-3;     // device time of the KKT solves incl. the fused ADMM tail
     out->res_time = res_time;
     out->kkt_inner_iterations = total_inner_;
     out->kkt_multiplications = total_mults_;
@@ -1841,6 +1908,7 @@ int cosmo_b200_default_settings(cosmo_b200_settings* s) {
   s->eps_abs = 1e-5; s->eps_rel = 1e-5; s->eps_prim_inf = 1e-4; s->eps_dual_inf = 1e-4;
   s->max_iter = 5000; s->check_termination = 25; s->check_infeasibility = 40;
   s->scaling = 10; s->adaptive_rho = 1; s->adaptive_rho_interval = 40; s->kkt_solver = COSMO_B200_KKT_CG;
+  s->adaptive_rho_fraction = 0.4; s->setup_time = 0.0;
   s->adaptive_rho_tolerance = 5.0; s->adaptive_rho_max_adaptions = INT64_MAX;
   s->RHO_MIN = 1e-6; s->RHO_MAX = 1e6; s->RHO_TOL = 1e-4; s->RHO_EQ_OVER_RHO_INEQ = 1e3;
   s->COSMO_INFTY = 1e20; s->MIN_SCALING = 1e-4;

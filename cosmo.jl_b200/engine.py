@@ -61,7 +61,8 @@ class SettingsStruct(C.Structure):
                 ("time_limit", C.c_double), ("tol_constant", C.c_double), ("tol_exponent", C.c_double),
                 ("verbose", C.c_int32), ("psd_max_sweeps", C.c_int32),
                 ("accelerator", C.c_int32), ("accelerator_mem", C.c_int32), ("accelerator_min_mem", C.c_int32),
-                ("safeguard", C.c_int32), ("safeguard_tol", C.c_double)]
+                ("safeguard", C.c_int32), ("safeguard_tol", C.c_double),
+                ("adaptive_rho_fraction", C.c_double), ("setup_time", C.c_double)]
 
 
 class ResultStruct(C.Structure):

@@ -221,6 +221,7 @@ class Settings:
     eps_dual_inf: float = 1e-4
     max_iter: int = 5000
     verbose: bool = False
+    verbose_timing: bool = False             # settings.jl:43: here it forces the device phase timers (proj_time, kkt_time)
     kkt_solver: str = "CGIndirectKKTSolver"   # the engine implements the indirect family only
     check_termination: int = 25
     check_infeasibility: int = 40
@@ -228,7 +229,8 @@ class Settings:
     MIN_SCALING: float = 1e-4
     MAX_SCALING: float = 1e4
     adaptive_rho: bool = True
-    adaptive_rho_interval: int = 40
+    adaptive_rho_interval: int = 40           # 0: automatic (a fraction of the setup time, solver.jl:244-256)
+    adaptive_rho_fraction: float = 0.4
     adaptive_rho_tolerance: float = 5.0
     adaptive_rho_max_adaptions: int = 2 ** 62
     RHO_MIN: float = 1e-6
@@ -276,10 +278,11 @@ class Settings:
                      "check_termination", "check_infeasibility", "scaling", "adaptive_rho_interval",
                      "adaptive_rho_tolerance", "adaptive_rho_max_adaptions", "RHO_MIN", "RHO_MAX", "RHO_TOL",
                      "RHO_EQ_OVER_RHO_INEQ", "COSMO_INFTY", "MIN_SCALING", "time_limit", "tol_constant",
-                     "tol_exponent", "psd_max_sweeps", "accelerator_mem", "accelerator_min_mem", "safeguard_tol"):
+                     "tol_exponent", "psd_max_sweeps", "accelerator_mem", "accelerator_min_mem", "safeguard_tol",
+                     "adaptive_rho_fraction"):
             setattr(s, name, getattr(self, name))
         s.adaptive_rho = int(self.adaptive_rho)
-        s.verbose = int(self.verbose)
+        s.verbose = int(bool(self.verbose)) | (2 if self.verbose_timing else 0)
         s.kkt_solver = self._KKT[self.kkt_solver]
         s.accelerator = _eng.ACC_ANDERSON if self.accelerator == "AndersonAccelerator" else _eng.ACC_EMPTY
         s.safeguard = int(self.safeguard)
@@ -547,6 +550,10 @@ class Model:
             raise RuntimeError("The model has to be assembled! / set! before optimize!() can be called.")
         t0 = time.perf_counter()
         setup_time = self._setup()
+        if self.settings.time_limit != 0 or (self.settings.adaptive_rho and self.settings.adaptive_rho_interval == 0):
+            st = self.settings.to_struct()           # both rules count setup! (solver.jl:119,244-256,349)
+            st.setup_time = setup_time
+            self.engine.update_settings(st)
         out = self.engine.solve()
         # reverse_scaling! (scaling.jl:170-179)
         x = self.D * out.x.astype(np.float64)

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define COSMO_B200_ABI_VERSION 2
+#define COSMO_B200_ABI_VERSION 3
 
 typedef struct cosmo_b200_handle cosmo_b200_handle;
 
@@ -140,14 +140,15 @@ typedef struct {
   int32_t check_termination, check_infeasibility;
   int32_t scaling; /* != 0: residuals are unscaled with Einv / cinv*Dinv (residuals.jl:43-49) */
   int32_t adaptive_rho;
-  int32_t adaptive_rho_interval; /* must be > 0 (0 = wall-clock rule, solver.jl:244-256, is host-side) */
+  int32_t adaptive_rho_interval; /* 0 = automatic: chosen once (time in the loop) > adaptive_rho_fraction * setup_time,
+                                    rounded to a multiple of check_termination (solver.jl:244-256) */
   int32_t kkt_solver;            /* COSMO_B200_KKT_* */
   double adaptive_rho_tolerance;
   int64_t adaptive_rho_max_adaptions;
   double RHO_MIN, RHO_MAX, RHO_TOL, RHO_EQ_OVER_RHO_INEQ, COSMO_INFTY, MIN_SCALING;
   double time_limit;
   double tol_constant, tol_exponent; /* kktsolver_indirect.jl:21,168-170 */
-  int32_t verbose;
+  int32_t verbose;                   /* bit 0: settings.verbose (iteration log), bit 1: settings.verbose_timing */
   int32_t psd_max_sweeps;            /* Jacobi eigensolver sweep cap (engine-specific) */
   /* accelerator (settings.jl:96-98,136-138; accelerator_interface.jl:58-114) */
   int32_t accelerator;         /* COSMO_B200_ACC_EMPTY | COSMO_B200_ACC_ANDERSON (Type2{QRDecomp}, RestartedMemory,
@@ -156,6 +157,12 @@ typedef struct {
   int32_t accelerator_min_mem; /* columns needed before a candidate is formed (package default 3) */
   int32_t safeguard;           /* settings.safeguard */
   double safeguard_tol;        /* settings.safeguard_tol (2.0) */
+  /* ABI 3 */
+  double adaptive_rho_fraction; /* settings.adaptive_rho_fraction (0.4), used by the automatic interval rule */
+  double setup_time;            /* seconds the host spent in setup! (ws.times.setup_time: scaling, decomposition, the creation
+                                   of this engine); 0: the engine uses its own creation time.  Feeds the automatic rho
+                                   interval and the time limit, which the reference measures from before setup!
+                                   (solver.jl:119,349) */
 } cosmo_b200_settings;
 
 /* COSMO.Result / ResultInfo / ResultTimes (types.jl:26-41, 65-71, 93-112) */
@@ -176,7 +183,10 @@ typedef struct {
   double* rho_updates;      /* optional caller buffer for ws.rho_updates */
   int64_t rho_updates_cap;
   int64_t n_rho_updates;
-  /* times in seconds */
+  /* times in seconds (ResultTimes, types.jl:26-41).  proj_time = device time of admm_z! (solver.jl:15,152; here fused
+     with the right-hand side of admm_x!), kkt_time = device time of the KKT solves incl. the fused ADMM tail: CUDA
+     events on the engine stream, filled when settings.verbose bit 1 is set or the problem is not latency-bound
+     (n + m >= 20000 or a large PSD cone), 0 otherwise; res_time = host time inside the termination checks. */
   double solver_time, setup_time, iter_time, proj_time, kkt_time, res_time;
   double iter_time_device; /* the loop timed with CUDA events on the engine stream */
   /* statistics */

@@ -26,7 +26,7 @@ def test_header_symbols_exported():
     for name in declared:
         assert hasattr(lib, name), name
     assert sorted(E.EXPORTS) == declared
-    assert lib.cosmo_b200_abi_version() == 2
+    assert lib.cosmo_b200_abi_version() == 3
 
 
 def test_default_settings_match_reference():
@@ -44,7 +44,7 @@ def test_struct_sizes():
     assert ctypes.sizeof(E.CscStruct) == 40
     assert ctypes.sizeof(E.SetStruct) == 48
     assert ctypes.sizeof(E.ProblemStruct) == 16 + 16 + 80 + 16 + 16 + 32 + 8
-    assert ctypes.sizeof(E.SettingsStruct) == 56 + 8 + 24 + 16 + 48 + 24 + 8 + 24
+    assert ctypes.sizeof(E.SettingsStruct) == 56 + 8 + 24 + 16 + 48 + 24 + 8 + 24 + 16   # ABI 3: adaptive_rho_fraction, setup_time
     assert ctypes.sizeof(E.ResultStruct) == 24 + 24 + 8 + 40 + 24 + 56 + 24
 
 
@@ -142,7 +142,7 @@ def test_c_header_layout_matches_ctypes_mirror(tmp_path):
             assert getattr(mirror[st], field).offset == int(v), k
             checked += 1
     assert checked >= 35
-    assert vals["abi"] == "2" and vals["defaults"] == "0.1 1e-06 1.6 5000 0 15 2"
+    assert vals["abi"] == "3" and vals["defaults"] == "0.1 1e-06 1.6 5000 0 15 2"
     assert int(vals["create_null"]) == E.ERR_INVALID and "null" in vals["last_error"]
 
 

@@ -841,3 +841,28 @@ def test_simple_statuses_and_warm_start():
     assert r1.status == "Solved" and r2.status == "Solved" and np.max(np.abs(r2.x - r1.x)) < 1e-3
     with pytest.raises(ValueError):
         m2.warm_start_primal(rng.random(4))
+
+
+def test_automatic_rho_interval_and_result_times():
+    """settings.adaptive_rho_interval = 0 (solver.jl:244-256): the interval is fixed once the loop has run for
+    adaptive_rho_fraction * setup_time, rounded to a multiple of check_termination; ResultTimes.proj_time / kkt_time
+    (types.jl:26-41) are filled from device timers under verbose_timing."""
+    P, q, A, b, sets = cosmo_b200.problems.random_sparse_qp(400, 700, 0.05, seed=3)
+    model = cosmo_b200.Model()
+    model.set(P, q, A, b, sets, cosmo_b200.Settings(adaptive_rho=True, adaptive_rho_interval=0, adaptive_rho_fraction=1e-9,
+                                                    check_termination=25, verbose_timing=True, scaling=0))
+    res = model.optimize()
+    ref = O.solve(P, q, A, b, to_oracle_cones(sets), O.Settings(kkt_solver="cg", scaling=0, adaptive_rho_interval=25))
+    assert res.status == "Solved"
+    # with a vanishing fraction the rule fires at iteration 1: interval = max(round_multiple(1, 25), 25) = 25, i.e. the
+    # run is the oracle's run with adaptive_rho_interval = 25
+    assert res.iter == ref.iter and len(res.info.rho_updates) == len(ref.info.rho_updates)
+    assert np.allclose(res.info.rho_updates, ref.info.rho_updates, rtol=1e-6)
+    assert abs(res.obj_val - ref.obj_val) <= 1e-6 * max(1.0, abs(ref.obj_val))
+    t = res.times
+    assert t["proj_time"] > 0 and t["kkt_time"] > 0 and t["proj_time"] + t["kkt_time"] <= 1.05 * t["iter_time_device"]
+    # never firing: fraction so large that the interval stays automatic -> no rho update at all
+    model2 = cosmo_b200.Model()
+    model2.set(P, q, A, b, sets, cosmo_b200.Settings(adaptive_rho=True, adaptive_rho_interval=0, adaptive_rho_fraction=1e9, scaling=0))
+    res2 = model2.optimize()
+    assert len(res2.info.rho_updates) == 1
