@@ -138,7 +138,7 @@ def oracle_iterations(P, q, A, b, sets, iters, warm, keep_w_at=None):
     res = ws.optimize(iter_callback=cb)
     dt = marks[warm + iters] - marks[warm]
     inner = res.kkt.inner_iterations
-    return dt, iters, float(np.mean(inner)) if inner else 0.0, F.max_threads(), kept.get("w")
+    return dt, iters, float(np.mean(inner)) if inner else 0.0, F.threads_in_use(), kept.get("w")
 
 
 def host_cores():
@@ -156,7 +156,7 @@ def run_reference(a, rank, world):
     # Same K steps and W warm-up iterations as the engine arm.  One ADMM iteration of C2 is ~110 sparse products of
     # 5e7 nonzeros: ~0.5 s on the host threads of a GPU box; the budget guard below only bites on small hosts.
     iters, warm = max(1, a.steps), max(1, a.warmup)
-    budget_s = float(os.environ.get("COSMO_B200_REF_BUDGET_S", "420"))
+    budget_s = float(os.environ.get("COSMO_B200_REF_BUDGET_S", "240"))
     t0 = time.perf_counter()
     dt1, _, _, _, _ = oracle_iterations(P, q, A, b, sets, 1, 1)          # probe: one timed iteration after one warm-up
     probe_s = time.perf_counter() - t0
@@ -168,7 +168,7 @@ def run_reference(a, rank, world):
     val = iters / dt
     sample = ("%d ADMM iterations after %d warm-up iterations (requested %d/%d%s), the reference loop restated in "
               "NumPy (oracle/cosmo_oracle.py) with the sparse products of the KKT operator on %d OpenMP threads "
-              "(oracle/spmv_omp.c); setup excluded like in the reference's iter_time" % (
+              "(oracle/spmv_omp.c; thread count calibrated on this host); setup excluded like in the reference's iter_time" % (
                   iters, warm, a.steps, a.warmup, ", capped by the %.0f s budget" % budget_s if capped else "", threads))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": iters,
             "warmup": warm, "ms_per_step": 1e3 * dt / iters, "higher_is_better": True, "scaling": "strong",

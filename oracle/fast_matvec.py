@@ -30,7 +30,11 @@ def load():
     global _lib
     if _lib is None:
         build()
+        os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")   # idle workers must not spin: the host may be over-subscribed
+        os.environ.setdefault("OMP_PROC_BIND", "false")
         _lib = C.CDLL(LIB)
+        _lib.oracle_spmv_set_threads.argtypes = [C.c_int]
+        _lib.oracle_spmv_set_threads.restype = None
         _lib.oracle_csr_matvec.argtypes = [C.c_int64] + [C.c_void_p] * 5
         _lib.oracle_csr_matvec.restype = None
         _lib.oracle_spmv_max_threads.restype = C.c_int
@@ -61,9 +65,45 @@ class ThreadedCsr:
         return y
 
 
+_threads = None
+
+
+def calibrate(M, candidates=None, reps=2):
+    """Pick the thread count that is actually fastest for y = M x on this host (a container can see 128 cores and be
+    allowed 8): returns (threads, seconds per product).  The choice is kept for all later products."""
+    import time
+    global _threads
+    lib = load()
+    T = M if isinstance(M, ThreadedCsr) else ThreadedCsr(M)
+    ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cand = candidates or [t for t in (1, 2, 4, 8, 16, 32, 64, 128, 256) if t <= ncores]
+    x = np.ones(T.shape[1])
+    best = (None, float("inf"))
+    for t in cand:
+        lib.oracle_spmv_set_threads(t)
+        T @ x                                   # start the team
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            T @ x
+        dt = (time.perf_counter() - t0) / reps
+        if dt < best[1]:
+            best = (t, dt)
+    _threads = best[0]
+    lib.oracle_spmv_set_threads(_threads)
+    return best
+
+
+def threads_in_use():
+    return _threads if _threads is not None else max_threads()
+
+
 def threaded(ws):
-    """Replace the operators of the KKT solver of an oracle Workspace (call after ws.setup())."""
+    """Replace the operators of the KKT solver of an oracle Workspace (call after ws.setup()); the first call
+    calibrates the thread count on the workspace's own A."""
     k = ws.kkt
     A = k.A
-    k.A, k.At, k.P = ThreadedCsr(A), ThreadedCsr(sp.csr_matrix(A.T)), ThreadedCsr(k.P)
+    TA = ThreadedCsr(A)
+    if _threads is None:
+        calibrate(TA)
+    k.A, k.At, k.P = TA, ThreadedCsr(sp.csr_matrix(A.T)), ThreadedCsr(k.P)
     return ws

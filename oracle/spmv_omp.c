@@ -21,11 +21,24 @@ void oracle_csr_matvec(int64_t nrows, const int32_t* indptr, const int32_t* indi
   }
 }
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
 int oracle_spmv_max_threads(void) {
 #ifdef _OPENMP
-  extern int omp_get_max_threads(void);
   return omp_get_max_threads();
 #else
   return 1;
+#endif
+}
+
+/* number of threads of the following mat-vecs (bench.py calibrates it: a container's CPU quota can be far below the
+   number of cores it sees) */
+void oracle_spmv_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
 #endif
 }
