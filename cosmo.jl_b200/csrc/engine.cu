@@ -29,6 +29,7 @@
 #include "aa.cuh"
 #include "spmv.cuh"
 #include "vector_kernels.cuh"
+#include "ruiz.cuh"
 #include "cg_persistent.cuh"
 
 namespace cosmo {
@@ -201,6 +202,7 @@ class EngineBase {
   virtual void get_rho_vec(void* out) = 0;
   virtual void get_w(void* out) = 0;
   virtual void psd_stats(int64_t* out8) = 0;
+  virtual void get_scaling(void* D, void* E, double* c) = 0;
   virtual void comm_init(int nranks, int rank, const void* id128) = 0;
   virtual void p2p_export(void* blob128) = 0;
   virtual void p2p_attach(const void* blobs, int nranks) = 0;
@@ -228,6 +230,8 @@ class Engine : public EngineBase {
   void get_rho_vec(void* out) override;
   void get_w(void* out) override;
   void psd_stats(int64_t* out8) override;
+  void get_scaling(void* D, void* E, double* c) override;
+  void equilibrate();
   void comm_init(int nranks, int rank, const void* id128) override;
   void p2p_export(void* blob128) override;
   void p2p_attach(const void* blobs, int nranks) override;
@@ -236,6 +240,7 @@ class Engine : public EngineBase {
   // ---- problem ----
   int n_ = 0, m_ = 0, device_ = 0;
   double create_time_ = 0.0;      // engine construction (the device part of setup!)
+  bool device_scaled_ = false;    // D, E, c were computed here (equilibrate), not handed over by the host
   int auto_rho_interval_ = 0;     // adaptive_rho_interval chosen by the automatic rule (kept across solves like settings)
   cosmo_b200_settings st_;
   bool scaled_ = false;
@@ -831,6 +836,9 @@ Engine<T>::Engine(const cosmo_b200_problem& p, const cosmo_b200_settings& st) : 
   }
   memset(&xv_, 0, sizeof(xv_));
   rho_ = st_.rho;
+  // scaling requested but no scaling matrices handed over: the data are unscaled, equilibrate them here
+  // (setup.jl:27-33 -> scale_ruiz!); the host reads D, E, c back with cosmo_b200_get_scaling
+  if (st_.scaling != 0 && !scaled_) equilibrate();
   classify_and_set_rho(true);
   sync();
   create_time_ = now_s() - t_ctor0;
@@ -888,6 +896,93 @@ void Engine<T>::classify_and_set_rho(bool reset_rho) {
   }
   rho_vec_kernel<T><<<vgrid(m_), kBlock, 0, stream_>>>(m_, rho_class_.p, (T)rho_, (T)st_.RHO_EQ_OVER_RHO_INEQ, (T)st_.RHO_MIN, rho_vec_.p);
   check_launch("rho_vec");
+}
+
+// scale_ruiz! (scaling.jl:21-116) on the resident data; see ruiz.cuh
+template <typename T>
+void Engine<T>::equilibrate() {
+  const int n = n_, m = m_;
+  const T lo = (T)st_.MIN_SCALING, hi = (T)(st_.MAX_SCALING > 0.0 ? st_.MAX_SCALING : 1e4);
+  D_.alloc(n, false); Dinv_.alloc(n, false); E_.alloc(m, false); Einv_.alloc(m, false);
+  DevBuf<T> cdev;
+  cdev.alloc(1, false);
+  ruiz_fill_kernel<T><<<vgrid(n), kBlock, 0, stream_>>>(n, D_.p, T(1));
+  ruiz_fill_kernel<T><<<vgrid(m), kBlock, 0, stream_>>>(m, E_.p, T(1));
+  ruiz_fill_kernel<T><<<1, 32, 0, stream_>>>(1, cdev.p, T(1));
+  T* Dw = Dinv_.p;   // the inverse scalings double as work vectors, like in the reference (scaling.jl:37-41)
+  T* Ew = Einv_.p;
+  auto wgrid = [&](long long rows) { return (int)std::min<long long>((rows * 32 + kBlock - 1) / kBlock + 1, kMaxGrid); };
+  for (int it = 0; it < st_.scaling; ++it) {
+    // kkt_col_norms! (scaling.jl:3-8)
+    ruiz_row_inf_kernel<T><<<wgrid(n), kBlock, 0, stream_>>>(n, P_.view(), D_.p, D_.p, cdev.p, Dw, 0);
+    ruiz_row_inf_kernel<T><<<wgrid(n), kBlock, 0, stream_>>>(n, At_.view(), D_.p, E_.p, (const T*)nullptr, Dw, 1);
+    ruiz_row_inf_kernel<T><<<wgrid(m), kBlock, 0, stream_>>>(m, A_.view(), E_.p, D_.p, (const T*)nullptr, Ew, 0);
+    ruiz_update_kernel<T><<<vgrid(n), kBlock, 0, stream_>>>(n, Dw, D_.p, lo, hi);
+    ruiz_update_kernel<T><<<vgrid(m), kBlock, 0, stream_>>>(m, Ew, E_.p, lo, hi);
+    // cost scaling (scaling.jl:73-90): column norms of the newly scaled P, |q|_inf
+    ruiz_row_inf_kernel<T><<<wgrid(n), kBlock, 0, stream_>>>(n, P_.view(), D_.p, D_.p, cdev.p, Dw, 0);
+    ruiz_cost_kernel<T><<<1, 1024, 0, stream_>>>(n, Dw, q_.p, D_.p, cdev.p, lo, hi);
+    launches_ += 7;
+  }
+  // rectify_set_scalings! (scaling.jl:129-142): one scalar per SOC / PSD / exponential / power cone
+  {
+    std::vector<int> off, dim;
+    for (size_t k = 0; k < sets_.size(); ++k) {
+      const int t = sets_[k].type;
+      if (t != COSMO_B200_ZERO && t != COSMO_B200_NONNEG && t != COSMO_B200_BOX && sets_[k].dim > 0) {
+        off.push_back(set_off_[k]);
+        dim.push_back((int)sets_[k].dim);
+      }
+    }
+    if (!off.empty()) {
+      DevBuf<int> off_d, dim_d;
+      off_d.upload(off, stream_); dim_d.upload(dim, stream_);
+      ruiz_rectify_kernel<T><<<(int)off.size(), kBlock, 0, stream_>>>(off_d.p, dim_d.p, E_.p);
+      sync();
+    }
+  }
+  // apply D, E, c to every copy of the data
+  ruiz_apply_csr_kernel<T><<<wgrid(m), kBlock, 0, stream_>>>(m, A_.rowptr.p, A_.col.p, A_.val.p, E_.p, D_.p, (const T*)nullptr);
+  ruiz_apply_csr_kernel<T><<<wgrid(n), kBlock, 0, stream_>>>(n, At_.rowptr.p, At_.col.p, At_.val.p, D_.p, E_.p, (const T*)nullptr);
+  ruiz_apply_csr_kernel<T><<<wgrid(n), kBlock, 0, stream_>>>(n, P_.rowptr.p, P_.col.p, P_.val.p, D_.p, D_.p, cdev.p);
+  if (A_.windowed)
+    ruiz_apply_win_kernel<T><<<wgrid((long long)A_.nwin * m), kBlock, 0, stream_>>>(A_.nwin, A_.W, m, n, A_.w_rowptr.p, A_.w_col.p, A_.w_val.p, E_.p, D_.p);
+  if (At_.windowed)
+    ruiz_apply_win_kernel<T><<<wgrid((long long)At_.nwin * n), kBlock, 0, stream_>>>(At_.nwin, At_.W, n, m, At_.w_rowptr.p, At_.w_col.p, At_.w_val.p, D_.p, E_.p);
+  ruiz_finish_n_kernel<T><<<vgrid(n), kBlock, 0, stream_>>>(n, q_.p, D_.p, Dinv_.p, cdev.p);
+  ruiz_finish_m_kernel<T><<<vgrid(m), kBlock, 0, stream_>>>(m, b_.p, E_.p, Einv_.p, row_class_.p, box_l_.p, box_u_.p);
+  check_launch("ruiz");
+  // the rho classification (setup.jl:75-85) looks at the SCALED b and Box bounds: refresh the host mirrors
+  {
+    std::vector<T> hb(m), hl(m), hu(m);
+    T ch = T(1);
+    if (m) {
+      CUDA_TRY(cudaMemcpyAsync(hb.data(), b_.p, (size_t)m * sizeof(T), cudaMemcpyDeviceToHost, stream_));
+      CUDA_TRY(cudaMemcpyAsync(hl.data(), box_l_.p, (size_t)m * sizeof(T), cudaMemcpyDeviceToHost, stream_));
+      CUDA_TRY(cudaMemcpyAsync(hu.data(), box_u_.p, (size_t)m * sizeof(T), cudaMemcpyDeviceToHost, stream_));
+    }
+    CUDA_TRY(cudaMemcpyAsync(&ch, cdev.p, sizeof(T), cudaMemcpyDeviceToHost, stream_));
+    sync();
+    for (int i = 0; i < m; ++i) { hb_[i] = (double)hb[i]; hl_[i] = (double)hl[i]; hu_[i] = (double)hu[i]; }
+    c_ = (double)ch;
+  }
+  scaled_ = true;
+  device_scaled_ = true;
+}
+
+template <typename T>
+void Engine<T>::get_scaling(void* D, void* E, double* c) {
+  if (!scaled_) {
+    std::vector<T> one_n(n_, T(1)), one_m(m_, T(1));
+    if (D) memcpy(D, one_n.data(), (size_t)n_ * sizeof(T));
+    if (E) memcpy(E, one_m.data(), (size_t)m_ * sizeof(T));
+    if (c) *c = 1.0;
+    return;
+  }
+  if (D) download_vec(D, D_.p, n_);
+  if (E) download_vec(E, E_.p, m_);
+  sync();
+  if (c) *c = c_;
 }
 
 template <typename T>
@@ -1908,7 +2003,7 @@ int cosmo_b200_default_settings(cosmo_b200_settings* s) {
   s->eps_abs = 1e-5; s->eps_rel = 1e-5; s->eps_prim_inf = 1e-4; s->eps_dual_inf = 1e-4;
   s->max_iter = 5000; s->check_termination = 25; s->check_infeasibility = 40;
   s->scaling = 10; s->adaptive_rho = 1; s->adaptive_rho_interval = 40; s->kkt_solver = COSMO_B200_KKT_CG;
-  s->adaptive_rho_fraction = 0.4; s->setup_time = 0.0;
+  s->adaptive_rho_fraction = 0.4; s->setup_time = 0.0; s->MAX_SCALING = 1e4;
   s->adaptive_rho_tolerance = 5.0; s->adaptive_rho_max_adaptions = INT64_MAX;
   s->RHO_MIN = 1e-6; s->RHO_MAX = 1e6; s->RHO_TOL = 1e-4; s->RHO_EQ_OVER_RHO_INEQ = 1e3;
   s->COSMO_INFTY = 1e20; s->MIN_SCALING = 1e-4;
@@ -1987,6 +2082,9 @@ int cosmo_b200_get_w(cosmo_b200_handle* h, void* out) {
 int cosmo_b200_psd_stats(cosmo_b200_handle* h, int64_t out[8]) {
   if (!out) return COSMO_B200_ERR_INVALID;
   ABI_GUARD(h, h->impl->psd_stats(out));
+}
+int cosmo_b200_get_scaling(cosmo_b200_handle* h, void* D, void* E, double* c) {
+  ABI_GUARD(h, h->impl->get_scaling(D, E, c));
 }
 int cosmo_b200_comm_unique_id(void* id128) {
   if (!id128) return COSMO_B200_ERR_INVALID;

@@ -62,7 +62,7 @@ class SettingsStruct(C.Structure):
                 ("verbose", C.c_int32), ("psd_max_sweeps", C.c_int32),
                 ("accelerator", C.c_int32), ("accelerator_mem", C.c_int32), ("accelerator_min_mem", C.c_int32),
                 ("safeguard", C.c_int32), ("safeguard_tol", C.c_double),
-                ("adaptive_rho_fraction", C.c_double), ("setup_time", C.c_double)]
+                ("adaptive_rho_fraction", C.c_double), ("setup_time", C.c_double), ("MAX_SCALING", C.c_double)]
 
 
 class ResultStruct(C.Structure):
@@ -85,7 +85,7 @@ EXPORTS = [
     "cosmo_b200_update_rho", "cosmo_b200_reset", "cosmo_b200_solve", "cosmo_b200_project", "cosmo_b200_kkt_solve",
     "cosmo_b200_residuals", "cosmo_b200_spmv", "cosmo_b200_spmv_bench", "cosmo_b200_get_rho_vec", "cosmo_b200_get_w",
     "cosmo_b200_comm_unique_id", "cosmo_b200_comm_init", "cosmo_b200_comm_p2p_export", "cosmo_b200_comm_p2p_attach",
-    "cosmo_b200_tc_gemm_test", "cosmo_b200_psd_stats",
+    "cosmo_b200_tc_gemm_test", "cosmo_b200_psd_stats", "cosmo_b200_get_scaling",
 ]
 
 _lib = None
@@ -132,6 +132,7 @@ def load_library(rebuild_if_stale=True):
     lib.cosmo_b200_comm_p2p_export.argtypes = [vp, vp]
     lib.cosmo_b200_comm_p2p_attach.argtypes = [vp, vp, C.c_int32]
     lib.cosmo_b200_psd_stats.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.cosmo_b200_get_scaling.argtypes = [vp, vp, vp, C.POINTER(C.c_double)]
     lib.cosmo_b200_tc_gemm_test.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, C.c_int32,
                                             C.POINTER(C.c_double), C.POINTER(C.c_double)]
     for name in EXPORTS:
@@ -367,6 +368,14 @@ class Engine:
         out = np.empty(self.n + self.m, dtype=self.dtype)
         self._check(self._lib.cosmo_b200_get_w(self._h, _ptr(out)))
         return out
+
+    def scaling(self):
+        """(D, E, c) as used by the engine (cosmo_b200_get_scaling)."""
+        D = np.empty(self.n, dtype=self.dtype)
+        E = np.empty(self.m, dtype=self.dtype)
+        c = C.c_double(1.0)
+        self._check(self._lib.cosmo_b200_get_scaling(self._h, _ptr(D), _ptr(E), C.byref(c)))
+        return D.astype(np.float64), E.astype(np.float64), float(c.value)
 
     def psd_stats(self):
         """Which path projected the large PSD cones so far (cosmo_b200_psd_stats)."""

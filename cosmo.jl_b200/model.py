@@ -17,6 +17,8 @@ import time
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Union
 
+import os
+
 import numpy as np
 import scipy.sparse as sp
 
@@ -279,7 +281,7 @@ class Settings:
                      "adaptive_rho_tolerance", "adaptive_rho_max_adaptions", "RHO_MIN", "RHO_MAX", "RHO_TOL",
                      "RHO_EQ_OVER_RHO_INEQ", "COSMO_INFTY", "MIN_SCALING", "time_limit", "tol_constant",
                      "tol_exponent", "psd_max_sweeps", "accelerator_mem", "accelerator_min_mem", "safeguard_tol",
-                     "adaptive_rho_fraction"):
+                     "adaptive_rho_fraction", "MAX_SCALING"):
             setattr(s, name, getattr(self, name))
         s.adaptive_rho = int(self.adaptive_rho)
         s.verbose = int(bool(self.verbose)) | (2 if self.verbose_timing else 0)
@@ -525,16 +527,17 @@ class Model:
                     self._x2 = np.concatenate([self.x, np.zeros(A2.shape[1] - self.n)])
                     self._s2, self._mu2 = np.zeros(A2.shape[0]), np.zeros(A2.shape[0])
             m2, n2 = A0.shape
-            if st.scaling != 0:
+            host_ruiz = os.environ.get("COSMO_B200_HOST_RUIZ") == "1"
+            if st.scaling != 0 and host_ruiz:      # the NumPy restatement (kept for the sharded path and as a cross-check)
                 P, q, A, b, sets, D, E, c = ruiz_equilibrate(P0, q0, A0, b0, sets0, st)
+                self.engine = _eng.Engine(P, q, A, b, [set_tuple(S) for S in sets], st.to_struct(), D=D, E=E, c=c,
+                                          dtype=self.dtype, device=self.device)
             else:
-                P, q, A, b, sets = P0, q0, A0, b0, sets0
-                D, E, c = np.ones(n2), np.ones(m2), 1.0
+                # scale_ruiz! runs on the device (csrc/ruiz.cuh): the engine ingests the unscaled data and hands D, E, c back
+                self.engine = _eng.Engine(P0, q0, A0, b0, [set_tuple(S) for S in sets0], st.to_struct(),
+                                          dtype=self.dtype, device=self.device)
+                D, E, c = self.engine.scaling() if st.scaling != 0 else (np.ones(n2), np.ones(m2), 1.0)
             self.D, self.E, self.c = D, E, c
-            set_tuples = [set_tuple(S) for S in sets]
-            self.engine = _eng.Engine(P, q, A, b, set_tuples, st.to_struct(),
-                                      D=D if st.scaling != 0 else None, E=E if st.scaling != 0 else None, c=c,
-                                      dtype=self.dtype, device=self.device)
         else:
             self.engine.update_settings(st.to_struct())
         # scale_variables! (scaling.jl:118-123)

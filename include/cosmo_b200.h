@@ -124,7 +124,9 @@ typedef struct {
   const void* b;    /* m */
   int64_t n_sets;
   const cosmo_b200_set* sets;
-  /* diagonal scalings (NULL => identity, i.e. settings.scaling == 0) */
+  /* diagonal scalings.  NULL with settings.scaling == 0: identity.  NULL with settings.scaling != 0: (P, q, A, b) and
+     the Box bounds are UNSCALED and the engine equilibrates them on the device (scale_ruiz!, scaling.jl:21-116);
+     the host then reads D, E, c back with cosmo_b200_get_scaling for scale_variables! / reverse_scaling!. */
   const void* D;
   const void* Dinv;
   const void* E;
@@ -163,6 +165,7 @@ typedef struct {
                                    of this engine); 0: the engine uses its own creation time.  Feeds the automatic rho
                                    interval and the time limit, which the reference measures from before setup!
                                    (solver.jl:119,349) */
+  double MAX_SCALING;           /* settings.MAX_SCALING (1e4), read by the device equilibration */
 } cosmo_b200_settings;
 
 /* COSMO.Result / ResultInfo / ResultTimes (types.jl:26-41, 65-71, 93-112) */
@@ -239,6 +242,9 @@ int cosmo_b200_spmv_bench(cosmo_b200_handle* h, int32_t which, int32_t reps, dou
                           double* algorithmic_bytes);
 /* read back the current per-row penalty vector (ws.rho_vec) */
 int cosmo_b200_get_rho_vec(cosmo_b200_handle* h, void* rho_vec);
+/* ws.sm.D.diag (n), ws.sm.E.diag (m), ws.sm.c[] as used by the engine: what the host passed at create, or what the
+   device equilibration computed (scaling.jl:21-116); all ones when settings.scaling == 0.  NULL pointers are skipped. */
+int cosmo_b200_get_scaling(cosmo_b200_handle* h, void* D, void* E, double* c);
 /* read back the operator variable w = [w_x; w_s] (n+m) */
 int cosmo_b200_get_w(cosmo_b200_handle* h, void* w);
 

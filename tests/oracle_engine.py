@@ -3,7 +3,7 @@
 It exists to exercise, without a GPU, the Python side of everything that normally talks to the CUDA engine: the host
 glue of Model (scaling, decomposition, warm starts) and the bodies of the GPU tests themselves (so a typo in a GPU
 test is found by the CPU run, not at the next GPU run).  It implements the part of the call surface those users need:
-ctor, update_settings, warm_start, update_qb, project, solve, w, rho_vec, close."""
+ctor, update_settings, warm_start, update_qb, project, solve, w, rho_vec, scaling, close."""
 import numpy as np
 import scipy.sparse as sp
 
@@ -44,8 +44,22 @@ class OracleEngine:
         self.cones = cones_from_tuples(sets)
         self.st = settings
         self.scaled = D is not None
+        self._scal = (np.ones(self.n), np.ones(self.m), 1.0) if D is None else (np.array(D), np.array(E), float(c))
+        if D is None and settings is not None and settings.scaling != 0:
+            # like the engine: unscaled data + scaling requested -> equilibrate here (scale_ruiz!)
+            ost = O.Settings(scaling=int(settings.scaling), MIN_SCALING=settings.MIN_SCALING)
+            Ps, qs, As, bs, cones, sm = O.scale_ruiz(self.P, self.q, self.A, self.b, self.cones, ost)
+            self.P, self.q, self.A, self.b, self.cones = sp.csc_matrix(Ps), qs, sp.csc_matrix(As), bs, cones
+            self._scal = (sm.D, sm.E, sm.c)
+            self.scaled = True
         self._w = self._rho = self._warm = None
         OracleEngine.instances.append(self)
+
+    def scaling(self):
+        return self._scal
+
+    def psd_stats(self):
+        return {"tc_projections": 0, "tc_fallbacks": 0}
 
     def update_settings(self, st):
         self.st = st

@@ -38,7 +38,12 @@ def main():
              # Anderson acceleration over sharded rows: inner products = local part (+ w_x on rank 0) + allreduce
              ("qp_accelerated", pr.random_sparse_qp(600, 1500, 0.05, seed=4), dict(accelerator="AndersonAccelerator")),
              ("socp_accelerated", pr.portfolio_socp(n=300, k=30, seed=2),
-              dict(max_iter=3000, scaling=0, accelerator="AndersonAccelerator"))]
+              dict(max_iter=3000, scaling=0, accelerator="AndersonAccelerator")),
+             # the same two at eps = 1e-8: the distance between two accelerated runs scales with the stopping tolerance
+             ("qp_accel_1e-8", pr.random_sparse_qp(600, 1500, 0.05, seed=4),
+              dict(accelerator="AndersonAccelerator", eps_abs=1e-8, eps_rel=1e-8, max_iter=20000)),
+             ("socp_accel_1e-8", pr.portfolio_socp(n=300, k=30, seed=2),
+              dict(max_iter=20000, scaling=0, accelerator="AndersonAccelerator", eps_abs=1e-8, eps_rel=1e-8))]
     ok = True
     for name, (P, q, A, b, sets), kw in cases:
         st = cosmo_b200.Settings(**kw)
@@ -68,9 +73,11 @@ def main():
                     and np.max(np.abs(x - ref.x)) <= tol * max(1, np.abs(ref.x).max())
                     and np.max(np.abs(s - ref.s)) <= tol_sm * max(1, np.abs(ref.s).max())
                     and np.max(np.abs(-mu - ref.y)) <= tol_sm * max(1, np.abs(ref.y).max()))
-            print("%-14s world=%d status=%s/%s iter=%d/%d obj=%.9g/%.9g dx=%.2e %s" % (
+            print("%-16s world=%d status=%s/%s iter=%d/%d obj=%.9g/%.9g dx=%.2e ds=%.2e dmu=%.2e (scales %.2g %.2g %.2g) %s" % (
                 name, world, out.status, ref.status, out.iter, ref.iter, out.obj_val, ref.obj_val,
-                np.max(np.abs(x - ref.x)), "OK" if good else "MISMATCH"), flush=True)
+                np.max(np.abs(x - ref.x)), np.max(np.abs(s - ref.s)), np.max(np.abs(-mu - ref.y)),
+                max(1, np.abs(ref.x).max()), max(1, np.abs(ref.s).max()), max(1, np.abs(ref.y).max()),
+                "OK" if good else "MISMATCH"), flush=True)
             ok = ok and good
         eng.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")

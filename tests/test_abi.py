@@ -44,7 +44,7 @@ def test_struct_sizes():
     assert ctypes.sizeof(E.CscStruct) == 40
     assert ctypes.sizeof(E.SetStruct) == 48
     assert ctypes.sizeof(E.ProblemStruct) == 16 + 16 + 80 + 16 + 16 + 32 + 8
-    assert ctypes.sizeof(E.SettingsStruct) == 56 + 8 + 24 + 16 + 48 + 24 + 8 + 24 + 16   # ABI 3: adaptive_rho_fraction, setup_time
+    assert ctypes.sizeof(E.SettingsStruct) == 56 + 8 + 24 + 16 + 48 + 24 + 8 + 24 + 24   # ABI 3: adaptive_rho_fraction, setup_time, MAX_SCALING
     assert ctypes.sizeof(E.ResultStruct) == 24 + 24 + 8 + 40 + 24 + 56 + 24
 
 
