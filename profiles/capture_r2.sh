@@ -17,4 +17,8 @@ COSMO_B200_PSD_TC=0 timeout 600 $NCU -k regex:'bj_pivot_kernel|bj_cols_kernel|bj
 # launch lists (shares of a step): C2 bench and C4
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 1500 --csv --log-file $O/launches_r2_c2.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/launches_r2_c2.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 1200 --csv --log-file $O/launches_r2_c4.csv python tests/run_configs.py c4 > $O/launches_r2_c4.log 2>&1
+# summarise on the box (only 64 MiB of gpurun_out/ travel back) and keep just the product kernel's report
+python profiles/summarize_r2.py $O/summaries_r2
 ls -la $O/*.ncu-rep $O/launches_r2_*.csv
+rm -f $O/ncu_r2_c4.ncu-rep $O/ncu_r2_c2.ncu-rep $O/ncu_r2_c5.ncu-rep $O/ncu_r2_bj.ncu-rep
+ls $O/summaries_r2

@@ -12,6 +12,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
+if len(sys.argv) > 1:          # on the GPU box: write the summaries next to the raw files (only gpurun_out/ travels back)
+    P = sys.argv[1]
+    os.makedirs(P, exist_ok=True)
 PEAKS = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
 
 METRICS = [

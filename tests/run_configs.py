@@ -39,6 +39,16 @@ def timed(name, P, q, A, b, sets, iters, cpu_iters, **kw):
         if cpu_iters == iters:
             line["obj_cpu"] = ref.obj_val
             line["max_abs_dx"] = float(np.max(np.abs(res.x - ref.x)))
+        # parity at full size: the operator variable w after the oracle's iterations on identical arrays
+        model.engine.update_settings(cosmo_b200.Settings(max_iter=cpu_iters, **st).to_struct())
+        model.engine.reset()
+        model.engine.warm_start(np.zeros(A.shape[1]), np.zeros(A.shape[0]), np.zeros(A.shape[0]))
+        model.engine.solve()
+        w_gpu = model.engine.w()
+        line["parity_w_rel"] = float(np.max(np.abs(w_gpu - ref.w)) / max(np.max(np.abs(ref.w)), 1e-300))
+        line["parity_iters"] = cpu_iters
+        line["parity_ok"] = bool(line["parity_w_rel"] <= 1e-8)
+        line["psd_stats"] = model.engine.psd_stats()
     print(json.dumps(line), flush=True)
 
 
