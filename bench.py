@@ -143,7 +143,8 @@ def oracle_iterations(P, q, A, b, sets, iters, warm, keep_w_at=None):
 
 def host_cores():
     try:
-        return len(os.sched_getaffinity(0))
+        from oracle import fast_matvec as F
+        return F.usable_cpus()       # affinity mask capped by the container's CPU quota
     except Exception:
         return os.cpu_count() or 1
 

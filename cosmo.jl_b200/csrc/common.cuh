@@ -104,7 +104,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
 constexpr int kMaxRanks = 8;
 template <typename T>
 struct P2pView {
-  const T* peer_data[kMaxRanks];   // peer_data[r] = base of rank r's exchange buffer (own buffer at r = rank)
+  T* peer_data[kMaxRanks];         // peer_data[r] = base of rank r's exchange buffer (own buffer at r = rank); PUSH model:
+                                   // rank q stores its partial into segment (slot * nranks + q) of EVERY rank's buffer,
+                                   // consumers read their own buffer only
   unsigned* peer_flags[kMaxRanks]; // peer_flags[r] = base of rank r's flag array (remote writes)
   const unsigned* local_flags;     // this rank's flag array
   unsigned* seq;                   // device-resident sequence counter (identical on every rank)

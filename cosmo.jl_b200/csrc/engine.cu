@@ -329,7 +329,7 @@ class Engine : public EngineBase {
   bool p2p_ = false;
   P2pView<T> xv_;
   DevBuf<T> xchg_data_;
-  DevBuf<unsigned> xchg_flags_, xchg_seq_;
+  DevBuf<unsigned> xchg_flags_, xchg_seq_, xchg_arrive_;
   std::vector<void*> ipc_opened_;
 
   // ---- helpers ----
@@ -838,7 +838,10 @@ Engine<T>::Engine(const cosmo_b200_problem& p, const cosmo_b200_settings& st) : 
   rho_ = st_.rho;
   // scaling requested but no scaling matrices handed over: the data are unscaled, equilibrate them here
   // (setup.jl:27-33 -> scale_ruiz!); the host reads D, E, c back with cosmo_b200_get_scaling
-  if (st_.scaling != 0 && !scaled_) equilibrate();
+  if ((p.flags & COSMO_B200_PROBLEM_EQUILIBRATE) && st_.scaling != 0) {
+    if (scaled_) throw EngineError{COSMO_B200_ERR_INVALID, "COSMO_B200_PROBLEM_EQUILIBRATE expects D = Dinv = E = Einv = NULL"};
+    equilibrate();
+  }
   classify_and_set_rho(true);
   sync();
   create_time_ = now_s() - t_ctor0;
@@ -1062,9 +1065,10 @@ template <typename T>
 void Engine<T>::p2p_export(void* blob128) {
   CUDA_TRY(cudaSetDevice(device_));
   const size_t stride = ((size_t)n_ + 8 + 15) & ~(size_t)15;
-  xchg_data_.alloc(2 * stride);
+  xchg_data_.alloc(2 * (size_t)kMaxRanks * stride);   // [slot][source rank][stride]
   xchg_flags_.alloc(2 * kMaxRanks);
   xchg_seq_.alloc(1);
+  xchg_arrive_.alloc(kMaxRanks);
   xv_.stride = stride;
   cudaIpcMemHandle_t hd, hf;
   CUDA_TRY(cudaIpcGetMemHandle(&hd, xchg_data_.p));
@@ -1092,7 +1096,7 @@ void Engine<T>::p2p_attach(const void* blobs, int nranks) {
     CUDA_TRY(cudaIpcOpenMemHandle(&pf, hf, cudaIpcMemLazyEnablePeerAccess));
     ipc_opened_.push_back(pd);
     ipc_opened_.push_back(pf);
-    xv_.peer_data[r] = static_cast<const T*>(pd);
+    xv_.peer_data[r] = static_cast<T*>(pd);
     xv_.peer_flags[r] = static_cast<unsigned*>(pf);
   }
   for (int r = nranks; r < kMaxRanks; ++r) { xv_.peer_data[r] = nullptr; xv_.peer_flags[r] = nullptr; }
@@ -1181,10 +1185,16 @@ void Engine<T>::kkt_op_stage2(const int* done, const T* u, const T* t_in, T* c_o
   } else if (lead) {
     M2 = &P_;
   }
-  if (px)
-    launch_spmv(At_, t_in, M2, u, n_, EpiKktOpX<T>{done, u, sig, pu, xv_, n_}, red_ptr(cb_.p + n_), "spmv_kkt_op");
-  else
-    launch_spmv(At_, t_in, M2, u, n_, EpiKktOp<T>{done, c_out, u, sig, pu}, red_ptr(cb_.p + n_), "spmv_kkt_op");
+  launch_spmv(At_, t_in, M2, u, n_, EpiKktOp<T>{done, c_out, u, sig, pu}, red_ptr(cb_.p + n_), "spmv_kkt_op");
+  if (px) {
+    // one-shot allreduce over NVLink: push [c; u'c] into every peer's exchange buffer (coalesced 16-byte remote
+    // stores), the consumers (cg_init / cg_update_xr) wait for the flags and sum their local segments in rank order
+    if (c_out != cb_.p) throw EngineError{COSMO_B200_ERR_INVALID, "peer exchange expects the operator output in cb_"};
+    const int len = n_ + 1;
+    const int gx = std::max(1, std::min(16, (len * (int)sizeof(T) + 32767) / 32768));
+    p2p_push_kernel<T><<<dim3(gx, nranks_), kBlock, 0, stream_>>>(xv_, cb_.p, len, done, xchg_arrive_.p);
+    check_launch("p2p_push");
+  }
 }
 
 template <typename T>

@@ -327,32 +327,6 @@ struct EpiKktOp {
   __device__ void operator()(T*) const {}
 };
 
-// Same operator, row-sharded peer-exchange variant: the partial goes into this rank's exchange slot
-// and is published to the peers from the kernel's scalar epilogue (the consumer kernels sum the slots;
-// no separate allreduce launch).
-template <typename T>
-struct EpiKktOpX {
-  static constexpr int NS = 1, NM = 0;
-  const int* done;
-  const T* u;
-  T sigma;
-  const T* add;
-  P2pView<T> x;
-  int n;
-  __device__ T* target() const { return const_cast<T*>(x.peer_data[x.rank]) + (size_t)(*x.seq & 1u) * x.stride; }
-  __device__ void row(int r, T s, T* accS, T*) const {
-    const T ur = u[r];
-    const T v = (add ? s + add[r] : s) + sigma * ur;
-    target()[r] = v;
-    accS[0] += ur * v;
-  }
-  __device__ void operator()(T* out) const {   // last block, one thread: out[0] = partial u'c
-    const unsigned sq = *x.seq;
-    target()[n] = out[0];
-    p2p_publish(x, sq & 1u, sq + 1u);
-  }
-};
-
 // rhs = x1 + A'(rho .* x2)                  (kktsolver_indirect.jl:52-54)
 template <typename T>
 struct EpiAddVec {

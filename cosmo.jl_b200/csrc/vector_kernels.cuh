@@ -195,12 +195,43 @@ __global__ void __launch_bounds__(kBlock) sub_kernel(int n, const T* a, const T*
 // kktsolver_indirect.jl:70).  Scalars live on the device; every kernel is a
 // no-op once isc[ISC_DONE] is set so the host can enqueue iterations ahead.
 // ---------------------------------------------------------------------------
-// sum of the ranks' partial vectors at index i, in rank order (one-shot allreduce on the fly)
+// sum of the ranks' partial vectors at index i, in rank order (one-shot allreduce on the fly).  The partials were PUSHED
+// into this rank's own buffer by p2p_push_kernel (segment slot * nranks + r holds rank r's vector): local reads only.
 template <typename T>
 __device__ __forceinline__ T p2p_gather(const P2pView<T>& v, unsigned slot, int i) {
-  T acc = ld_peer(v.peer_data[0] + (size_t)slot * v.stride + i);
-  for (int r = 1; r < v.nranks; ++r) acc += ld_peer(v.peer_data[r] + (size_t)slot * v.stride + i);
+  const T* base = v.peer_data[v.rank] + (size_t)slot * v.nranks * v.stride + i;
+  T acc = ld_peer(base);
+  for (int r = 1; r < v.nranks; ++r) acc += ld_peer(base + (size_t)r * v.stride);
   return acc;
+}
+
+// Producer side of the exchange: copy this rank's partial vector (len elements, len = n + 1 with the partial dot
+// product riding at the end) into segment (slot, rank) of every peer's buffer over NVLink with coalesced 16-byte
+// stores -- blockIdx.y = destination rank -- then publish the sequence number to that destination (last CTA of the
+// destination, after a system-scope fence of every contributing CTA).
+template <typename T>
+__global__ void __launch_bounds__(kBlock) p2p_push_kernel(P2pView<T> v, const T* __restrict__ src, int len, const int* __restrict__ done,
+                                                          unsigned* __restrict__ arrive) {
+  if (done != nullptr && *done) return;
+  const unsigned sq = *v.seq;
+  const unsigned slot = sq & 1u;
+  const int dst = blockIdx.y;
+  T* out = v.peer_data[dst] + ((size_t)slot * v.nranks + v.rank) * v.stride;
+  constexpr int VEC = 16 / (int)sizeof(T);
+  const int nvec = len / VEC;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x)
+    reinterpret_cast<int4*>(out)[i] = reinterpret_cast<const int4*>(src)[i];       // src and out are 16-byte aligned
+  for (int i = nvec * VEC + blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) out[i] = src[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(arrive + dst, 1u);
+    if (t == gridDim.x - 1) {
+      arrive[dst] = 0;
+      __threadfence_system();
+      st_release_sys(v.peer_flags[dst] + slot * kMaxRanks + v.rank, sq + 1u);
+    }
+  }
 }
 
 template <typename T>

@@ -42,7 +42,7 @@ class SetStruct(C.Structure):
 
 
 class ProblemStruct(C.Structure):
-    _fields_ = [("dtype", C.c_int32), ("index_base", C.c_int32), ("device", C.c_int32), ("_pad", C.c_int32),
+    _fields_ = [("dtype", C.c_int32), ("index_base", C.c_int32), ("device", C.c_int32), ("flags", C.c_int32),
                 ("m", C.c_int64), ("n", C.c_int64), ("P", CscStruct), ("A", CscStruct),
                 ("q", C.c_void_p), ("b", C.c_void_p), ("n_sets", C.c_int64), ("sets", C.c_void_p),
                 ("D", C.c_void_p), ("Dinv", C.c_void_p), ("E", C.c_void_p), ("Einv", C.c_void_p), ("c", C.c_double)]
@@ -178,7 +178,10 @@ class Engine:
     """
 
     def __init__(self, P, q, A, b, sets: Sequence[tuple], settings: Optional[SettingsStruct] = None,
-                 D=None, E=None, c: float = 1.0, dtype=np.float64, device: int = 0, julia_indexing: bool = True):
+                 D=None, E=None, c: float = 1.0, dtype=np.float64, device: int = 0, julia_indexing: bool = True,
+                 equilibrate: bool = False):
+        """equilibrate=True: the data are unscaled and settings.scaling != 0 -- the engine runs scale_ruiz! on the
+        device (COSMO_B200_PROBLEM_EQUILIBRATE); read D, E, c back with scaling()."""
         import scipy.sparse as sp
         self._lib = load_library()
         self.dtype = np.dtype(dtype)
@@ -218,6 +221,7 @@ class Engine:
         prob.dtype = F64 if T == np.float64 else F32
         prob.index_base = base
         prob.device = device
+        prob.flags = 1 if equilibrate else 0
         prob.m, prob.n = self.m, self.n
         prob.P, prob.A = csc(P), csc(A)
         qa = np.ascontiguousarray(q, dtype=T)

@@ -535,7 +535,7 @@ class Model:
             else:
                 # scale_ruiz! runs on the device (csrc/ruiz.cuh): the engine ingests the unscaled data and hands D, E, c back
                 self.engine = _eng.Engine(P0, q0, A0, b0, [set_tuple(S) for S in sets0], st.to_struct(),
-                                          dtype=self.dtype, device=self.device)
+                                          dtype=self.dtype, device=self.device, equilibrate=(st.scaling != 0))
                 D, E, c = self.engine.scaling() if st.scaling != 0 else (np.ones(n2), np.ones(m2), 1.0)
             self.D, self.E, self.c = D, E, c
         else:

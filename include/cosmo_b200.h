@@ -42,6 +42,9 @@ extern "C" {
 
 typedef struct cosmo_b200_handle cosmo_b200_handle;
 
+/* cosmo_b200_problem.flags */
+#define COSMO_B200_PROBLEM_EQUILIBRATE 1 /* run scale_ruiz! on the device (data handed over unscaled) */
+
 enum {
   COSMO_B200_OK = 0,
   COSMO_B200_ERR_INVALID = -1,     /* bad argument / dimension mismatch (interface.jl:369-392) */
@@ -116,7 +119,7 @@ typedef struct {
   int32_t dtype;      /* COSMO_B200_F64 | COSMO_B200_F32 */
   int32_t index_base; /* 1 = Julia, 0 = C */
   int32_t device;     /* CUDA device ordinal */
-  int32_t _pad;
+  int32_t flags;      /* COSMO_B200_PROBLEM_* */
   int64_t m, n;
   cosmo_b200_csc P; /* n x n, both triangles stored */
   cosmo_b200_csc A; /* m x n, model form A x + s = b */
@@ -124,9 +127,10 @@ typedef struct {
   const void* b;    /* m */
   int64_t n_sets;
   const cosmo_b200_set* sets;
-  /* diagonal scalings.  NULL with settings.scaling == 0: identity.  NULL with settings.scaling != 0: (P, q, A, b) and
-     the Box bounds are UNSCALED and the engine equilibrates them on the device (scale_ruiz!, scaling.jl:21-116);
-     the host then reads D, E, c back with cosmo_b200_get_scaling for scale_variables! / reverse_scaling!. */
+  /* diagonal scalings (NULL => identity).  With flags & COSMO_B200_PROBLEM_EQUILIBRATE and settings.scaling != 0 they
+     must be NULL: (P, q, A, b) and the Box bounds are UNSCALED and the engine equilibrates them on the device
+     (scale_ruiz!, scaling.jl:21-116); the host then reads D, E, c back with cosmo_b200_get_scaling for
+     scale_variables! / reverse_scaling!. */
   const void* D;
   const void* Dinv;
   const void* E;

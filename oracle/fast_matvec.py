@@ -30,7 +30,6 @@ def load():
     global _lib
     if _lib is None:
         build()
-        os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")   # idle workers must not spin: the host may be over-subscribed
         os.environ.setdefault("OMP_PROC_BIND", "false")
         _lib = C.CDLL(LIB)
         _lib.oracle_spmv_set_threads.argtypes = [C.c_int]
@@ -68,6 +67,19 @@ class ThreadedCsr:
 _threads = None
 
 
+def usable_cpus():
+    """CPUs this process may actually burn: the affinity mask capped by the cgroup CPU quota (a container on the GPU
+    box sees 128 cores and is allowed 16; more threads than that only buys throttling)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) // int(period))))
+    except Exception:
+        pass
+    return n
+
+
 def calibrate(M, candidates=None, reps=2):
     """Pick the thread count that is actually fastest for y = M x on this host (a container can see 128 cores and be
     allowed 8): returns (threads, seconds per product).  The choice is kept for all later products."""
@@ -75,7 +87,7 @@ def calibrate(M, candidates=None, reps=2):
     global _threads
     lib = load()
     T = M if isinstance(M, ThreadedCsr) else ThreadedCsr(M)
-    ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    ncores = usable_cpus()
     cand = candidates or [t for t in (1, 2, 4, 8, 16, 32, 64, 128, 256) if t <= ncores]
     x = np.ones(T.shape[1])
     best = (None, float("inf"))

@@ -37,7 +37,8 @@ def cones_from_tuples(sets):
 class OracleEngine:
     instances = []
 
-    def __init__(self, P, q, A, b, sets, settings=None, D=None, E=None, c=1.0, dtype=np.float64, device=0, julia_indexing=True):
+    def __init__(self, P, q, A, b, sets, settings=None, D=None, E=None, c=1.0, dtype=np.float64, device=0, julia_indexing=True,
+                 equilibrate=False):
         self.P, self.q = sp.csc_matrix(P), np.array(q, dtype=float)
         self.A, self.b = sp.csc_matrix(A), np.array(b, dtype=float)
         self.m, self.n = self.A.shape
@@ -45,7 +46,7 @@ class OracleEngine:
         self.st = settings
         self.scaled = D is not None
         self._scal = (np.ones(self.n), np.ones(self.m), 1.0) if D is None else (np.array(D), np.array(E), float(c))
-        if D is None and settings is not None and settings.scaling != 0:
+        if equilibrate and D is None and settings is not None and settings.scaling != 0:
             # like the engine: unscaled data + scaling requested -> equilibrate here (scale_ruiz!)
             ost = O.Settings(scaling=int(settings.scaling), MIN_SCALING=settings.MIN_SCALING)
             Ps, qs, As, bs, cones, sm = O.scale_ruiz(self.P, self.q, self.A, self.b, self.cones, ost)

@@ -892,7 +892,7 @@ def test_device_ruiz_matches_oracle(prob):
     else:   # wide enough for the column-windowed slabs (ncols * 8 B > 200 KB)
         P, q, A, b, sets = pr.random_sparse_qp(30000, 4000, 0.002, seed=5)
     st = cosmo_b200.Settings()          # scaling = 10
-    eng = _engine(P, q, A, b, sets)     # default settings, no D / E handed over -> device equilibration
+    eng = E.Engine(P, q, A, b, _tuples(sets), st.to_struct(), equilibrate=True)   # unscaled data in, scale_ruiz! on the device
     D, Ev, c = eng.scaling()
     Ps, qs, As, bs, cones, sm = O.scale_ruiz(P, q, A, b, to_oracle_cones(sets), O.Settings())
     assert np.max(np.abs(D - sm.D) / sm.D) <= 1e-13

@@ -19,8 +19,8 @@ class _OracleEngine:
     """stand-in with the call surface Model uses: ctor, update_settings, warm_start, update_qb, solve, close"""
     instances = []
 
-    def __init__(self, P, q, A, b, sets, settings, D=None, E=None, c=1.0, dtype=np.float64, device=0):
-        assert D is None and E is None          # the glue test runs with scaling = 0
+    def __init__(self, P, q, A, b, sets, settings, D=None, E=None, c=1.0, dtype=np.float64, device=0, equilibrate=False):
+        assert D is None and E is None and not equilibrate         # the glue test runs with scaling = 0
         self.P, self.q, self.A, self.b = sp.csc_matrix(P), np.array(q), sp.csc_matrix(A), np.array(b)
         self.cones = [O.Box(t[2], t[3]) if t[0] == E_BOX else _CODE[t[0]](t[1]) for t in sets]
         self.st = settings
