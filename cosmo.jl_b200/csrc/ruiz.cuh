@@ -117,11 +117,15 @@ __global__ void __launch_bounds__(kBlock) ruiz_apply_csr_kernel(int nrows, const
   }
 }
 
-// the column-windowed slabs: entry k of row r in window w has the global column w * W + col16[k]; padding entries are 0
+// the column-windowed slabs (build_windows / win_fill_segment in engine.cu): a row segment [s, e) of window w is a
+// sequence of 256-entry steps; in step st lane l / slot i keeps its window-local COLUMN at s + 256 st + 8 l + i and
+// its VALUE at s + 256 st + (i / EPL) (EPL ls) + l EPL + i % EPL  (EPL = 16 / sizeof(T) entries per 16-byte load,
+// ls = lanes of the step).  Global column = w W + local column; padding entries are zeros.
 template <typename T>
 __global__ void __launch_bounds__(kBlock) ruiz_apply_win_kernel(int nwin, int W, int nrows, int ncols, const int* __restrict__ w_rowptr,
                                                                 const unsigned short* __restrict__ w_col, T* __restrict__ w_val,
                                                                 const T* __restrict__ wrow, const T* __restrict__ wcol) {
+  constexpr int EPL = 16 / (int)sizeof(T);
   const int lane = threadIdx.x & 31;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const long long total = (long long)nwin * nrows;
@@ -129,12 +133,16 @@ __global__ void __launch_bounds__(kBlock) ruiz_apply_win_kernel(int nwin, int W,
     const int w = (int)(wr / nrows), r = (int)(wr % nrows);
     const int* rp = w_rowptr + (size_t)w * (nrows + 1);
     const int s = rp[r], e = rp[r + 1];
+    const int kpad = e - s, lanes_total = kpad >> 3;
     const T er = wrow[r];
-    for (int k = s + lane; k < e; k += 32) {
-      const T v = w_val[k];
+    for (int idx = lane; idx < kpad; idx += 32) {
+      const int st = idx >> 8, rem = idx & 255, l = rem >> 3, i = rem & 7;
+      const int ls = min(32, lanes_total - 32 * st);
+      const long long pv = (long long)s + (long long)st * 256 + (long long)(i / EPL) * (EPL * ls) + (long long)l * EPL + (i % EPL);
+      const T v = w_val[pv];
       if (v != T(0)) {
-        const int c = w * W + (int)w_col[k];
-        if (c < ncols) w_val[k] = v * er * wcol[c];
+        const int c = w * W + (int)w_col[(long long)s + idx];
+        if (c < ncols) w_val[pv] = v * er * wcol[c];
       }
     }
   }
