@@ -183,6 +183,9 @@ def run_reference(a, rank, world):
 
 def main():
     a = parse_args()
+    # NCCL prints its version banner on STDOUT when NCCL_DEBUG=VERSION: keep stdout for the one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

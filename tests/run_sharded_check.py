@@ -65,11 +65,17 @@ def main():
             if okw.pop("accelerator", None) == "AndersonAccelerator":
                 okw["accelerator"] = "anderson"
             ref = O.solve(P, q, A, b, to_oracle_cones(sets), O.Settings(kkt_solver="cg", **okw))
-            # accelerated runs with inexact (CG) KKT solves amplify the inner solver's rounding: both runs stop
-            # at the same iteration but agree to the solver tolerance only (measured 8e-6 on x for the SOCP)
-            tol = 2e-4 if "accelerator" in kw else 1e-5
-            tol_sm = 2e-3 if "accelerator" in kw else 1e-5      # slack / dual: not measured on the run above, kept looser
-            good = (out.status == ref.status and abs(out.obj_val - ref.obj_val) <= tol * max(1, abs(ref.obj_val))
+            # Accelerated runs are chaotic in the rounding of the inner products (the Anderson least-squares problem
+            # amplifies the different summation order of the sharded reductions): both runs converge to the same
+            # point, their distance is a few stopping tolerances.  Measured on 2 x B200 (profiles/sharded_check_r2_2gpu.log):
+            # socp_accelerated at eps = 1e-5: dx 7.8e-6, ds 2.6e-5, dmu 1.3e-7 with equal status and iteration count;
+            # at eps = 1e-8 the distance drops to 3e-7 / 5e-7 / 1e-8 while the iteration counts differ (1962 vs 3438):
+            # the bound is 5 eps on x, s and mu separately; the eps = 1e-8 legs compare the end points only.
+            accel = "accelerator" in kw
+            tight = accel and kw.get("eps_abs", 1e-5) < 1e-6
+            tol = (5e-6 if tight else 5e-5) if accel else 1e-5
+            tol_sm = tol
+            good = ((tight or out.status == ref.status) and abs(out.obj_val - ref.obj_val) <= tol * max(1, abs(ref.obj_val))
                     and np.max(np.abs(x - ref.x)) <= tol * max(1, np.abs(ref.x).max())
                     and np.max(np.abs(s - ref.s)) <= tol_sm * max(1, np.abs(ref.s).max())
                     and np.max(np.abs(-mu - ref.y)) <= tol_sm * max(1, np.abs(ref.y).max()))
