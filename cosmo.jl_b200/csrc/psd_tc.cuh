@@ -121,8 +121,13 @@ struct PsdTc {
   double *state_d = nullptr, *partial_d = nullptr, *const_d = nullptr, *x2_d = nullptr;
   double* state_h = nullptr;   // pinned
   int capN = 0, shapeN = 0;
-  int last_steps = 0, last_checks = 0;
+  int last_steps = 0, last_checks = 0, last_phases = 0;
   double last_delta = 0, last_resid = -1;
+  // lower end of the spectrum the scaling schedule is laid out for, adapted from call to call (ADMM iterates move
+  // slowly): a projection that converged inside its first schedule makes the next one more optimistic (x10, up to 1e-2),
+  // one that needed a second schedule pulls it back (x1e-3 per extra schedule) and caps the optimism for a while
+  double l0_cur = -1.0, l0_cap = 1e-2;
+  int cap_hold = 0;
   bool configured = false;
   std::string err;
 
@@ -193,7 +198,10 @@ struct PsdTc {
     if (!ensure(N, st)) return false;
     const int g = (int)std::min<long long>(((long long)N * N + kBlock - 1) / kBlock, kMaxGrid);
     const int ntiles = gemm.ntiles;
-    const double l0 = env_double("COSMO_B200_TC_L0", 1e-7);
+    const bool adapt = env_int("COSMO_B200_TC_ADAPT", 1) != 0;
+    if (l0_cur < 0.0 || !adapt) l0_cur = env_double("COSMO_B200_TC_L0", 1e-7);
+    const double l0 = l0_cur;
+    const double l_rearm = 1e-3;                         // a failed check re-arms the schedule for three more decades
     const double alpha_max = env_double("COSMO_B200_TC_ALPHA_MAX", 1.5);
     const double tol = 1e-7;                              // quadratic convergence: the step after delta < tol reaches ~delta^2
     const double rtol = sizeof(T) == 8 ? 5e-13 : 1e-7;    // accepted weighted residual
@@ -217,7 +225,7 @@ struct PsdTc {
     double* S = S0_d;
     double* Sn = S1_d;
     double prev = 1e300, resid = -1.0, prev_resid = 1e300, delta = 2.0;
-    int it = 0, next_check = -1, checks = 0;
+    int it = 0, next_check = -1, checks = 0, phases = 1;
     bool have_P = false;
     for (;;) {
       ok = ok && gemm.slice(S, slS, st);
@@ -252,11 +260,26 @@ struct PsdTc {
         if (resid < rtol || (resid < 1e2 * rtol && resid > 0.5 * prev_resid)) { have_P = true; break; }
         if (it >= cap) { err = "PsdTc: no convergence"; return false; }
         prev_resid = resid;
-        next_check = it + 3;
+        // eigenvalues below the schedule's range are still on their way: run the aggressive schedule again from l_rearm
+        // (the converged part of the spectrum bounces inside [0.56, 1] meanwhile and settles in the taper)
+        state_h[3] = l_rearm;
+        if (cudaMemcpyAsync(state_d + 3, state_h + 3, sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess) return false;
+        ++phases;
+        next_check = -1;
       }
       prev = delta;
     }
-    last_steps = it; last_checks = checks; last_delta = delta; last_resid = resid;
+    last_steps = it; last_checks = checks; last_delta = delta; last_resid = resid; last_phases = phases;
+    if (adapt) {
+      if (phases == 1) {
+        if (cap_hold > 0) --cap_hold; else l0_cap = 1e-2;
+        l0_cur = std::min(l0_cur * 10.0, l0_cap);
+      } else {
+        l0_cap = std::max(l0 * 0.1, 1e-12);              // this optimism failed: stay below it for the next 25 projections
+        cap_hold = 25;
+        l0_cur = std::max(l0 * std::pow(1e-3, phases - 1) * 10.0, 1e-12);
+      }
+    }
     if (!have_P) {
       ok = ok && gemm.slice(S, slS, st);
       ok = ok && gemm.gemm(slS, slX, U_d, X_d, nullptr, 0, const_d + 3, nullptr, st);
@@ -266,7 +289,8 @@ struct PsdTc {
     ns_store_kernel<T><<<g, kBlock, 0, st>>>(d, U_d, s_out);
     ++launches;
     if (getenv("COSMO_B200_PSD_DEBUG"))
-      fprintf(stderr, "[psd-tc] N=%d steps=%d checks=%d delta=%g resid=%g l=%g\n", N, it, checks, delta, resid, state_h[3]);
+      fprintf(stderr, "[psd-tc] N=%d steps=%d checks=%d phases=%d delta=%g resid=%g l0=%g next l0=%g\n", N, it, checks, phases, delta,
+              resid, l0, l0_cur);
     return cudaGetLastError() == cudaSuccess;
   }
 
