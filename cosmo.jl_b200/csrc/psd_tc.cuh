@@ -123,11 +123,24 @@ struct PsdTc {
   int capN = 0, shapeN = 0;
   int last_steps = 0, last_checks = 0, last_phases = 0;
   double last_delta = 0, last_resid = -1;
-  // lower end of the spectrum the scaling schedule is laid out for, adapted from call to call (ADMM iterates move
-  // slowly): a projection that converged inside its first schedule makes the next one more optimistic (x10, up to 1e-2),
-  // one that needed a second schedule pulls it back (x1e-3 per extra schedule) and caps the optimism for a while
+  // Lower end of the spectrum the scaling schedule is laid out for, adapted from call to call (ADMM iterates move
+  // slowly).  A schedule for l0 takes sched_len(l0) steps; eigenvalues below l0 lag behind at the plain Newton-Schulz
+  // rate, so a projection that needed more than sched_len + 3 steps was laid out too optimistically (l0 /= 10 and that
+  // value is not tried again for 25 projections), one that finished on schedule lets every 2nd call probe l0 * 10.
+  // Measured on config C4 (N = 2000): 24 / 21 / 19 / 22 / 25 steps for l0 = 1e-7 / 1e-6 / 1e-5 / 1e-4 / 1e-3.
   double l0_cur = -1.0, l0_cap = 1e-2;
-  int cap_hold = 0;
+  int cap_hold = 0, good_streak = 0;
+  static int sched_len(double l, double alpha_max) {
+    int k = 0;
+    while (l <= 0.999 && k < 200) {
+      double a = std::sqrt(3.0 / (1.0 + l + l * l));
+      if (a > alpha_max) a = alpha_max;
+      const double y = a * l, gl = 0.5 * y * (3.0 - y * y), gu = 0.5 * a * (3.0 - a * a);
+      l = gl < gu ? gl : gu;
+      ++k;
+    }
+    return k;
+  }
   bool configured = false;
   std::string err;
 
@@ -271,13 +284,15 @@ struct PsdTc {
     }
     last_steps = it; last_checks = checks; last_delta = delta; last_resid = resid; last_phases = phases;
     if (adapt) {
-      if (phases == 1) {
-        if (cap_hold > 0) --cap_hold; else l0_cap = 1e-2;
-        l0_cur = std::min(l0_cur * 10.0, l0_cap);
+      const bool on_schedule = (phases == 1) && it <= sched_len(l0, alpha_max) + 3;
+      if (on_schedule) {
+        if (cap_hold > 0 && --cap_hold == 0) l0_cap = 1e-2;
+        if (++good_streak >= 2) { good_streak = 0; l0_cur = std::min(l0 * 10.0, l0_cap); }
       } else {
+        good_streak = 0;
         l0_cap = std::max(l0 * 0.1, 1e-12);              // this optimism failed: stay below it for the next 25 projections
         cap_hold = 25;
-        l0_cur = std::max(l0 * std::pow(1e-3, phases - 1) * 10.0, 1e-12);
+        l0_cur = std::max(l0 * (phases > 1 ? 1e-3 : 0.1), 1e-12);
       }
     }
     if (!have_P) {
