@@ -125,7 +125,7 @@ struct PsdTc {
   double last_delta = 0, last_resid = -1;
   // Lower end of the spectrum the scaling schedule is laid out for, adapted from call to call (ADMM iterates move
   // slowly).  A schedule for l0 takes sched_len(l0) steps; eigenvalues below l0 lag behind at the plain Newton-Schulz
-  // rate, so a projection that needed more than sched_len + 3 steps was laid out too optimistically (l0 /= 10 and that
+  // rate, so a projection that needed more than sched_len + 6 steps was laid out too optimistically (l0 /= 10 and that
   // value is not tried again for 25 projections), one that finished on schedule lets every 2nd call probe l0 * 10.
   // Measured on config C4 (N = 2000): 24 / 21 / 19 / 22 / 25 steps for l0 = 1e-7 / 1e-6 / 1e-5 / 1e-4 / 1e-3.
   double l0_cur = -1.0, l0_cap = 1e-2;
@@ -284,7 +284,7 @@ struct PsdTc {
     }
     last_steps = it; last_checks = checks; last_delta = delta; last_resid = resid; last_phases = phases;
     if (adapt) {
-      const bool on_schedule = (phases == 1) && it <= sched_len(l0, alpha_max) + 3;
+      const bool on_schedule = (phases == 1) && it <= sched_len(l0, alpha_max) + 6;
       if (on_schedule) {
         if (cap_hold > 0 && --cap_hold == 0) l0_cap = 1e-2;
         if (++good_streak >= 2) { good_streak = 0; l0_cur = std::min(l0 * 10.0, l0_cap); }
@@ -292,7 +292,7 @@ struct PsdTc {
         good_streak = 0;
         l0_cap = std::max(l0 * 0.1, 1e-12);              // this optimism failed: stay below it for the next 25 projections
         cap_hold = 25;
-        l0_cur = std::max(l0 * (phases > 1 ? 1e-3 : 0.1), 1e-12);
+        l0_cur = std::max(l0 * (phases > 1 ? 1e-2 : 0.1), 1e-12);
       }
     }
     if (!have_P) {
