@@ -761,14 +761,26 @@ Engine<T>::Engine(const cosmo_b200_problem& p, const cosmo_b200_settings& st) : 
 
   // ---- matrices -----------------------------------------------------------
   {
+    const bool dbg = getenv("COSMO_B200_SETUP_DEBUG") != nullptr;
+    double tp = now_s();
+    auto lap = [&](const char* what) {
+      if (dbg) { const double t = now_s(); fprintf(stderr, "[setup] %-22s %.3f s\n", what, t - tp); tp = t; }
+    };
+    lap("cone tables");
     HostCsr a, at, pp, ppt;
     csc_to_host_csrs<T>(p.A, p.index_base, a, at);
+    lap("csc -> csr (A, A')");
     build_csr(A_, a);
+    lap("upload csr A");
     build_windows(A_, a);
+    lap("windows A");
     build_csr(At_, at);
+    lap("upload csr A'");
     build_windows(At_, at);
+    lap("windows A'");
     csc_to_host_csrs<T>(p.P, p.index_base, pp, ppt);
     build_csr(P_, pp);
+    lap("P");
     // A' and P rows are traversed by the same lane group in the fused operator kernel
     double mean = n_ ? (double)(At_.nnz + P_.nnz) / n_ : 0.0;
     At_.lanes = pick_lanes(mean);
