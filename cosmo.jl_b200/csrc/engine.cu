@@ -612,24 +612,54 @@ static void csc_to_host_csrs(const cosmo_b200_csc& M, int base, HostCsr& csr, Ho
   }
   csr.nrows = (int)nr; csr.ncols = (int)nc;
   csr.rowptr.assign(nr + 1, 0);
-  for (long long k = 0; k < nnz; ++k) {
-    long long r = M.rowval[k] - base;
-    if (r < 0 || r >= nr) throw EngineError{COSMO_B200_ERR_INVALID, "rowval out of range"};
-    csr_t.col[k] = (int)r;
-    csr_t.val[k] = (double)vals[k];
-    csr.rowptr[r + 1]++;
-  }
-  for (long long r = 0; r < nr; ++r) csr.rowptr[r + 1] += csr.rowptr[r];
   csr.col.resize(nnz);
   csr.val.resize(nnz);
-  std::vector<int> next(csr.rowptr.begin(), csr.rowptr.end() - 1);
-  for (long long j = 0; j < nc; ++j)
-    for (int k = csr_t.rowptr[j]; k < csr_t.rowptr[j + 1]; ++k) {
-      int r = csr_t.col[k];
-      int dstk = next[r]++;
-      csr.col[dstk] = (int)j;
-      csr.val[dstk] = csr_t.val[k];
+  // Stable counting-sort transposition, parallel over column blocks: thread t counts the rows of its columns, a prefix
+  // over (row, thread) gives every thread its own slots in every row, so the scatter needs no synchronisation and the
+  // entries of a row stay ordered by column whatever the thread count (deterministic).
+  const int nt = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(32, (long long)std::thread::hardware_concurrency()),
+                                                                  std::min<long long>(nnz / 200000 + 1, nc ? nc : 1)));
+  std::vector<long long> cb(nt + 1, 0);                    // column block boundaries, balanced by nnz
+  for (int t = 1; t < nt; ++t) {
+    const long long target = nnz * t / nt;
+    cb[t] = std::lower_bound(csr_t.rowptr.begin(), csr_t.rowptr.end(), (int)target) - csr_t.rowptr.begin();
+    if (cb[t] > nc) cb[t] = nc;
+    if (cb[t] < cb[t - 1]) cb[t] = cb[t - 1];
+  }
+  cb[nt] = nc;
+  std::vector<std::vector<int>> cnt(nt);
+  std::vector<int> bad(nt, 0);
+  auto run = [&](const std::function<void(int)>& fn) {
+    if (nt == 1) { fn(0); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) th.emplace_back(fn, t);
+    for (auto& x : th) x.join();
+  };
+  run([&](int t) {
+    cnt[t].assign(nr, 0);
+    for (long long k = csr_t.rowptr[cb[t]]; k < csr_t.rowptr[cb[t + 1]]; ++k) {
+      const long long r = M.rowval[k] - base;
+      if (r < 0 || r >= nr) { bad[t] = 1; return; }
+      csr_t.col[k] = (int)r;
+      csr_t.val[k] = (double)vals[k];
+      cnt[t][r]++;
     }
+  });
+  for (int t = 0; t < nt; ++t) if (bad[t]) throw EngineError{COSMO_B200_ERR_INVALID, "rowval out of range"};
+  for (long long r = 0; r < nr; ++r) {
+    int run_sum = csr.rowptr[r];
+    for (int t = 0; t < nt; ++t) { const int c = cnt[t][r]; cnt[t][r] = run_sum; run_sum += c; }   // cnt -> first slot of (t, r)
+    csr.rowptr[r + 1] = run_sum;
+  }
+  run([&](int t) {
+    std::vector<int>& next = cnt[t];
+    for (long long j = cb[t]; j < cb[t + 1]; ++j)
+      for (int k = csr_t.rowptr[j]; k < csr_t.rowptr[j + 1]; ++k) {
+        const int dstk = next[csr_t.col[k]]++;
+        csr.col[dstk] = (int)j;
+        csr.val[dstk] = csr_t.val[k];
+      }
+  });
 }
 
 template <typename T>
