@@ -260,6 +260,7 @@ class Engine : public EngineBase {
   DevBuf<T> soc_norm_, soc_chunk_sum_, soc_norm2_;
   PsdBatch<T> psd_;
   PhaseTimer t_proj_, t_kkt_;
+  DevBuf<T> proj_w_, proj_s_;     // scratch of the plugin-level project() entry point
   int n_c3_ = 0;             // exponential / power cones and their duals (cone3.cuh)
   DevBuf<int> c3_off_, c3_maxit_;
   DevBuf<unsigned char> c3_kind_;
@@ -350,7 +351,7 @@ class Engine : public EngineBase {
   void download_vec(void* host, const T* src, size_t count);
   void build_csr(DevCsr<T>& dst, const HostCsr& h);
   void build_windows(DevCsr<T>& dst, const HostCsr& h);
-  void classify_and_set_rho(bool reset_rho);
+  void classify_and_set_rho(bool reset_rho, bool rebuild_vec = true);
   void allreduce_sum(T* buf, size_t count);
   void allreduce_max(T* buf, size_t count);
 
@@ -914,7 +915,7 @@ Engine<T>::~Engine() {
 // classify_constraints! (setup.jl:75-85; convexset.jl:62-69, 831-842) and
 // set_rho_vec! / update_rho_vec! (parameters.jl:3-13, 75-81)
 template <typename T>
-void Engine<T>::classify_and_set_rho(bool reset_rho) {
+void Engine<T>::classify_and_set_rho(bool reset_rho, bool rebuild_vec) {
   std::vector<unsigned char> cls(m_, 0);
   const double big = st_.COSMO_INFTY * st_.MIN_SCALING;
   for (size_t k = 0; k < sets_.size(); ++k) {
@@ -1046,7 +1047,7 @@ void Engine<T>::update_qb(const void* q, const void* b) {
     for (int i = 0; i < m_; ++i) hb_[i] = (double)static_cast<const T*>(b)[i];
   }
   sync();
-  if (b) classify_and_set_rho(false);
+  if (b) classify_and_set_rho(false, !is_optimized_);
   sync();
 }
 
@@ -1933,11 +1934,15 @@ void Engine<T>::solve(cosmo_b200_result* out) {
 template <typename T>
 void Engine<T>::project(const void* ws, void* s_out) {
   CUDA_TRY(cudaSetDevice(device_));
-  // stage w_s in the s-part of a scratch operator variable
+  // stage w_s in the s-part of a scratch operator variable of its own and put the slack iterate back afterwards: a
+  // caller that projects between two solves must not disturb w_prev or s of the finished one
+  if (proj_w_.n < (size_t)n_ + m_) { proj_w_.alloc((size_t)n_ + m_); proj_s_.alloc(std::max(m_, 1), false); }
   upload_vec(vec_m_, ws, m_);
-  CUDA_TRY(cudaMemcpyAsync(W_[1 - cur_].p + n_, vec_m_.p, m_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
-  project_device(W_[1 - cur_].p, false, nullptr);
+  CUDA_TRY(cudaMemcpyAsync(proj_s_.p, s_.p, m_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+  CUDA_TRY(cudaMemcpyAsync(proj_w_.p + n_, vec_m_.p, m_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+  project_device(proj_w_.p, false, nullptr);
   download_vec(s_out, s_.p, m_);
+  CUDA_TRY(cudaMemcpyAsync(s_.p, proj_s_.p, m_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
   sync();
 }
 
