@@ -464,12 +464,19 @@ static void win_fill_segment(const int* cols, const double* vals, const int* idx
     const int r = cls[ci];
     for (int e : S.bucket[r]) {
       int best = -1, best_free = 0, fallback = -1, fb_free = 0;
-      for (int t = 0; t < G; ++t) {
-        const int g = (cursor + t) % G;
-        const int free_slots = S.cap[g] - S.load[g];
-        if (free_slots <= 0) continue;
-        if (!((S.used[g] >> r) & 1)) { if (free_slots > best_free) { best = g; best_free = free_slots; if (free_slots == GL) break; } }
-        else if (free_slots > fb_free) { fallback = g; fb_free = free_slots; }
+      // bounded scan from the rotating cursor (long rows have hundreds of groups: an unbounded scan made the build
+      // quadratic in the row length -- 15 s for the 10 000-entry rows of config C3); a second, unbounded pass only if
+      // the window found no free slot at all
+      const int scan = std::min(G, 96);
+      for (int pass = 0; pass < 2 && best < 0 && fallback < 0; ++pass) {
+        const int lim = pass == 0 ? scan : G;
+        for (int t = 0; t < lim; ++t) {
+          const int g = (cursor + t) % G;
+          const int free_slots = S.cap[g] - S.load[g];
+          if (free_slots <= 0) continue;
+          if (!((S.used[g] >> r) & 1)) { if (free_slots > best_free) { best = g; best_free = free_slots; if (free_slots == GL) break; } }
+          else if (free_slots > fb_free) { fallback = g; fb_free = free_slots; }
+        }
       }
       const int g = best >= 0 ? best : fallback;
       S.members[g].push_back(e);

@@ -910,3 +910,56 @@ def test_device_ruiz_matches_oracle(prob):
     ref = O.solve(P, q, A, b, to_oracle_cones(sets), O.Settings(kkt_solver="cg"))
     assert res.status == ref.status and abs(res.iter - ref.iter) <= 25
     assert abs(res.obj_val - ref.obj_val) <= 1e-4 * max(1.0, abs(ref.obj_val))
+
+
+def test_c4_closest_correlation_through_the_tensor_core_projection():
+    """Config C4 at N = 256 (one PsdConeTriangle projected by psd_tc.cuh in every iteration), default settings incl. the
+    device Ruiz scaling, run to Solved: status, iteration count, x / s / y and objective against the oracle (dsyevr),
+    the closestcorr.jl:70-80 properties, and no fallback to block Jacobi in any of the projections."""
+    N = 256
+    P, q, A, b, sets = cosmo_b200.problems.closest_correlation_sdp(N=N, seed=12345)
+    res, ref = _parity(P, q, A, b, sets, tol_x=1e-4)
+    assert res.status == "Solved" and res.iter == ref.iter
+    X = np.zeros((N, N))
+    iu = np.triu_indices(N)
+    order = np.lexsort((iu[0], iu[1]))
+    r, c = iu[0][order], iu[1][order]
+    X[r, c] = np.where(r == c, res.x, res.x / np.sqrt(2))
+    X = X + np.triu(X, 1).T
+    assert np.max(np.abs(np.diag(X) - 1.0)) < 1e-4 and np.linalg.eigvalsh(X).min() > -1e-3
+    model = cosmo_b200.Model()
+    model.set(P, q, A, b, sets, cosmo_b200.Settings())
+    out = model.optimize()
+    st = model.engine.psd_stats()
+    assert st["tc_projections"] >= out.iter and st["tc_fallbacks"] == 0, st
+    assert out.times["proj_time"] > 0.5 * out.times["iter_time_device"]      # the projection is the step here
+
+
+def test_psd_tensor_core_large_and_fallback(monkeypatch):
+    """N = 1500 (12 x 12 tiles, several tiles per CTA) at the LAPACK bar; then the fallback: with the step cap forced to
+    3 the Newton-Schulz iteration cannot converge, the engine must fall back to block Jacobi and still be right."""
+    rng = np.random.default_rng(5)
+    N = 1500
+    X = _psd_test_matrix("admm_like", N, rng)
+    sets = [cosmo_b200.PsdConeTriangle(N * (N + 1) // 2)]
+    ws = G._svec(X)
+    eng = _engine(sp.identity(1, format="csc"), np.zeros(1), sp.csc_matrix((ws.size, 1)), np.zeros(ws.size), sets)
+    ref = ws.copy()
+    O.project(ref, to_oracle_cones(sets))
+    got = eng.project(ws)
+    st = eng.psd_stats()
+    assert st["tc_projections"] == 1 and st["tc_fallbacks"] == 0, st
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ws) < 1e-12, st
+    eng.close()
+    monkeypatch.setenv("COSMO_B200_TC_MAX_STEPS", "3")
+    N = 200
+    X = _psd_test_matrix("wigner", N, rng)
+    sets = [cosmo_b200.PsdConeTriangle(N * (N + 1) // 2)]
+    ws = G._svec(X)
+    eng = _engine(sp.identity(1, format="csc"), np.zeros(1), sp.csc_matrix((ws.size, 1)), np.zeros(ws.size), sets)
+    ref = ws.copy()
+    O.project(ref, to_oracle_cones(sets))
+    got = eng.project(ws)
+    st = eng.psd_stats()
+    assert st["tc_projections"] == 0 and st["tc_fallbacks"] == 1, st
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ws) < 1e-12
