@@ -336,6 +336,19 @@ class Engine : public EngineBase {
   // ---- helpers ----
   RedBuf<T> red(int out_slot) { return RedBuf<T>{partials_.p, sc_.p + out_slot, ticket_.p}; }
   RedBuf<T> red_ptr(T* out) { return RedBuf<T>{partials_.p, out, ticket_.p}; }
+  // K5 + K7 pass: 128-bit kernel for fp64 when every (n+m)-vector's m-part is 16-byte aligned (n even; ws_rhs too)
+  void launch_proj_rhs(const ProjRhsArgs<T>& a) {
+    if constexpr (std::is_same<T, double>::value) {
+      if ((a.n & 1) == 0 && ((reinterpret_cast<uintptr_t>(a.ws_rhs) & 15) == 0) && ((reinterpret_cast<uintptr_t>(a.w) & 15) == 0)) {
+        const long long pairs = (a.n >> 1) + ((a.m + 1) >> 1);
+        proj_rhs_vec2_kernel<<<vgrid(pairs), kBlock, 0, stream_>>>(a);
+        check_launch("proj_rhs_vec2");
+        return;
+      }
+    }
+    proj_rhs_kernel<T><<<vgrid((long long)a.n + a.m), kBlock, 0, stream_>>>(a);
+    check_launch("proj_rhs");
+  }
   static int vgrid(long long n) { return (int)std::min<long long>(std::max<long long>((n + kBlock - 1) / kBlock, 1), kMaxGrid); }
   static int sgrid(long long rows, int lanes) {
     long long per = kBlock / lanes;
@@ -1213,8 +1226,7 @@ void Engine<T>::project_device(const T* w, bool with_rhs, const T* ws_rhs) {
   a.soc = SocTable<T>{soc_off_.p, soc_norm_.p};
   a.s = s_.p; a.ls = ls_.p; a.t0 = t0_.p; a.sigma = (T)st_.sigma;
   a.do_proj = 1; a.do_rhs = with_rhs ? 1 : 0;
-  proj_rhs_kernel<T><<<vgrid((long long)n_ + m_), kBlock, 0, stream_>>>(a);
-  check_launch("proj_rhs");
+  launch_proj_rhs(a);
 }
 
 // c = A' tm + P u + sigma u ; cb[n] = u'c   (second half of reduced_mul!, kktsolver_indirect.jl:61-65)
@@ -1761,8 +1773,7 @@ void Engine<T>::solve(cosmo_b200_result* out) {
       a.box_l = box_l_.p; a.box_u = box_u_.p; a.row_class = row_class_.p; a.row_cone = row_cone_.p;
       a.soc = SocTable<T>{soc_off_.p, soc_norm_.p};
       a.s = s_.p; a.ls = ls_.p; a.t0 = t0_.p; a.sigma = (T)st_.sigma; a.do_proj = 0; a.do_rhs = 1;
-      proj_rhs_kernel<T><<<vgrid((long long)n + m), kBlock, 0, stream_>>>(a);
-      check_launch("proj_rhs");
+      launch_proj_rhs(a);
     }
     // the tail reads w_s from ws_rhs's buffer and writes W[dst] (elementwise, may alias)
     T* wd = W_[dst].p;

@@ -109,6 +109,83 @@ __global__ void __launch_bounds__(kBlock) proj_rhs_kernel(ProjRhsArgs<T> a) {
   }
 }
 
+// The same pass with 128-bit loads and stores: one thread owns TWO consecutive entries of [w_x; w_s] (fp64; four for
+// fp32 would need another unroll and is left to the scalar kernel).  Requires n even, so that the m-part of every
+// (n+m)-vector starts 16-byte aligned like the m-vectors do; the host picks the scalar kernel otherwise.  The cone
+// class is read as one 16-bit load per pair; SOC / PSD / Exp rows take the scalar formulas per element.
+template <typename T>
+__device__ __forceinline__ T proj_row_scalar(const ProjRhsArgs<T>& a, int r, T ws, unsigned char cls) {
+  if (cls == ROW_ZERO) return T(0);
+  if (cls == ROW_NONNEG) return (ws > T(0)) ? ws : ((ws != ws) ? ws : T(0));
+  if (cls == ROW_BOX) {
+    const T l = a.box_l[r], u = a.box_u[r];
+    return (ws < l) ? l : ((ws > u) ? u : ws);
+  }
+  if (cls == ROW_SOC) {
+    const int k = a.row_cone[r];
+    const int off = a.soc.off[k];
+    const T t = a.w[a.n + off];
+    const T nx = a.soc.norm[k];
+    if (nx <= t) return ws;
+    if (nx <= -t) return T(0);
+    return (r == off) ? (nx + t) / T(2) : (nx + t) / (T(2) * nx) * ws;
+  }
+  return a.s[r];   // PSD and Exp/Pow rows: projected by their own kernels beforehand
+}
+
+__global__ void __launch_bounds__(kBlock) proj_rhs_vec2_kernel(ProjRhsArgs<double> a) {
+  const int npx = a.n >> 1;                      // pairs in the x-part (n even)
+  const int npairs = npx + ((a.m + 1) >> 1);
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npairs; p += gridDim.x * blockDim.x) {
+    if (p < npx) {
+      if (a.do_rhs) {
+        const double2 w = reinterpret_cast<const double2*>(a.w)[p];
+        const double2 q = reinterpret_cast<const double2*>(a.q)[p];
+        reinterpret_cast<double2*>(a.ls)[p] = make_double2(a.sigma * w.x - q.x, a.sigma * w.y - q.y);
+      }
+      continue;
+    }
+    const int r = (p - npx) << 1;
+    if (r + 1 >= a.m) {                           // odd tail row
+      double sv;
+      if (a.do_proj) { sv = proj_row_scalar<double>(a, r, a.w[a.n + r], a.row_class[r]); a.s[r] = sv; }
+      else sv = a.s[r];
+      if (a.do_rhs) {
+        const double x2 = a.b[r] - 2.0 * sv + a.ws_rhs[r];
+        a.ls[a.n + r] = x2;
+        a.t0[r] = a.rho[r] * x2;
+      }
+      continue;
+    }
+    double2 sv;
+    if (a.do_proj) {
+      const double2 ws = *reinterpret_cast<const double2*>(a.w + a.n + r);
+      const unsigned short c2 = *reinterpret_cast<const unsigned short*>(a.row_class + r);
+      const unsigned char c0 = (unsigned char)(c2 & 0xff), c1 = (unsigned char)(c2 >> 8);
+      if (c0 == ROW_BOX && c1 == ROW_BOX) {       // the common long run: vector loads of the bounds
+        const double2 l = *reinterpret_cast<const double2*>(a.box_l + r);
+        const double2 u = *reinterpret_cast<const double2*>(a.box_u + r);
+        sv.x = (ws.x < l.x) ? l.x : ((ws.x > u.x) ? u.x : ws.x);
+        sv.y = (ws.y < l.y) ? l.y : ((ws.y > u.y) ? u.y : ws.y);
+      } else {
+        sv.x = proj_row_scalar<double>(a, r, ws.x, c0);
+        sv.y = proj_row_scalar<double>(a, r + 1, ws.y, c1);
+      }
+      *reinterpret_cast<double2*>(a.s + r) = sv;
+    } else {
+      sv = *reinterpret_cast<const double2*>(a.s + r);
+    }
+    if (a.do_rhs) {
+      const double2 b = *reinterpret_cast<const double2*>(a.b + r);
+      const double2 wr = *reinterpret_cast<const double2*>(a.ws_rhs + r);
+      const double2 rho = *reinterpret_cast<const double2*>(a.rho + r);
+      const double2 x2 = make_double2(b.x - 2.0 * sv.x + wr.x, b.y - 2.0 * sv.y + wr.y);
+      *reinterpret_cast<double2*>(a.ls + a.n + r) = x2;
+      *reinterpret_cast<double2*>(a.t0 + r) = make_double2(rho.x * x2.x, rho.y * x2.y);
+    }
+  }
+}
+
 // SOC norms, stage 1: one block per chunk of a cone's tail (deterministic tree).
 template <typename T>
 __global__ void __launch_bounds__(kBlock) soc_chunk_kernel(const T* __restrict__ ws, const int* __restrict__ chunk_start,

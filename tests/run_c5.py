@@ -57,8 +57,16 @@ def main():
         cones = to_oracle_cones(sets2)
         k = min(iters, 20)
         t0 = time.time()
-        O.solve(P2, q2, A2, b2, cones, O.Settings(kkt_solver="cg", scaling=0, adaptive_rho=False, max_iter=k, eps_abs=0.0, eps_rel=0.0))
+        ref = O.solve(P2, q2, A2, b2, cones, O.Settings(kkt_solver="cg", scaling=0, adaptive_rho=False, max_iter=k, eps_abs=0.0, eps_rel=0.0))
         line["cpu_oracle_iter_per_s"] = k / (time.time() - t0)
+        # parity at full size: the operator variable w after the same k iterations on the identical arrays
+        eng.update_settings(cosmo_b200.Settings(scaling=0, adaptive_rho=False, max_iter=k, eps_abs=0.0, eps_rel=0.0).to_struct())
+        eng.reset()
+        eng.warm_start(np.zeros(A2.shape[1]), np.zeros(A2.shape[0]), np.zeros(A2.shape[0]))
+        eng.solve()
+        line["parity_w_rel"] = float(np.max(np.abs(eng.w() - ref.w)) / max(np.max(np.abs(ref.w)), 1e-300))
+        line["parity_iters"] = k
+        line["parity_ok"] = bool(line["parity_w_rel"] <= 1e-8)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
