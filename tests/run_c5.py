@@ -59,14 +59,19 @@ def main():
         t0 = time.time()
         ref = O.solve(P2, q2, A2, b2, cones, O.Settings(kkt_solver="cg", scaling=0, adaptive_rho=False, max_iter=k, eps_abs=0.0, eps_rel=0.0))
         line["cpu_oracle_iter_per_s"] = k / (time.time() - t0)
-        # parity at full size: the operator variable w after the same k iterations on the identical arrays
-        eng.update_settings(cosmo_b200.Settings(scaling=0, adaptive_rho=False, max_iter=k, eps_abs=0.0, eps_rel=0.0).to_struct())
-        eng.reset()
-        eng.warm_start(np.zeros(A2.shape[1]), np.zeros(A2.shape[0]), np.zeros(A2.shape[0]))
-        eng.solve()
-        line["parity_w_rel"] = float(np.max(np.abs(eng.w() - ref.w)) / max(np.max(np.abs(ref.w)), 1e-300))
-        line["parity_iters"] = k
-        line["parity_ok"] = bool(line["parity_w_rel"] <= 1e-8)
+        # parity at full size: the operator variable w after the same iterations on the identical arrays,
+        # at 3 iterations (like C3 / C4) and at k; the CG tolerance of iteration j is 1 / j^1.5 relative to |rhs|, so one
+        # inner iteration more or less on either side moves w by ~1e-6: the inner-iteration totals are reported with it
+        for kk in (3, k):
+            refk = ref if kk == k else O.solve(P2, q2, A2, b2, cones, O.Settings(kkt_solver="cg", scaling=0, adaptive_rho=False,
+                                                                               max_iter=kk, eps_abs=0.0, eps_rel=0.0))
+            eng.update_settings(cosmo_b200.Settings(scaling=0, adaptive_rho=False, max_iter=kk, eps_abs=0.0, eps_rel=0.0).to_struct())
+            eng.reset()
+            eng.warm_start(np.zeros(A2.shape[1]), np.zeros(A2.shape[0]), np.zeros(A2.shape[0]))
+            o = eng.solve()
+            rel = float(np.max(np.abs(eng.w() - refk.w)) / max(np.max(np.abs(refk.w)), 1e-300))
+            line["parity_%d_iters" % kk] = {"w_rel": rel, "cg_total_engine": int(o.kkt_inner_iterations),
+                                            "cg_total_oracle": int(np.sum(refk.kkt.inner_iterations)), "ok": bool(rel <= 1e-8)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -438,12 +438,12 @@ def test_minres_solve_matches_oracle(name, kind):
     model = cosmo_b200.Model()
     model.set(P, q, A, b, sets, cosmo_b200.Settings(kkt_solver=name, max_iter=300))
     res = model.optimize()
-    # the reference's MINRES tolerance rule (abstol = tol_k / initial residual) makes the outer
-    # iteration plateau (see tests/test_oracle_golden.py); inner iteration counts sit on a knife
-    # edge there, so the two trajectories are only compared loosely.  kkt_solve above is the tight check.
+    # the reference's MINRES tolerance rule (abstol = tol_k / initial residual) makes the outer iteration plateau (see
+    # tests/test_oracle_golden.py): both runs stop at max_iter.  Measured on B200 over three seeds (tests/run_minres_diffs.py,
+    # round 2): |x - x_ref| <= 1e-10 and |obj - obj_ref| <= 2e-11 relative (full KKT), 1e-15 (reduced); bound 1e-8.
     assert res.status == ref.status and res.iter == ref.iter
-    assert abs(res.obj_val - ref.obj_val) <= 2e-2 * max(1, abs(ref.obj_val))
-    assert np.max(np.abs(res.x - ref.x)) <= 5e-2 * max(1, np.abs(ref.x).max())
+    assert abs(res.obj_val - ref.obj_val) <= 1e-8 * max(1, abs(ref.obj_val))
+    assert np.max(np.abs(res.x - ref.x)) <= 1e-8 * max(1, np.abs(ref.x).max())
 
 
 def test_residuals_match_oracle():
