@@ -62,16 +62,49 @@ def main():
         # parity at full size: the operator variable w after the same iterations on the identical arrays,
         # at 3 iterations (like C3 / C4) and at k; the CG tolerance of iteration j is 1 / j^1.5 relative to |rhs|, so one
         # inner iteration more or less on either side moves w by ~1e-6: the inner-iteration totals are reported with it
+        # The reduced KKT matrix of this P = 0 problem makes CG lose orthogonality within ~20 iterations: the oracle with
+        # exactly rounded inner products (math.fsum) instead of np.dot ends 1e-4 away from itself at equal iteration
+        # counts (measured, profiles/c5_r2_1gpu.json), so the bound here is that self-sensitivity, not 1e-8.
+        import math
+
+        def cg_fsum(x, L, bvec, abstol, reltol=0.0, maxiter=None):
+            nn = bvec.shape[0]
+            maxiter = nn if maxiter is None else maxiter
+            r = bvec - L(x)
+            u = np.zeros(nn)
+            residual, prev, it = math.sqrt(math.fsum(r * r)), 1.0, 0
+            tol = max(reltol * residual, abstol)
+            while it < maxiter and not (residual <= tol):
+                u = r + (residual ** 2 / prev ** 2) * u
+                c = L(u)
+                alpha = residual ** 2 / math.fsum(u * c)
+                x += alpha * u
+                r -= alpha * c
+                prev, residual, it = residual, math.sqrt(math.fsum(r * r)), it + 1
+            return x, it, it + 1
+
         for kk in (3, k):
-            refk = ref if kk == k else O.solve(P2, q2, A2, b2, cones, O.Settings(kkt_solver="cg", scaling=0, adaptive_rho=False,
-                                                                               max_iter=kk, eps_abs=0.0, eps_rel=0.0))
+            stk = O.Settings(kkt_solver="cg", scaling=0, adaptive_rho=False, max_iter=kk, eps_abs=0.0, eps_rel=0.0)
+            refk = ref if kk == k else O.solve(P2, q2, A2, b2, cones, stk)
+            self_rel = None
+            if kk == 3:
+                orig = O.cg_solve
+                O.cg_solve = cg_fsum
+                try:
+                    alt = O.solve(P2, q2, A2, b2, cones, stk)
+                finally:
+                    O.cg_solve = orig
+                self_rel = float(np.max(np.abs(alt.w - refk.w)) / max(np.max(np.abs(refk.w)), 1e-300))
             eng.update_settings(cosmo_b200.Settings(scaling=0, adaptive_rho=False, max_iter=kk, eps_abs=0.0, eps_rel=0.0).to_struct())
             eng.reset()
             eng.warm_start(np.zeros(A2.shape[1]), np.zeros(A2.shape[0]), np.zeros(A2.shape[0]))
             o = eng.solve()
             rel = float(np.max(np.abs(eng.w() - refk.w)) / max(np.max(np.abs(refk.w)), 1e-300))
             line["parity_%d_iters" % kk] = {"w_rel": rel, "cg_total_engine": int(o.kkt_inner_iterations),
-                                            "cg_total_oracle": int(np.sum(refk.kkt.inner_iterations)), "ok": bool(rel <= 1e-8)}
+                                            "cg_total_oracle": int(np.sum(refk.kkt.inner_iterations)),
+                                            "oracle_np_dot_vs_fsum_w_rel": self_rel,
+                                            "ok": bool(int(o.kkt_inner_iterations) == int(np.sum(refk.kkt.inner_iterations)) and
+                                                       rel <= max(1e-8, 2.0 * (self_rel or 1e-4)))}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
