@@ -116,27 +116,41 @@ class ClockSampler:
 def oracle_iterations(P, q, A, b, sets, iters, warm, keep_w_at=None):
     """Time `iters` ADMM iterations of the oracle port after `warm` >= 1 untimed ones (same settings as the engine).
     setup() (the reference's setup!, excluded from its own iter_time too) runs before the clock starts; the sparse
-    products of the KKT operator run on all host threads (oracle/fast_matvec.py), everything else is the oracle as is.
-    Returns (seconds, iterations, mean CG iterations, host threads, w after `keep_w_at` iterations or None)."""
+    products of the KKT operator run on the host threads (oracle/fast_matvec.py), everything else is the oracle as is.
+    The thread count is calibrated in situ during extra warm-up iterations (a container's CPU quota, wake-up latencies
+    and NUMA placement make a stand-alone product benchmark a poor predictor: measured 10x off on the GPU box).
+    Returns (seconds, iterations, mean CG iterations, host threads, w after `keep_w_at` iterations from the cold start or None)."""
     from oracle import cosmo_oracle as O
     from oracle import fast_matvec as F
     from oracle.bridge import to_oracle_cones
     cones = to_oracle_cones(sets)
     warm = max(1, warm)
-    marks, kept = {}, {}
+    cands = F.thread_candidates() if F._threads is None else []
+    probe = len(cands)                      # one extra warm-up iteration per candidate thread count
+    marks, kept, per_t = {}, {}, {}
 
     def cb(it, ws):
         marks[it] = time.perf_counter()
-        if keep_w_at is not None and it == keep_w_at:
+        if 1 <= it <= probe:                # iteration `it` ran with cands[it - 1] threads ... (set below for the next one)
+            per_t[cands[it - 1]] = marks[it] - marks.get(it - 1, t_first[0])
+        if it < probe:
+            F.set_threads(cands[it])
+        elif it == probe and probe:
+            F.set_threads(min(per_t, key=per_t.get))
+        if keep_w_at is not None and it == keep_w_at:       # absolute iteration count from the cold start
             kept["w"] = ws.w.copy()
 
-    st = O.Settings(kkt_solver="cg", scaling=0, adaptive_rho=False, max_iter=warm + iters, eps_abs=0.0, eps_rel=0.0,
+    st = O.Settings(kkt_solver="cg", scaling=0, adaptive_rho=False, max_iter=probe + warm + iters, eps_abs=0.0, eps_rel=0.0,
                     check_termination=25, check_infeasibility=40)
     ws = O.Workspace(P, q, A, b, cones, st)
     ws.setup()
+    if probe:
+        F._threads = cands[0]               # keeps threaded() from running its stand-alone calibration
+        F.load().oracle_spmv_set_threads(cands[0])
     F.threaded(ws)
+    t_first = [time.perf_counter()]
     res = ws.optimize(iter_callback=cb)
-    dt = marks[warm + iters] - marks[warm]
+    dt = marks[probe + warm + iters] - marks[probe + warm]
     inner = res.kkt.inner_iterations
     return dt, iters, float(np.mean(inner)) if inner else 0.0, F.threads_in_use(), kept.get("w")
 

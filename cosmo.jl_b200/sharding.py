@@ -116,11 +116,20 @@ def create_engine(shard: Shard, settings: M.Settings, device: int = 0, dist=None
         obj = [_eng.nccl_unique_id() if shard.rank == 0 else None]
         dist.broadcast_object_list(obj, src=0)
         eng.comm_init(shard.world, shard.rank, obj[0])
-        if os.environ.get("COSMO_B200_P2P", "0") == "1" and shard.world <= 8:
-            # peer-memory exchange (CUDA IPC over NVLink), opt-in: measured SLOWER than the graph-captured
-            # NVLS allreduce of NCCL on 4 x B200 (168.6 vs 181.3 iter/s on C2, profiles/bench_r1_4gpu*.json).
-            # all-gather the 128-byte handle blobs
+        # Peer-memory PUSH exchange of the operator partials (CUDA IPC over NVLink; p2p_push_kernel) instead of one
+        # NCCL allreduce per operator application.  Bit-identical results; measured on C2 (round 2, profiles/
+        # bench_r2_{2,4,8}gpu*.json): 120.6 vs 122.9 iter/s with NCCL on 2 GPUs, 176.8 vs 167.9 on 4, 220.6 vs 205.7 on 8
+        # -> default from 4 ranks up (COSMO_B200_P2P=0 / 1 forces either).
+        mode = os.environ.get("COSMO_B200_P2P", "auto")
+        use_p2p = (mode == "1" or (mode not in ("0", "1") and shard.world >= 4)) and shard.world <= 8
+        if use_p2p:
+            # every rank must take the same path: export first, agree, then attach
+            try:
+                blob, ok = eng.p2p_export(), True
+            except _eng.EngineError:
+                blob, ok = b"", False
             blobs = [None] * shard.world
-            dist.all_gather_object(blobs, eng.p2p_export())
-            eng.p2p_attach(b"".join(blobs), shard.world)
+            dist.all_gather_object(blobs, (ok, blob))
+            if all(o for o, _ in blobs):
+                eng.p2p_attach(b"".join(bl for _, bl in blobs), shard.world)
     return eng

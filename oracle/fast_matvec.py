@@ -105,6 +105,19 @@ def calibrate(M, candidates=None, reps=2):
     return best
 
 
+def set_threads(t):
+    """Fix the thread count of the following products (in-situ calibration by bench.py)."""
+    global _threads
+    _threads = int(t)
+    load().oracle_spmv_set_threads(_threads)
+
+
+def thread_candidates():
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    q = usable_cpus()
+    return sorted({t for t in (q // 2, q, 2 * q, 4 * q) if 1 <= t <= n})
+
+
 def threads_in_use():
     return _threads if _threads is not None else max_threads()
 
