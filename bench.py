@@ -113,7 +113,7 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def oracle_iterations(P, q, A, b, sets, iters, warm, keep_w_at=None):
+def oracle_iterations(P, q, A, b, sets, iters, warm, keep_w_at=None, budget_s=None):
     """Time `iters` ADMM iterations of the oracle port after `warm` >= 1 untimed ones (same settings as the engine).
     setup() (the reference's setup!, excluded from its own iter_time too) runs before the clock starts; the sparse
     products of the KKT operator run on the host threads (oracle/fast_matvec.py), everything else is the oracle as is.
@@ -137,6 +137,13 @@ def oracle_iterations(P, q, A, b, sets, iters, warm, keep_w_at=None):
             F.set_threads(cands[it])
         elif it == probe and probe:
             F.set_threads(min(per_t, key=per_t.get))
+        if budget_s is not None and it == probe + warm and it >= 2:
+            # bounded sample: cut the timed iterations so that the run ends inside the budget (disclosed in `sample`)
+            per_iter = marks[it] - marks[it - 1]
+            left = budget_s - (marks[it] - t_first[0])
+            fit = max(1, int(left / max(per_iter, 1e-9)))
+            if fit < iters:
+                st.max_iter = probe + warm + fit
         if keep_w_at is not None and it == keep_w_at:       # absolute iteration count from the cold start
             kept["w"] = ws.w.copy()
 
@@ -150,6 +157,7 @@ def oracle_iterations(P, q, A, b, sets, iters, warm, keep_w_at=None):
     F.threaded(ws)
     t_first = [time.perf_counter()]
     res = ws.optimize(iter_callback=cb)
+    iters = st.max_iter - probe - warm
     dt = marks[probe + warm + iters] - marks[probe + warm]
     inner = res.kkt.inner_iterations
     return dt, iters, float(np.mean(inner)) if inner else 0.0, F.threads_in_use(), kept.get("w")
@@ -170,16 +178,12 @@ def run_reference(a, rank, world):
     P, q, A, b, sets = cosmo_b200.problems.random_sparse_qp(a.n, a.m, a.density, a.seed)
     # Same K steps and W warm-up iterations as the engine arm.  One ADMM iteration of C2 is ~110 sparse products of
     # 5e7 nonzeros: ~0.5 s on the host threads of a GPU box; the budget guard below only bites on small hosts.
-    iters, warm = max(1, a.steps), max(1, a.warmup)
-    budget_s = float(os.environ.get("COSMO_B200_REF_BUDGET_S", "240"))
+    iters, warm = max(1, a.steps), max(2, a.warmup)
+    budget_s = float(os.environ.get("COSMO_B200_REF_BUDGET_S", "330"))
     t0 = time.perf_counter()
-    dt1, _, _, _, _ = oracle_iterations(P, q, A, b, sets, 1, 1)          # probe: one timed iteration after one warm-up
+    dt, iters, cg, threads, _ = oracle_iterations(P, q, A, b, sets, iters, warm, budget_s=budget_s)
     probe_s = time.perf_counter() - t0
-    capped = False
-    if (iters + warm) * dt1 > budget_s:
-        iters = max(1, int(budget_s / dt1) - warm)
-        capped = True
-    dt, iters, cg, threads, _ = oracle_iterations(P, q, A, b, sets, iters, warm)
+    capped = iters < max(1, a.steps)
     val = iters / dt
     sample = ("%d ADMM iterations after %d warm-up iterations (requested %d/%d%s), the reference loop restated in "
               "NumPy (oracle/cosmo_oracle.py) with the sparse products of the KKT operator on %d OpenMP threads "
