@@ -28,9 +28,15 @@ namespace cosmo {
 // state[7] = alpha_max
 template <int DUMMY = 0>
 __global__ void ns_coef_kernel(const double* __restrict__ partial, int ntiles, int N, double* __restrict__ state) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  // one warp folds the per-tile partials in a fixed order (lane-strided sums, then a shuffle tree): deterministic
   double f = 0.0, d = 0.0;
-  for (int i = 0; i < ntiles; ++i) { f += partial[2 * i]; d += partial[2 * i + 1]; }
+  for (int i = threadIdx.x; i < ntiles; i += 32) { f += partial[2 * i]; d += partial[2 * i + 1]; }
+  for (int o = 16; o > 0; o >>= 1) {
+    f += __shfl_xor_sync(0xffffffffu, f, o);
+    d += __shfl_xor_sync(0xffffffffu, d, o);
+  }
+  if (threadIdx.x != 0) return;
   double l = state[3];
   double gamma = 1.0;
   if (!(f > 0.0)) {            // zero matrix (f == 0) or NaN: hand it to the host through delta
@@ -58,26 +64,36 @@ __global__ void ns_coef_kernel(const double* __restrict__ partial, int ntiles, i
 // state[4] = |X - S W|_F / |X|_F
 template <int DUMMY = 0>
 __global__ void ns_residual_kernel(const double* __restrict__ partial, int ntiles, const double* __restrict__ x2, double* __restrict__ state) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
   double r = 0.0;
-  for (int i = 0; i < ntiles; ++i) r += partial[2 * i + 1];
+  for (int i = threadIdx.x; i < ntiles; i += 32) r += partial[2 * i + 1];
+  for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  if (threadIdx.x != 0) return;
   state[4] = (*x2 > 0.0) ? sqrt(r / *x2) : 0.0;
 }
 
-// S = X / |X|_F (fp64, whatever the model type); x2[0] = |X|_F^2 (from the load kernel's partial sums); Xd: fp64 copy of
-// X when the model type is not fp64
+// x2[0] = |X|_F^2: one block folds the load kernel's partial sums in a fixed order
 template <typename T>
-__global__ void __launch_bounds__(kBlock) ns_scale_kernel(int N, const T* __restrict__ X, const T* __restrict__ fro_partials, int nparts,
-                                                          double* __restrict__ S, double* __restrict__ Xd, double* __restrict__ x2) {
-  __shared__ double sc_s;
-  if (threadIdx.x == 0) {
-    double f = 0.0;
-    for (int i = 0; i < nparts; ++i) f += (double)fro_partials[i];
-    sc_s = (f > 0.0) ? 1.0 / sqrt(f) : 0.0;
-    if (blockIdx.x == 0) *x2 = f;
-  }
+__global__ void __launch_bounds__(kBlock) ns_norm_kernel(const T* __restrict__ fro_partials, int nparts, double* __restrict__ x2) {
+  __shared__ double red[kWarpsPerBlock];
+  double f = 0.0;
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) f += (double)fro_partials[i];
+  for (int o = 16; o > 0; o >>= 1) f += __shfl_xor_sync(0xffffffffu, f, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = f;
   __syncthreads();
-  const double sc = sc_s;
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kWarpsPerBlock; ++w) t += red[w];
+    *x2 = t;
+  }
+}
+
+// S = X / |X|_F (fp64, whatever the model type); Xd: fp64 copy of X when the model type is not fp64
+template <typename T>
+__global__ void __launch_bounds__(kBlock) ns_scale_kernel(int N, const T* __restrict__ X, double* __restrict__ S, double* __restrict__ Xd,
+                                                          const double* __restrict__ x2) {
+  const double f = *x2;
+  const double sc = (f > 0.0) ? 1.0 / sqrt(f) : 0.0;
   const long long total = (long long)N * N;
   for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
     const double x = (double)X[k];
@@ -223,10 +239,12 @@ struct PsdTc {
     const double* X_d;
     if (sizeof(T) == 8) {
       X_d = reinterpret_cast<const double*>(X_in);
-      ns_scale_kernel<T><<<g, kBlock, 0, st>>>(N, X_in, fro_partials, nfro, S0_d, (double*)nullptr, x2_d);
+      ns_norm_kernel<T><<<1, kBlock, 0, st>>>(fro_partials, nfro, x2_d);
+      ns_scale_kernel<T><<<g, kBlock, 0, st>>>(N, X_in, S0_d, (double*)nullptr, x2_d);
     } else {
       X_d = Xd_d;
-      ns_scale_kernel<T><<<g, kBlock, 0, st>>>(N, X_in, fro_partials, nfro, S0_d, Xd_d, x2_d);
+      ns_norm_kernel<T><<<1, kBlock, 0, st>>>(fro_partials, nfro, x2_d);
+      ns_scale_kernel<T><<<g, kBlock, 0, st>>>(N, X_in, S0_d, Xd_d, x2_d);
     }
     {
       double init[8] = {0, 0, 0, l0, 2.0, 0, 1.0, alpha_max};
@@ -238,6 +256,9 @@ struct PsdTc {
     double* S = S0_d;
     double* Sn = S1_d;
     double prev = 1e300, resid = -1.0, prev_resid = 1e300, delta = 2.0;
+    // the host has nothing to decide while the schedule is still far from its taper: those steps are enqueued without
+    // reading the state back (coefficients and scalings live on the device)
+    const int nosync_until = std::max(0, sched_len(l0, alpha_max) - 3);
     int it = 0, next_check = -1, checks = 0, phases = 1;
     bool have_P = false;
     for (;;) {
@@ -248,6 +269,7 @@ struct PsdTc {
       ok = ok && gemm.gemm(slS, slY, Sn, S, nullptr, 0, state_d, nullptr, st);                  // S' = c1 S + c0 S Y
       launches += 5;
       if (!ok) { err = gemm.err; return false; }
+      if (phases == 1 && it + 1 < nosync_until) { std::swap(S, Sn); ++it; continue; }
       if (cudaMemcpyAsync(state_h, state_d, 8 * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) return false;
       if (cudaStreamSynchronize(st) != cudaSuccess) { err = std::string("PsdTc: ") + cudaGetErrorString(cudaGetLastError()); return false; }
       std::swap(S, Sn);
