@@ -179,7 +179,7 @@ def run_reference(a, rank, world):
     # Same K steps and W warm-up iterations as the engine arm.  One ADMM iteration of C2 is ~110 sparse products of
     # 5e7 nonzeros: ~0.5 s on the host threads of a GPU box; the budget guard below only bites on small hosts.
     iters, warm = max(1, a.steps), max(2, a.warmup)
-    budget_s = float(os.environ.get("COSMO_B200_REF_BUDGET_S", "330"))
+    budget_s = float(os.environ.get("COSMO_B200_REF_BUDGET_S", "270"))
     t0 = time.perf_counter()
     dt, iters, cg, threads, _ = oracle_iterations(P, q, A, b, sets, iters, warm, budget_s=budget_s)
     probe_s = time.perf_counter() - t0
