@@ -30,6 +30,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -153,11 +154,53 @@ __device__ __forceinline__ double biased_double(uint32_t v) { return __hiloint2d
 constexpr double kBias = 4503599627370496.0 + 2147483648.0;
 
 // ---------------------------------------------------------------------------------------------------------------
-// Slicing: one CTA per row.  scale[r] = 2^(e_r - 6) with 2^e_r > max |M[r, :]|; digits by round-to-nearest so that
-// every digit is in [-64, 64]; all operations are exact in fp64.  Output layout: see the note above.
+// Slicing: one CTA per row.  scale[r] = 2^(e_r - 6) with 2^e_r > max |M[r, :]|, so t = x / scale is in (-64, 64).
+// The K digits are the balanced base-128 digits of the fixed-point number v = rn(t 2^(7K-7)) (unit of the last kept
+// digit = 1): with the bias B = 64 sum_{j<K} 128^j added, u = v + B >= 0 and the 7-bit FIELDS of u are digit + 64 --
+// no carries, no per-digit rounding: one fp64 multiply and one conversion per element, integer field extraction per
+// digit (the first version took rint / subtract / scale / convert per digit in fp64).  Digits are in [-64, 63], the
+// leading one in [-64, 64]; all of it exact.  Output layout: see the note above.
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256) slice_rows_kernel(const T* __restrict__ M, int N, int Np, int k, int8_t* __restrict__ slices,
+template <int K>
+struct SliceFix {
+  static constexpr int kShift = 7 * K - 7;
+  __host__ __device__ static constexpr unsigned long long bias() {
+    unsigned long long b = 0;
+    for (int j = 0; j < K; ++j) b += 64ull << (7 * j);
+    return b;
+  }
+};
+
+template <int K>
+__host__ __device__ __forceinline__ unsigned long long slice_fixed(double t) {
+  const double s = t * (double)(1ull << SliceFix<K>::kShift);
+#ifdef __CUDA_ARCH__
+  const long long v = __double2ll_rn(s);
+#else
+  const long long v = llrint(s);
+#endif
+  return (unsigned long long)(v + (long long)SliceFix<K>::bias());
+}
+
+// digit p (0 = most significant) of u[0..3] as the four int8 bytes of one word
+template <int K>
+__host__ __device__ __forceinline__ uint32_t slice_pack4(const unsigned long long* u, int p) {
+  const int off = 7 * (K - 1 - p);
+  uint32_t w = 0;
+  if (p == 0) {   // the leading field runs over [0, 128]
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w |= ((uint32_t)((int)(u[j] >> off) - 64) & 0xffu) << (8 * j);
+    return w;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) w |= ((uint32_t)(u[j] >> off) & 127u) << (8 * j);
+  // field f -> int8(f - 64), four bytes at a time: f >= 64: f ^ 0x40;  f < 64: (f ^ 0x40) | 0x80 = f + 192
+  const uint32_t x = w ^ 0x40404040u;
+  return x | ((x & 0x40404040u) << 1);
+}
+
+template <typename T, int K>
+__global__ void __launch_bounds__(256) slice_rows_kernel(const T* __restrict__ M, int N, int Np, int8_t* __restrict__ slices,
                                                         double* __restrict__ scale) {
   const int r = blockIdx.x;
   const T* row = M + (size_t)r * N;   // symmetric: row r == column r of the column-major matrix
@@ -175,21 +218,13 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const T* __restrict__ M
   const double inv = ldexp(1.0, 6 - e);
   int8_t* out_row = slices + (size_t)r * Np * kSlices;
   for (int c0 = threadIdx.x * 8; c0 < N; c0 += blockDim.x * 8) {
-    double t[8];
+    unsigned long long u[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) t[j] = (c0 + j < N) ? (double)row[c0 + j] * inv : 0.0;
+    for (int j = 0; j < 8; ++j) u[j] = slice_fixed<K>((c0 + j < N) ? (double)row[c0 + j] * inv : 0.0);
     int8_t* dst = out_row + (size_t)(c0 >> 5) * (kSlices * 32) + (c0 & 31);
-    for (int p = 0; p < k; ++p) {
-      uint32_t lo = 0, hi = 0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const double d = rint(t[j]);
-        t[j] = (t[j] - d) * 128.0;
-        const uint32_t b = (uint32_t)(uint8_t)(int8_t)(int)d;
-        if (j < 4) lo |= b << (8 * j); else hi |= b << (8 * (j - 4));
-      }
-      *reinterpret_cast<uint2*>(dst + p * 32) = make_uint2(lo, hi);
-    }
+    for (int p = 0; p < K; ++p)
+      *reinterpret_cast<uint2*>(dst + p * 32) = make_uint2(slice_pack4<K>(u, p), slice_pack4<K>(u + 4, p));
   }
 }
 
@@ -540,7 +575,10 @@ struct OzakiGemm {
   }
   // slices of an N x N symmetric matrix (ld = N) into `sl` (padding rows / columns must have been cleared)
   bool slice(const T* M, Sliced& sl, cudaStream_t st) {
-    slice_rows_kernel<T><<<N, 256, 0, st>>>(M, N, Np, k, sl.d, sl.scale);
+    if (k == 8) slice_rows_kernel<T, 8><<<N, 256, 0, st>>>(M, N, Np, sl.d, sl.scale);
+    else if (k == 7) slice_rows_kernel<T, 7><<<N, 256, 0, st>>>(M, N, Np, sl.d, sl.scale);
+    else if (k == 6) slice_rows_kernel<T, 6><<<N, 256, 0, st>>>(M, N, Np, sl.d, sl.scale);
+    else slice_rows_kernel<T, 4><<<N, 256, 0, st>>>(M, N, Np, sl.d, sl.scale);
     return cudaGetLastError() == cudaSuccess;
   }
   // out = c0 (A B) + c1 D + c2 I   (+ reductions into partial[2 * ntiles])

@@ -9,17 +9,23 @@ import pytest
 
 
 def slice_rows(M, k):
-    """slice_rows_kernel: per row 2^e > max|x|, t = x 2^(6-e), digits by round-to-nearest, remainder * 128."""
+    """slice_rows_kernel: per row 2^e > max|x|, t = x 2^(6-e) in (-64, 64); the k digits are the balanced base-128
+    digits of v = rn(t 2^(7k-7)), read off as the 7-bit fields of v + 64 sum_j 128^j (slice_fixed / slice_pack4)."""
     mx = np.max(np.abs(M), axis=1)
     e = np.where(mx > 0, np.frexp(np.where(mx > 0, mx, 1.0))[1], 0)
     scale = np.ldexp(1.0, e - 6)
     t = M * np.ldexp(1.0, 6 - e)[:, None]
+    v = np.rint(t * 2.0 ** (7 * k - 7)).astype(np.int64)
+    u = v + sum(64 << (7 * j) for j in range(k))
+    assert np.all(u >= 0)
     digits = []
-    for _ in range(k):
-        d = np.rint(t)
-        t = (t - d) * 128.0
-        digits.append(d.astype(np.int64))
-    return digits, scale, t      # t: the remainder, in units of the last digit
+    for p in range(k):
+        f = u >> (7 * (k - 1 - p))
+        if p > 0:
+            f = f & 127
+        digits.append((f - 64).astype(np.int64))
+    rem = t * 2.0 ** (7 * k - 7) - v              # what the last digit does not hold, in its own units
+    return digits, scale, rem
 
 
 def sliced_product(A, B, k, g):
@@ -52,7 +58,8 @@ def test_slicing_is_an_exact_digit_expansion():
         err = np.abs(recon - M)
         rowmax = np.max(np.abs(M), axis=1)
         assert np.all(err <= 2.0 ** (-7 * k) * np.maximum(rowmax, 1e-300)[:, None] * 2.0000001)   # truncation only: half a unit of the last digit
-        assert np.all(np.abs(rem) <= 64.0)
+        assert np.all(np.abs(rem) <= 0.5)
+        assert all(np.max(d) <= 63 for d in digits[1:])                        # only the leading digit reaches +64
 
 
 @pytest.mark.parametrize("k,g,bound", [(8, 10, 2e-15), (8, 8, 5e-15), (7, 7, 1e-12), (6, 8, 1e-11), (4, 6, 2e-7)])
@@ -125,3 +132,20 @@ def test_capped_minimax_newton_schulz_schedule(spectrum):
     # projection error bound of the weighted residual: |lambda| (1 - |s|) / 2
     assert np.max(np.abs(lam) * (1.0 - np.abs(s)) / 2) <= (1e-9 if spectrum in ("cluster_at_zero", "graded") else 1e-13) * np.max(np.abs(lam))
     assert steps <= (80 if spectrum in ("cluster_at_zero", "graded") else 32)
+
+
+def test_device_digit_extraction_functions_on_the_host(tmp_path):
+    """slice_fixed / slice_pack4 are __host__ __device__: tests/slice_probe.cu runs the functions the kernel calls on
+    3.2 million values (edge cases, 40 binades) for 8, 7, 6 and 4 slices."""
+    import os
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or ("/usr/local/cuda/bin/nvcc" if os.path.exists("/usr/local/cuda/bin/nvcc") else None)
+    if nvcc is None:
+        pytest.skip("no nvcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "slice_probe")
+    subprocess.run([nvcc, "-std=c++17", "-I", os.path.join(root, "cosmo.jl_b200", "csrc"), "-gencode", "arch=compute_100a,code=sm_100a",
+                    "-o", exe, os.path.join(root, "tests", "slice_probe.cu"), "-lcuda"], check=True, cwd=str(tmp_path))
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "bad 0" in out.stdout, out.stdout + out.stderr
