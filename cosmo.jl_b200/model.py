@@ -409,6 +409,7 @@ class Model:
         self.settings = Settings()
         self.times = {}
         self._dec = None          # chordal DecompositionInfo of the problem the engine holds (settings.decompose)
+        self._x2 = None           # iterates of the decomposed problem (None: restart from self.x)
 
     # assemble!(model, P, q, constraints; settings, x0, y0), interface.jl:30-77
     def assemble(self, P, q, constraints: Union[Constraint, Sequence[Constraint]], settings: Optional[Settings] = None,
@@ -460,6 +461,7 @@ class Model:
         self.is_assembled = True
         self.is_scaled = False
         self._dec = None
+        self._x2 = None
         if self.engine is not None:
             self.engine.close()
             self.engine = None
@@ -471,15 +473,18 @@ class Model:
             raise ValueError("Dimension of warm starting vector doesn't match the length of index range ind.")
         self.x[:] = x0
         self.s[:] = self.b0 - self.A0 @ self.x   # s0 = b - A x0 (interface.jl:131-147)
+        self._x2 = None                           # a decomposed model restarts from this point (see _setup)
 
     def warm_start_slack(self, s0):
         self.s[:] = s0
+        self._x2 = None
 
     def warm_start_dual(self, y0):
         y0 = np.asarray(y0, dtype=np.float64)
         if y0.shape != (self.m,):
             raise ValueError("Dimension of warm starting vector doesn't match the length of index range ind.")
         self.mu[:] = -y0
+        self._x2 = None
 
     # update!(model; q, b), interface.jl:187-211
     def update(self, q=None, b=None):
@@ -496,7 +501,10 @@ class Model:
                 raise ValueError("The dimension of b, does not agree with the model dimension, m.")
             self.b0 = b.copy()
         if self.engine is not None and getattr(self, "_dec", None) is not None:
-            # the row map of b into the clique blocks is rebuilt with the decomposition at the next optimize!
+            # the row map of b into the clique blocks is rebuilt with the decomposition at the next optimize! (rho and
+            # the iterates of the decomposed problem restart; the reference refuses: "can not be updated if the model
+            # has been chordally decomposed before", interface.jl:192,204)
+            self._x2 = None
             self.engine.close()
             self.engine = None
         elif self.engine is not None:
@@ -541,7 +549,15 @@ class Model:
         else:
             self.engine.update_settings(st.to_struct())
         # scale_variables! (scaling.jl:118-123)
-        if self._dec is not None:   # the decomposed problem keeps its own iterates between solves
+        if self._dec is not None:
+            # The decomposed problem keeps its own iterates between solves.  A warm start given in the ORIGINAL
+            # coordinates enters through x only (the clique copies of s and mu start from zero): the reference
+            # re-allocates all variables after the decomposition (pre_allocate_variables!, chordal_decomposition.jl:29),
+            # i.e. drops the warm start altogether, and cannot re-solve a decomposed model.
+            if getattr(self, "_x2", None) is None:
+                n2, m2 = len(self.D), len(self.E)
+                self._x2 = np.concatenate([self.x, np.zeros(n2 - self.n)])
+                self._s2, self._mu2 = np.zeros(m2), np.zeros(m2)
             self.engine.warm_start(self._x2 / self.D, self.E * self._s2, (self._mu2 / self.E) * self.c)
         else:
             self.engine.warm_start(self.x / self.D, self.E * self.s, (self.mu / self.E) * self.c)

@@ -89,6 +89,11 @@ def test_model_decomposes_solves_and_reverses(oracle_engine, merge):
     res2 = model.optimize()
     assert len(oracle_engine.instances) == n_eng and res2.status == "Solved"
     assert eng._warm[0].shape == (eng.A.shape[1],) and eng._warm[1].shape == (eng.A.shape[0],)
+    assert np.any(eng._warm[1] != 0)                                             # ... from the previous decomposed iterates
+    # a warm start in the original coordinates restarts the decomposed iterates from x0 (clique copies of s, mu: zero)
+    model.warm_start_primal(np.array([0.25, -0.5]))
+    assert model.optimize().status == "Solved" and len(oracle_engine.instances) == n_eng
+    assert np.array_equal(eng._warm[0][:2], [0.25, -0.5]) and not np.any(eng._warm[0][2:]) and not np.any(eng._warm[1]) and not np.any(eng._warm[2])
     # update!(b) drops the engine: the clique row map is rebuilt
     model.update(b=model.b0 * 1.0)
     assert model.engine is None
