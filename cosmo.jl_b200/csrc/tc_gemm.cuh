@@ -199,14 +199,25 @@ __host__ __device__ __forceinline__ uint32_t slice_pack4(const unsigned long lon
   return x | ((x & 0x40404040u) << 1);
 }
 
+// The row is read once, coalesced, for the maximum and parked in shared memory (element c at c + c / 8: the padding
+// makes the 8-consecutive-columns-per-thread reads of the second pass conflict-free; read straight from global memory
+// they cost 16 L1 wavefronts per load instruction).  Rows too long for shared memory (`staged` = 0) are re-read.
+constexpr int kSliceStageMaxBytes = 200 * 1024;
+__host__ __device__ constexpr size_t slice_stage_bytes(int N) { return ((size_t)N + (size_t)N / 8 + 8) * sizeof(double); }
+
 template <typename T, int K>
 __global__ void __launch_bounds__(256) slice_rows_kernel(const T* __restrict__ M, int N, int Np, int8_t* __restrict__ slices,
-                                                        double* __restrict__ scale) {
+                                                        double* __restrict__ scale, int staged) {
+  extern __shared__ __align__(16) double slice_srow[];
   const int r = blockIdx.x;
   const T* row = M + (size_t)r * N;   // symmetric: row r == column r of the column-major matrix
   __shared__ double red[8];
   double mx = 0.0;
-  for (int c = threadIdx.x; c < N; c += blockDim.x) mx = fmax(mx, fabs((double)row[c]));
+  for (int c = threadIdx.x; c < N; c += blockDim.x) {
+    const double v = (double)row[c];
+    if (staged) slice_srow[c + (c >> 3)] = v;
+    mx = fmax(mx, fabs(v));
+  }
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
   __syncthreads();
@@ -219,8 +230,13 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const T* __restrict__ M
   int8_t* out_row = slices + (size_t)r * Np * kSlices;
   for (int c0 = threadIdx.x * 8; c0 < N; c0 += blockDim.x * 8) {
     unsigned long long u[8];
+    const double* sp = slice_srow + c0 + (c0 >> 3);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) u[j] = slice_fixed<K>((c0 + j < N) ? (double)row[c0 + j] * inv : 0.0);
+    for (int j = 0; j < 8; ++j) {
+      double x = 0.0;
+      if (c0 + j < N) x = staged ? sp[j] : (double)row[c0 + j];
+      u[j] = slice_fixed<K>(x * inv);
+    }
     int8_t* dst = out_row + (size_t)(c0 >> 5) * (kSlices * 32) + (c0 & 31);
 #pragma unroll
     for (int p = 0; p < K; ++p)
@@ -537,6 +553,10 @@ struct OzakiGemm {
   static bool set_attr() {
     return cudaFuncSetAttribute(ozaki_gemm_kernel<T, K, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes()) == cudaSuccess;
   }
+  template <int K>
+  static bool set_slice_attr() {
+    return cudaFuncSetAttribute(slice_rows_kernel<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSliceStageMaxBytes) == cudaSuccess;
+  }
   static bool supported(int k_, int g_) {
     return (k_ == 8 && (g_ == 10 || g_ == 8)) || (k_ == 7 && g_ == 7) || (k_ == 6 && g_ == 8) || (k_ == 4 && g_ == 6);
   }
@@ -550,6 +570,10 @@ struct OzakiGemm {
     // per device, every time: function attributes are per device and cheap to set
     if (!(set_attr<8, 10>() && set_attr<8, 8>() && set_attr<7, 7>() && set_attr<6, 8>() && set_attr<4, 6>())) {
       err = "cudaFuncSetAttribute(ozaki_gemm_kernel)";
+      return false;
+    }
+    if (!(set_slice_attr<8>() && set_slice_attr<7>() && set_slice_attr<6>() && set_slice_attr<4>())) {
+      err = "cudaFuncSetAttribute(slice_rows_kernel)";
       return false;
     }
     ready = true;
@@ -575,10 +599,12 @@ struct OzakiGemm {
   }
   // slices of an N x N symmetric matrix (ld = N) into `sl` (padding rows / columns must have been cleared)
   bool slice(const T* M, Sliced& sl, cudaStream_t st) {
-    if (k == 8) slice_rows_kernel<T, 8><<<N, 256, 0, st>>>(M, N, Np, sl.d, sl.scale);
-    else if (k == 7) slice_rows_kernel<T, 7><<<N, 256, 0, st>>>(M, N, Np, sl.d, sl.scale);
-    else if (k == 6) slice_rows_kernel<T, 6><<<N, 256, 0, st>>>(M, N, Np, sl.d, sl.scale);
-    else slice_rows_kernel<T, 4><<<N, 256, 0, st>>>(M, N, Np, sl.d, sl.scale);
+    const int staged = slice_stage_bytes(N) <= (size_t)kSliceStageMaxBytes ? 1 : 0;
+    const size_t sm = staged ? slice_stage_bytes(N) : 0;
+    if (k == 8) slice_rows_kernel<T, 8><<<N, 256, sm, st>>>(M, N, Np, sl.d, sl.scale, staged);
+    else if (k == 7) slice_rows_kernel<T, 7><<<N, 256, sm, st>>>(M, N, Np, sl.d, sl.scale, staged);
+    else if (k == 6) slice_rows_kernel<T, 6><<<N, 256, sm, st>>>(M, N, Np, sl.d, sl.scale, staged);
+    else slice_rows_kernel<T, 4><<<N, 256, sm, st>>>(M, N, Np, sl.d, sl.scale, staged);
     return cudaGetLastError() == cudaSuccess;
   }
   // out = c0 (A B) + c1 D + c2 I   (+ reductions into partial[2 * ntiles])
