@@ -777,8 +777,7 @@ Engine<T>::Engine(const cosmo_b200_problem& p, const cosmo_b200_settings& st) : 
         cls = ROW_PSD;
         const long long Nc = (long long)llround(sqrt((double)sdesc.dim));
         if (Nc * Nc != sdesc.dim) throw EngineError{COSMO_B200_ERR_INVALID, "complex PsdConeTriangle: dimension must be a square"};
-        if (2 * Nc > kPsdSmallMax)
-          throw EngineError{COSMO_B200_ERR_UNSUPPORTED, "complex PsdConeTriangle with N > 48: fall back to the host loop"};
+        if (2 * Nc >= (1LL << 15)) throw EngineError{COSMO_B200_ERR_INVALID, "complex PsdConeTriangle: N too large"};
         for (long long i = 0; i < sdesc.dim; ++i) row_cone[off + i] = (int)psd_descs.size();
         // N = 1: project! is max(x, 0) (convexset.jl:404-405), the real 1 x 1 case
         if (sdesc.dim == 1) psd_descs.push_back(PsdConeDesc{(int)off, 1, 1});

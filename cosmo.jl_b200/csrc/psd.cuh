@@ -36,7 +36,7 @@ struct PsdConeDesc {
   int triangle;  // 1: svec upper triangle (PsdConeTriangle), 0: column-major square (PsdCone),
                  // 2: PsdConeTriangle{T, Complex{T}} (convexset.jl:344-360, 444-490): the Hermitian Nc x Nc matrix
                  //    X = A + iB is handled through its real embedding [[A, -B], [B, A]] of side N = 2 Nc, whose
-                 //    projection is the embedding of the projection of X (small path only, Nc <= 48)
+                 //    projection is the embedding of the projection of X
 };
 
 constexpr int kPsdSmallMax = 96;   // 2 * (N+1)^2 * 8 B <= 227 KB shared memory
@@ -64,6 +64,55 @@ __device__ __forceinline__ void rr_pair(int Ne, int r, int k, int& p, int& q) {
 
 // position of (i,j), i<=j, in the column-major upper triangle (convexset.jl:432-442)
 __device__ __forceinline__ long long svec_pos(int i, int j) { return (long long)j * (j + 1) / 2 + i; }
+
+// Entry (i, j) of the real embedding [[A, -B], [B, A]] (side 2 Nc) of the Hermitian matrix X = A + iB stored as
+// PsdConeTriangle{T, Complex{T}} (convexset.jl:444-490): the sqrt 2 scaled real upper triangle column by column,
+// followed by the sqrt 2 scaled strictly upper imaginary parts column by column.
+template <typename T>
+__device__ __forceinline__ T hermitian_embedding_entry(const T* __restrict__ x, int Nc, int i, int j) {
+  const T inv_sqrt2 = T(0.70710678118654752440);
+  const int I = i % Nc, bi = i / Nc, J = j % Nc, bj = j / Nc;
+  const int a = I < J ? I : J, b = I < J ? J : I;
+  if (bi == bj) {                                   // A = Re X (symmetric)
+    const T v = x[svec_pos(a, b)];
+    return (a != b) ? v * inv_sqrt2 : v;
+  }
+  if (I == J) return T(0);                          // Im X has a zero diagonal
+  const T im_ab = x[(long long)Nc * (Nc + 1) / 2 + (long long)b * (b - 1) / 2 + a] * inv_sqrt2;   // Im X[a, b], a < b
+  const T b_IJ = (I < J) ? im_ab : -im_ab;          // B = Im X is antisymmetric
+  return (bi == 1) ? b_IJ : -b_IJ;                  // lower-left block B, upper-right block -B
+}
+
+// s[cone] <- X+ = A+ + i B+ from the projected embedding P (side N = 2 Nc, symmetric; only its upper triangle is read):
+// A+ = (P11 + P22) / 2,  B+ = (P21 - P12) / 2
+template <typename T, typename TP>
+__global__ void __launch_bounds__(kBlock) psd_embedding_store_kernel(PsdConeDesc d, const TP* __restrict__ P, T* __restrict__ s) {
+  const int N = d.N, Nc = N >> 1;
+  const long long tri = (long long)Nc * (Nc + 1) / 2;
+  const double sqrt2 = 1.41421356237309504880;
+  const long long total = (long long)Nc * Nc;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const bool imag = e >= tri;
+    const long long ee = imag ? e - tri : e;
+    long long i, j;
+    if (!imag) {          // (i, j), i <= j, of the triangle: ee = j (j + 1) / 2 + i
+      j = (long long)((sqrt(8.0 * (double)ee + 1.0) - 1.0) * 0.5);
+      while ((j + 1) * (j + 2) / 2 <= ee) ++j;
+      while (j * (j + 1) / 2 > ee) --j;
+      i = ee - j * (j + 1) / 2;
+      const double v = 0.5 * ((double)P[j * N + i] + (double)P[(Nc + j) * N + (Nc + i)]);
+      s[d.off + e] = (T)((i == j) ? v : sqrt2 * v);
+    } else {              // (i, j), i < j, of the strict triangle: ee = j (j - 1) / 2 + i
+      j = (long long)((sqrt(8.0 * (double)ee + 1.0) + 1.0) * 0.5);
+      while (j * (j + 1) / 2 <= ee) ++j;
+      while (j * (j - 1) / 2 > ee) --j;
+      i = ee - j * (j - 1) / 2;
+      // P21[i, j] = P[Nc + i, j] = P[j, Nc + i] (upper triangle);  P12[i, j] = P[i, Nc + j]
+      const double v = 0.5 * ((double)P[(Nc + i) * N + j] - (double)P[(Nc + j) * N + i]);
+      s[d.off + e] = (T)(sqrt2 * v);
+    }
+  }
+}
 
 // ---------------------------------------------------------------------------
 // Small cones: one CTA per cone, everything in shared memory.
@@ -106,21 +155,7 @@ __global__ void __launch_bounds__(kBlock) psd_small_kernel(const PsdConeDesc* __
       v = x[svec_pos(a, b)];
       if (a != b) v *= inv_sqrt2;
     } else if (d.triangle == 2) {
-      // real embedding of the Hermitian matrix: block (bi, bj) of [[A, -B], [B, A]], entry (I, J)
-      const int Nc = N >> 1;
-      const int I = i % Nc, bi = i / Nc, J = j % Nc, bj = j / Nc;
-      const int a = I < J ? I : J, b = I < J ? J : I;
-      if (bi == bj) {                                   // A = Re X (symmetric)
-        v = x[svec_pos(a, b)];
-        if (a != b) v *= inv_sqrt2;
-      } else if (I == J) {
-        v = T(0);                                       // Im X has a zero diagonal
-      } else {
-        // Im X[a, b], a < b, sits behind the real triangle, strictly upper entries column by column
-        const T im_ab = x[(long long)Nc * (Nc + 1) / 2 + (long long)b * (b - 1) / 2 + a] * inv_sqrt2;
-        const T b_IJ = (I < J) ? im_ab : -im_ab;        // B = Im X is antisymmetric
-        v = (bi == 1) ? b_IJ : -b_IJ;                   // lower-left block B, upper-right block -B
-      }
+      v = hermitian_embedding_entry(x, N >> 1, i, j);
     } else {
       v = (x[(long long)j * N + i] + x[(long long)i * N + j]) / T(2);   // symmetrize_upper!, algebra.jl:201-208
     }
@@ -286,7 +321,9 @@ __global__ void __launch_bounds__(kBlock) psd_large_load_kernel(PsdConeDesc d, c
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int i = (int)(e % N), j = (int)(e / N);
     T v;
-    if (d.triangle) {
+    if (d.triangle == 2) {
+      v = hermitian_embedding_entry(x, N >> 1, i, j);
+    } else if (d.triangle) {
       const int a = i < j ? i : j, b = i < j ? j : i;
       v = x[svec_pos(a, b)];
       if (a != b) v *= inv_sqrt2;
@@ -916,7 +953,7 @@ struct PsdBatch {
         if (getenv("COSMO_B200_PSD_DEBUG")) fprintf(stderr, "[psd-tc] fallback to block Jacobi: %s\n", tc_.err.c_str());
         cudaGetLastError();
       }
-      if (sign_enabled) {   // experimental: Pi_+(X) = (X + sign(X) X) / 2 by Newton-Schulz products, no eigenvectors
+      if (sign_enabled && d.triangle != 2) {   // experimental: Pi_+(X) = (X + sign(X) X) / 2 by Newton-Schulz products, no eigenvectors
         const int N = d.N;
         const int g = (int)std::min<long long>(((long long)N * N + kBlock - 1) / kBlock, kMaxGrid);
         psd_large_load_kernel<T><<<g, kBlock, 0, st>>>(d, ws, A_d, V_d, fro_d);
@@ -929,7 +966,16 @@ struct PsdBatch {
       const int g = (int)std::min<long long>(((long long)N * N + kBlock - 1) / kBlock, kMaxGrid);
       psd_large_scale_kernel<T><<<g, kBlock, 0, st>>>(N, A_d, V_d);
       dim3 gt((N + 31) / 32, (N + 31) / 32);
-      psd_large_syrk_kernel<T><<<gt, 256, 0, st>>>(d, V_d, s);
+      if (d.triangle == 2) {
+        // Hermitian cone: reconstruct the projected embedding as a square matrix in A_d (its eigenvalues are no longer
+        // needed), then read A+ and B+ off its blocks
+        const PsdConeDesc sq{0, N, 0};
+        psd_large_syrk_kernel<T><<<gt, 256, 0, st>>>(sq, V_d, A_d);
+        psd_embedding_store_kernel<T, T><<<g, kBlock, 0, st>>>(d, A_d, s);
+        ++launches;
+      } else {
+        psd_large_syrk_kernel<T><<<gt, 256, 0, st>>>(d, V_d, s);
+      }
       ck(cudaGetLastError(), "psd large reconstruct");
       launches += 2;
     }

@@ -323,7 +323,8 @@ struct PsdTc {
       launches += 2;
       if (!ok) { err = gemm.err; return false; }
     }
-    ns_store_kernel<T><<<g, kBlock, 0, st>>>(d, U_d, s_out);
+    if (d.triangle == 2) psd_embedding_store_kernel<T, double><<<g, kBlock, 0, st>>>(d, U_d, s_out);
+    else ns_store_kernel<T><<<g, kBlock, 0, st>>>(d, U_d, s_out);
     ++launches;
     if (getenv("COSMO_B200_PSD_DEBUG"))
       fprintf(stderr, "[psd-tc] N=%d steps=%d checks=%d phases=%d delta=%g resid=%g l0=%g next l0=%g\n", N, it, checks, phases, delta,

@@ -963,3 +963,65 @@ def test_psd_tensor_core_large_and_fallback(monkeypatch):
     st = eng.psd_stats()
     assert st["tc_projections"] == 0 and st["tc_fallbacks"] == 1, st
     assert np.linalg.norm(got - ref) / np.linalg.norm(ws) < 1e-12
+
+
+def _hermitian_ws(N, rng, kind):
+    Z = rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))
+    H = (Z + Z.conj().T) / 2
+    if kind == "shifted":
+        H = H - 0.3 * np.sqrt(N) * np.eye(N)
+    elif kind == "low_rank_plus_noise":          # an ADMM-like iterate: a PSD part plus a small indefinite perturbation
+        Y = rng.standard_normal((N, N // 4)) + 1j * rng.standard_normal((N, N // 4))
+        H = Y @ Y.conj().T / N + 1e-3 * H
+    return O.extract_upper_triangle_complex(H, np.sqrt(2.0)), H
+
+
+@pytest.mark.parametrize("Nc,kind", [(49, "shifted"), (100, "wigner"), (100, "low_rank_plus_noise"), (193, "shifted")])
+def test_complex_psd_cone_large_through_the_tensor_core_path(Nc, kind):
+    """PsdConeTriangle{T, Complex{T}} beyond the shared-memory path (2 Nc > 96): the real embedding [[A, -B], [B, A]]
+    goes through the same tensor-core projection as a real cone of side 2 Nc; against numpy's Hermitian eigh."""
+    rng = np.random.default_rng(1000 + Nc)
+    ws, H = _hermitian_ws(Nc, rng, kind)
+    sets = [cosmo_b200.ComplexPsdConeTriangle(Nc * Nc)]
+    eng = _engine(sp.identity(1, format="csc"), np.zeros(1), sp.csc_matrix((ws.size, 1)), np.zeros(ws.size), sets)
+    got = eng.project(ws)
+    st = eng.psd_stats()
+    assert st["tc_projections"] == 1 and st["tc_fallbacks"] == 0, st
+    ref = ws.copy()
+    O.project(ref, to_oracle_cones(sets))
+    lam, U = np.linalg.eigh(H)
+    truth = O.extract_upper_triangle_complex((U * np.maximum(lam, 0.0)) @ U.conj().T, np.sqrt(2.0))
+    assert np.linalg.norm(ref - truth) / np.linalg.norm(ws) < 1e-12          # the oracle is the Hermitian eigh
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ws) < 1e-12, st
+    # idempotent, and the imaginary diagonal stays out of the picture
+    again = eng.project(got)
+    assert np.linalg.norm(again - got) / np.linalg.norm(ws) < 1e-12
+
+
+def test_complex_psd_cone_large_block_jacobi_fallback_and_solve(monkeypatch):
+    """the same cone through the fallback eigensolver (Newton-Schulz capped at 3 steps), and a solve: the least
+    eigenvalue of a 60 x 60 Hermitian matrix as an SDP (least_eigenvalue.jl:33-39 at a size beyond the small path)."""
+    rng = np.random.default_rng(77)
+    Nc = 60
+    ws, H = _hermitian_ws(Nc, rng, "wigner")
+    sets = [cosmo_b200.ComplexPsdConeTriangle(Nc * Nc)]
+    monkeypatch.setenv("COSMO_B200_TC_MAX_STEPS", "3")
+    eng = _engine(sp.identity(1, format="csc"), np.zeros(1), sp.csc_matrix((ws.size, 1)), np.zeros(ws.size), sets)
+    got = eng.project(ws)
+    st = eng.psd_stats()
+    assert st["tc_projections"] == 0 and st["tc_fallbacks"] == 1, st
+    ref = ws.copy()
+    O.project(ref, to_oracle_cones(sets))
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ws) < 1e-12
+    eng.close()
+    monkeypatch.delenv("COSMO_B200_TC_MAX_STEPS")
+    # max t  s.t.  H - t I  in the Hermitian PSD cone:  x = t, minimise -t, A x + s = b with A = svec(I), b = svec(H)
+    eye = O.extract_upper_triangle_complex(np.eye(Nc, dtype=complex), np.sqrt(2.0))
+    A = sp.csc_matrix(eye.reshape(-1, 1))
+    P = sp.csc_matrix((1, 1))
+    q = np.array([-1.0])
+    m1 = cosmo_b200.Model()
+    m1.set(P, q, A, ws, sets, cosmo_b200.Settings(eps_abs=1e-7, eps_rel=1e-7))
+    res = m1.optimize()
+    assert res.status == "Solved"
+    assert abs(res.x[0] - np.linalg.eigvalsh(H)[0]) < 1e-4
