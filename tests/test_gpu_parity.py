@@ -1023,7 +1023,11 @@ def test_complex_psd_cone_large_block_jacobi_fallback_and_solve(monkeypatch):
     m1 = cosmo_b200.Model()
     m1.set(P, q, A, ws, sets, cosmo_b200.Settings())
     res = m1.optimize()
-    ref = O.solve(P, q, A, ws, to_oracle_cones(sets), O.Settings())               # 3100 iterations at the default 1e-5
-    assert res.status == "Solved" == ref.status and abs(res.iter - ref.iter) <= 25
-    assert abs(res.x[0] - ref.x[0]) < 1e-6 * abs(ref.x[0])
+    # the engine's KKT solver is CG with the reference's tolerance schedule: the run to compare with is the oracle's CG
+    # run (4725 iterations, 16 rho updates; with the direct solver the oracle needs 3100 -- a 1.3 % difference in the
+    # first rho update is enough on this slowly converging problem)
+    ref = O.solve(P, q, A, ws, to_oracle_cones(sets), O.Settings(kkt_solver="cg"))
+    assert res.status == "Solved" == ref.status and res.iter == ref.iter
+    assert np.allclose(res.info.rho_updates, ref.info.rho_updates, rtol=1e-6)
+    assert abs(res.x[0] - ref.x[0]) < 1e-8 * abs(ref.x[0])
     assert abs(res.x[0] - np.linalg.eigvalsh(H)[0]) < 1e-3 * abs(ref.x[0])
