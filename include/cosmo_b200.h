@@ -48,7 +48,7 @@ typedef struct cosmo_b200_handle cosmo_b200_handle;
 enum {
   COSMO_B200_OK = 0,
   COSMO_B200_ERR_INVALID = -1,     /* bad argument / dimension mismatch (interface.jl:369-392) */
-  COSMO_B200_ERR_UNSUPPORTED = -2, /* complex PSD, BigFloat: shim falls back to Julia */
+  COSMO_B200_ERR_UNSUPPORTED = -2, /* unknown set type, BigFloat, unsupported option: shim falls back to Julia */
   COSMO_B200_ERR_CUDA = -3,        /* CUDA runtime error or no usable sm_100 device */
   COSMO_B200_ERR_ALLOC = -4,
   COSMO_B200_ERR_NCCL = -5,
@@ -71,7 +71,8 @@ enum {
   COSMO_B200_POW = 8,          /* PowerCone(alpha),     convexset.jl:625-742 */
   COSMO_B200_DUAL_POW = 9,     /* DualPowerCone(alpha), convexset.jl:765-789 */
   COSMO_B200_PSD_TRIANGLE_COMPLEX = 10 /* PsdConeTriangle{T, Complex{T}}(dim), dim = N^2 (convexset.jl:344-360,444-490);
-                                          N <= 48 (projected through the real 2N x 2N embedding in shared memory) */
+                                          projected through the real 2N x 2N embedding [[A, -B], [B, A]]: in shared
+                                          memory up to N = 48, through the large-cone path (tensor cores) beyond */
 };
 
 /* status (src/solver.jl:113,161,175,311-353) */
