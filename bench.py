@@ -285,6 +285,24 @@ def main():
     ms_A, bytes_A = eng.spmv_bench(0, 20)
     ms_At, bytes_At = eng.spmv_bench(3, 20)
 
+    # ---- the ResultTimes split (types.jl:26-41) of a short extra run with the device phase timers on; outside the timed
+    # region (the timers add event records around every phase) -- reporting only, never fatal
+    phases = None
+    try:
+        k_ph = max(3, min(10, a.steps))
+        stp = cosmo_b200.Settings(scaling=0, adaptive_rho=False, max_iter=k_ph, eps_abs=0.0, eps_rel=0.0, verbose_timing=True).to_struct()
+        eng.update_settings(stp)
+        eng.reset()
+        barrier()
+        outp = eng.solve(ox, os_, omu)
+        barrier()
+        phases = {"iters": k_ph, "proj_ms_per_iter": 1e3 * outp.times["proj_time"] / k_ph,
+                  "kkt_ms_per_iter": 1e3 * outp.times["kkt_time"] / k_ph,
+                  "iter_ms_per_iter": 1e3 * outp.times["iter_time_device"] / k_ph,
+                  "note": "rank 0, CUDA events around the projection and the KKT solve (verbose_timing)"}
+    except Exception as exc:                                   # noqa: BLE001
+        phases = {"error": str(exc)[:200]}
+
     if dist is not None:
         t = torch.tensor([dev_s, e2e_s, ms_A, ms_At], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -328,6 +346,7 @@ def main():
                                                "upload) + the K iterations"}},
                 "gpu_launches": int(out.kernel_launches),
                 "clocks": clocks,
+                "phases": phases,
                 "roofline": {"bound": "hbm", "kernel": "spmv_win_kernel<double,EpiScale> (t = rho.*(A u), x staged in smem by TMA bulk copy)",
                              "achieved": ach_A, "peak": peak, "unit": "GB/s", "frac": ach_A / peak,
                              "traffic": traffic, "peak_source": peak_src, "ms_per_launch": ms_A,
