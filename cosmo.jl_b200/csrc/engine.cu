@@ -1874,7 +1874,9 @@ void Engine<T>::solve(cosmo_b200_result* out) {
       cost = info[4];
       if (fabs(cost) > 1e20) { status = COSMO_B200_UNSOLVED; break; }
       if (st_.verbose & 1) printf("%lld\t%.4e\t%.4e\t%.4e\t%.4e\n", iter, cost, info[0], info[1], rho_);
-      if (info[0] < st_.eps_abs + st_.eps_rel * info[2] && info[1] < st_.eps_abs + st_.eps_rel * info[3]) {
+      // has_converged (residuals.jl:127-140): a known optimal value, when given, must be met as well
+      const bool obj_ok = (st_.obj_true != st_.obj_true) || fabs(st_.obj_true - cost) <= st_.obj_true_tol;
+      if (info[0] < st_.eps_abs + st_.eps_rel * info[2] && info[1] < st_.eps_abs + st_.eps_rel * info[3] && obj_ok) {
         status = COSMO_B200_SOLVED;
         break;
       }
@@ -2078,6 +2080,7 @@ int cosmo_b200_default_settings(cosmo_b200_settings* s) {
   s->max_iter = 5000; s->check_termination = 25; s->check_infeasibility = 40;
   s->scaling = 10; s->adaptive_rho = 1; s->adaptive_rho_interval = 40; s->kkt_solver = COSMO_B200_KKT_CG;
   s->adaptive_rho_fraction = 0.4; s->setup_time = 0.0; s->MAX_SCALING = 1e4;
+  s->obj_true = NAN; s->obj_true_tol = 1e-3;
   s->adaptive_rho_tolerance = 5.0; s->adaptive_rho_max_adaptions = INT64_MAX;
   s->RHO_MIN = 1e-6; s->RHO_MAX = 1e6; s->RHO_TOL = 1e-4; s->RHO_EQ_OVER_RHO_INEQ = 1e3;
   s->COSMO_INFTY = 1e20; s->MIN_SCALING = 1e-4;

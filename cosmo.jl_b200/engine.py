@@ -62,7 +62,8 @@ class SettingsStruct(C.Structure):
                 ("verbose", C.c_int32), ("psd_max_sweeps", C.c_int32),
                 ("accelerator", C.c_int32), ("accelerator_mem", C.c_int32), ("accelerator_min_mem", C.c_int32),
                 ("safeguard", C.c_int32), ("safeguard_tol", C.c_double),
-                ("adaptive_rho_fraction", C.c_double), ("setup_time", C.c_double), ("MAX_SCALING", C.c_double)]
+                ("adaptive_rho_fraction", C.c_double), ("setup_time", C.c_double), ("MAX_SCALING", C.c_double),
+                ("obj_true", C.c_double), ("obj_true_tol", C.c_double)]
 
 
 class ResultStruct(C.Structure):

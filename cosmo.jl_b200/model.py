@@ -241,6 +241,9 @@ class Settings:
     RHO_EQ_OVER_RHO_INEQ: float = 1e3
     COSMO_INFTY: float = 1e20
     time_limit: float = 0.0
+    obj_true: float = float("nan")            # residuals.jl:132-137: |obj_true - cost| <= obj_true_tol joins the convergence test
+    obj_true_tol: float = 1e-3
+    nearly_ratio: float = 100.0               # only read by is_primal/dual_nearly_feasible (the MOI layer, residuals.jl:119-125)
     tol_constant: float = 1.0
     tol_exponent: float = 1.5
     psd_max_sweeps: int = 30
@@ -281,7 +284,7 @@ class Settings:
                      "adaptive_rho_tolerance", "adaptive_rho_max_adaptions", "RHO_MIN", "RHO_MAX", "RHO_TOL",
                      "RHO_EQ_OVER_RHO_INEQ", "COSMO_INFTY", "MIN_SCALING", "time_limit", "tol_constant",
                      "tol_exponent", "psd_max_sweeps", "accelerator_mem", "accelerator_min_mem", "safeguard_tol",
-                     "adaptive_rho_fraction", "MAX_SCALING"):
+                     "adaptive_rho_fraction", "MAX_SCALING", "obj_true", "obj_true_tol"):
             setattr(s, name, getattr(self, name))
         s.adaptive_rho = int(self.adaptive_rho)
         s.verbose = int(bool(self.verbose)) | (2 if self.verbose_timing else 0)

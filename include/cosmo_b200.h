@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define COSMO_B200_ABI_VERSION 3
+#define COSMO_B200_ABI_VERSION 4
 
 typedef struct cosmo_b200_handle cosmo_b200_handle;
 
@@ -171,6 +171,10 @@ typedef struct {
                                    interval and the time limit, which the reference measures from before setup!
                                    (solver.jl:119,349) */
   double MAX_SCALING;           /* settings.MAX_SCALING (1e4), read by the device equilibration */
+  /* ABI 4 */
+  double obj_true;              /* settings.obj_true (NaN = off): has_converged additionally requires
+                                   |obj_true - cost| <= obj_true_tol at a termination check (residuals.jl:127-140) */
+  double obj_true_tol;          /* settings.obj_true_tol (1e-3) */
 } cosmo_b200_settings;
 
 /* COSMO.Result / ResultInfo / ResultTimes (types.jl:26-41, 65-71, 93-112) */

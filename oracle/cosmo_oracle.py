@@ -594,6 +594,9 @@ class Settings:
     RHO_EQ_OVER_RHO_INEQ: float = 1e3
     COSMO_INFTY: float = 1e20
     time_limit: float = 0.0
+    obj_true: float = float("nan")   # settings.jl:128-129, residuals.jl:132-137
+    obj_true_tol: float = 1e-3
+    nearly_ratio: float = 100.0      # residuals.jl:119-125 (read by the MOI layer only)
     kkt_solver: str = "direct"  # "direct" (QDLDL stand-in) | "cg" | "minres" | "minres_reduced"
     tol_constant: float = 1.0   # kktsolver_indirect.jl:21
     tol_exponent: float = 1.5
@@ -1179,8 +1182,11 @@ class Workspace:
 
     def has_converged(self, r: ResultInfo):  # residuals.jl:98-140
         st = self.st
+        obj_true_flag = True
+        if not np.isnan(st.obj_true):   # a known optimal value must be met as well (residuals.jl:132-137)
+            obj_true_flag = abs(st.obj_true - self.calculate_cost()) <= st.obj_true_tol
         return (r.r_prim < st.eps_abs + st.eps_rel * r.max_norm_prim) and \
-               (r.r_dual < st.eps_abs + st.eps_rel * r.max_norm_dual)
+               (r.r_dual < st.eps_abs + st.eps_rel * r.max_norm_dual) and obj_true_flag
 
     # ---- infeasibility.jl --------------------------------------------------
     def is_primal_infeasible(self, dy):  # infeasibility.jl:1-29

@@ -24,6 +24,7 @@ int main(void) {
   F(cosmo_b200_settings, accelerator); F(cosmo_b200_settings, accelerator_mem); F(cosmo_b200_settings, accelerator_min_mem);
   F(cosmo_b200_settings, safeguard); F(cosmo_b200_settings, safeguard_tol);
   F(cosmo_b200_settings, adaptive_rho_fraction); F(cosmo_b200_settings, setup_time); F(cosmo_b200_settings, MAX_SCALING);
+  F(cosmo_b200_settings, obj_true); F(cosmo_b200_settings, obj_true_tol);
   F(cosmo_b200_result, obj_val); F(cosmo_b200_result, iter); F(cosmo_b200_result, safeguarding_iter);
   F(cosmo_b200_result, status); F(cosmo_b200_result, r_prim); F(cosmo_b200_result, rho_updates);
   F(cosmo_b200_result, solver_time); F(cosmo_b200_result, kernel_launches);

@@ -26,7 +26,7 @@ def test_header_symbols_exported():
     for name in declared:
         assert hasattr(lib, name), name
     assert sorted(E.EXPORTS) == declared
-    assert lib.cosmo_b200_abi_version() == 3
+    assert lib.cosmo_b200_abi_version() == 4
 
 
 def test_default_settings_match_reference():
@@ -44,7 +44,7 @@ def test_struct_sizes():
     assert ctypes.sizeof(E.CscStruct) == 40
     assert ctypes.sizeof(E.SetStruct) == 48
     assert ctypes.sizeof(E.ProblemStruct) == 16 + 16 + 80 + 16 + 16 + 32 + 8
-    assert ctypes.sizeof(E.SettingsStruct) == 56 + 8 + 24 + 16 + 48 + 24 + 8 + 24 + 24   # ABI 3: adaptive_rho_fraction, setup_time, MAX_SCALING
+    assert ctypes.sizeof(E.SettingsStruct) == 56 + 8 + 24 + 16 + 48 + 24 + 8 + 24 + 24 + 16   # ABI 3: adaptive_rho_fraction, setup_time, MAX_SCALING; ABI 4: obj_true, obj_true_tol
     assert ctypes.sizeof(E.ResultStruct) == 24 + 24 + 8 + 40 + 24 + 56 + 24
 
 
@@ -142,7 +142,7 @@ def test_c_header_layout_matches_ctypes_mirror(tmp_path):
             assert getattr(mirror[st], field).offset == int(v), k
             checked += 1
     assert checked >= 35
-    assert vals["abi"] == "3" and vals["defaults"] == "0.1 1e-06 1.6 5000 0 15 2"
+    assert vals["abi"] == "4" and vals["defaults"] == "0.1 1e-06 1.6 5000 0 15 2"
     assert int(vals["create_null"]) == E.ERR_INVALID and "null" in vals["last_error"]
 
 
@@ -175,3 +175,22 @@ def test_c_example_solves_the_reference_qp(tmp_path):
     out = subprocess.run([_build_c_example(tmp_path)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.startswith("status 1 ")                              # COSMO_B200_SOLVED; x = (0.3, 0.7), obj 1.88 checked in C
+
+
+def test_obj_true_settings_mapping_and_oracle_rule():
+    # ABI 4: obj_true (NaN = off) / obj_true_tol reach the engine's settings; the oracle applies the rule of
+    # residuals.jl:127-140 (a wrong value keeps the loop running, a tight tolerance costs iterations)
+    import math
+    from oracle import cosmo_oracle as O
+    from tests import golden_problems as G
+    d = E.default_settings()
+    assert math.isnan(d.obj_true) and d.obj_true_tol == 1e-3
+    st = cosmo_b200.Settings(obj_true=1.88, obj_true_tol=1e-6).to_struct()
+    assert (st.obj_true, st.obj_true_tol) == (1.88, 1e-6) and math.isnan(cosmo_b200.Settings().to_struct().obj_true)
+    P, q, cons = G.g1_qp_nonneg()
+    Pm, qm, A, b, cones = O.assemble(P, q, cons)
+    plain = O.solve(Pm, qm, A, b, cones, O.Settings())
+    tight = O.solve(Pm, qm, A, b, cones, O.Settings(obj_true=1.88, obj_true_tol=1e-8))
+    wrong = O.solve(Pm, qm, A, b, cones, O.Settings(obj_true=2.88, max_iter=200))
+    assert plain.status == tight.status == "Solved" and tight.iter > plain.iter and abs(tight.obj_val - 1.88) <= 1e-8
+    assert wrong.status == "Max_iter_reached" and wrong.iter == 200

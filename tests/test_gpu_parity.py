@@ -1031,3 +1031,22 @@ def test_complex_psd_cone_large_block_jacobi_fallback_and_solve(monkeypatch):
     assert np.allclose(res.info.rho_updates, ref.info.rho_updates, rtol=1e-6)
     assert abs(res.x[0] - ref.x[0]) < 1e-8 * abs(ref.x[0])
     assert abs(res.x[0] - np.linalg.eigvalsh(H)[0]) < 1e-3 * abs(ref.x[0])
+
+
+@pytest.mark.parametrize("scaling", [0, 10])
+def test_obj_true_joins_the_convergence_test(scaling):
+    """settings.obj_true / obj_true_tol (residuals.jl:127-140): with a known optimal value the run only stops once the
+    cost is within obj_true_tol of it as well -- the reference's examples/qp.jl (optimum 1.88)."""
+    plain, _ = _solve_mine(G.g1_qp_nonneg, scaling=scaling)
+    for kw in (dict(obj_true=1.88, obj_true_tol=1e-3), dict(obj_true=1.88, obj_true_tol=1e-8),
+               dict(obj_true=2.88, obj_true_tol=1e-3, max_iter=300)):
+        res, _ = _solve_mine(G.g1_qp_nonneg, scaling=scaling, **kw)
+        ref = _solve_oracle(G.g1_qp_nonneg, scaling=scaling, **kw)
+        assert res.status == ref.status and res.iter == ref.iter, (kw, res.status, res.iter, ref.iter)
+        assert abs(res.obj_val - ref.obj_val) < 1e-9
+        if kw["obj_true"] == 1.88:
+            assert res.status == "Solved" and abs(res.obj_val - 1.88) <= kw["obj_true_tol"]
+    loose, _ = _solve_mine(G.g1_qp_nonneg, scaling=scaling, obj_true=1.88, obj_true_tol=1e-3)
+    tight, _ = _solve_mine(G.g1_qp_nonneg, scaling=scaling, obj_true=1.88, obj_true_tol=1e-8)
+    wrong, _ = _solve_mine(G.g1_qp_nonneg, scaling=scaling, obj_true=2.88, obj_true_tol=1e-3, max_iter=300)
+    assert loose.iter == plain.iter and tight.iter > plain.iter and wrong.status == "Max_iter_reached" and wrong.iter == 300
