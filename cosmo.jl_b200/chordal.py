@@ -33,6 +33,7 @@ from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
+from sortedcontainers import SortedList
 import scipy.sparse as sp
 
 from . import model as M
@@ -264,13 +265,19 @@ def reduced_clique_graph(cliques: List[set], seps: List[set]) -> Tuple[List[int]
     `seps` contribute their edges several times (the reference then *adds* the duplicate weights)."""
     rows: List[int] = []
     cols: List[int] = []
+    members: Dict[int, set] = {}
+    for k, c in enumerate(cliques):
+        for v in c:
+            members.setdefault(v, set()).add(k)
     for separator in sorted(seps, key=len, reverse=True):      # sort! is stable, as is sorted()
         if not separator:
             # the empty separator of a root would link every pair of cliques from different connected components
             # of the pattern (O(p^2) edges of weight n1^3 + n2^3 - (n1+n2)^3 < 0 that can never be merged and never
             # make an edge impermissible); they are left out, so a disconnected pattern keeps a forest
             continue
-        ind = [k for k, c in enumerate(cliques) if separator <= c]
+        # cliques that contain the separator, in index order (inverted index instead of a scan over all cliques)
+        holders = sorted((members[v] for v in separator), key=len)
+        ind = sorted(set.intersection(*holders)) if holders else []
         H: Dict[int, List[int]] = {v: [] for v in ind}
         for a in range(len(ind)):
             for b_ in range(a + 1, len(ind)):
@@ -317,6 +324,8 @@ class CliqueGraph:
         for r, c in zip(rows, cols):                             # sparse(rows, cols, weights): duplicates add up
             self.edges[(r, c)] = self.edges.get((r, c), 0.0) + _complexity_weight(self.snd[r], self.snd[c])
         self.edges = {e: w for e, w in self.edges.items() if w != 0.0}
+        # the candidate order of traverse(): weight descending, ties in CSC order (col, then row) -- kept incrementally
+        self._ranked = SortedList((-w, e[1], e[0]) for e, w in self.edges.items())
         self.adj: Dict[int, set] = {k: set() for k in range(self.num)}
         for (r, c) in self.edges:
             self.adj[r].add(c)
@@ -334,6 +343,13 @@ class CliqueGraph:
         return True
 
     def traverse(self):                                          # clique_merging.jl:242-259
+        for (_, c, r) in self._ranked:                           # = sortperm(weights, rev = true), stable in CSC order
+            if self.permissible((r, c)):
+                return (r, c)
+        return None
+
+    def traverse_by_sorting(self):
+        """the literal restatement (sort all edges at every call); kept as the cross-check of the incremental order"""
         order = self._csc()
         if not order:
             return None
@@ -343,6 +359,14 @@ class CliqueGraph:
                 return e
         return None
 
+    def _set_edge(self, key, w: float) -> None:
+        old = self.edges.pop(key, None)
+        if old is not None:
+            self._ranked.remove((-old, key[1], key[0]))
+        if w != 0.0:                                             # dropzeros!
+            self.edges[key] = w
+            self._ranked.add((-w, key[1], key[0]))
+
     def merge(self, edge) -> None:                              # merge_two_cliques! + update_strategy!
         c1, removed = edge
         self.snd[c1] |= self.snd[removed]
@@ -351,20 +375,15 @@ class CliqueGraph:
         neighbors = set(self.adj[c1])
         new_neighbors = self.adj[removed] - neighbors - {c1}
         for nb in (neighbors - {removed}) | new_neighbors:
-            w = _complexity_weight(self.snd[c1], self.snd[nb])
-            key = (max(c1, nb), min(c1, nb))
-            if w != 0.0:
-                self.edges[key] = w
-            else:
-                self.edges.pop(key, None)                      # dropzeros!
-        for key in [e for e in self.edges if removed in e]:
-            del self.edges[key]
+            self._set_edge((max(c1, nb), min(c1, nb)), _complexity_weight(self.snd[c1], self.snd[nb]))
+        for nb in self.adj[removed]:                           # every edge of `removed` (adj is a superset of edges)
+            self._set_edge((max(removed, nb), min(removed, nb)), 0.0)
         self.adj[c1] |= new_neighbors
         for nb in new_neighbors:
             self.adj[nb].add(c1)
+        for nb in self.adj[removed]:
+            self.adj[nb].discard(removed)
         del self.adj[removed]
-        for st in self.adj.values():
-            st.discard(removed)
 
     def run(self) -> None:                                      # _merge_cliques!, clique_merging.jl:112-133
         while self.num > 1:
@@ -466,8 +485,12 @@ def decompose(P, q, A, b, sets, merge: str = "parent_child", min_dim: int = 3):
         decomposable = isinstance(S, M.PsdConeTriangle) and S.sqrt_dim >= min_dim
         if decomposable:
             N = S.sqrt_dim
-            sub = Acoo_by_row[off:off + dim]
-            nz_rows = np.unique(np.concatenate([np.nonzero(np.diff(sub.indptr))[0], np.nonzero(b[off:off + dim])[0]]))
+            # rows of the cone that hold an entry of A or b -- straight from the row pointers (slicing the CSR matrix
+            # would copy a 50-million-row cone: C5 has N = 10 000)
+            ip = A.indptr
+            row_nnz = ip[off + 1:off + dim + 1] - ip[off:off + dim]
+            a_rows = np.nonzero(row_nnz)[0]
+            nz_rows = np.unique(np.concatenate([a_rows, np.nonzero(b[off:off + dim])[0]]))
             ii, jj = svec_to_ij(nz_rows)
             diag_rows = np.arange(N, dtype=np.int64) * (np.arange(N, dtype=np.int64) + 1) // 2 + np.arange(N)
             if len(np.union1d(nz_rows, diag_rows)) >= dim:   # dense pattern: keep the cone (chordal_decomposition.jl:53-60)
@@ -530,11 +553,12 @@ def decompose(P, q, A, b, sets, merge: str = "parent_child", min_dim: int = 3):
                 cols_new.append(np.array(ov_cols, dtype=np.int64))
                 vals_new.append(np.array(ov_vals))
             sets_new.append(M.PsdConeTriangle(nc * (nc + 1) // 2))
-        sub = Acoo_by_row[off:off + dim].tocoo()
-        mapped = np.array([owner[int(r)] for r in sub.row], dtype=np.int64) if sub.nnz else np.zeros(0, dtype=np.int64)
+        lo, hi = int(ip[off]), int(ip[off + dim])
+        sub_row = np.repeat(a_rows, row_nnz[a_rows])             # cone-local row of every entry, CSR order
+        mapped = np.array([owner[int(r)] for r in sub_row], dtype=np.int64) if hi > lo else np.zeros(0, dtype=np.int64)
         rows_new.append(mapped)
-        cols_new.append(sub.col)
-        vals_new.append(sub.data)
+        cols_new.append(A.indices[lo:hi].astype(np.int64))
+        vals_new.append(A.data[lo:hi].copy())
         bseg = np.zeros(row_ptr - starts[0])
         nzb = np.nonzero(b[off:off + dim])[0]
         for r in nzb:

@@ -293,3 +293,27 @@ def test_merge_strategies_give_valid_decompositions(merge):
     x, s, mu = chordal.reverse(info, dec.x, dec.s, -dec.y, complete_dual=True)
     assert np.allclose(x, ref.x, atol=2e-3 * max(1, np.abs(ref.x).max()))
     assert np.linalg.eigvalsh(chordal._svec_to_mat(-mu, nv)).min() > -1e-3
+
+
+@pytest.mark.parametrize("nv,deg,band,seed", [(60, 3.0, 6, 1), (200, 3.0, 20, 2), (150, 5.0, 12, 3), (120, 4.0, 30, 4), (80, 2.0, 40, 4)])
+def test_clique_graph_merge_incremental_order_equals_the_literal_restatement(nv, deg, band, seed):
+    """CliqueGraph keeps its candidate order (weight descending, ties in CSC order) incrementally; the literal
+    restatement of traverse (clique_merging.jl:242-259) sorts all edges at every step.  Both must pick the same edge at
+    every step of the merge, and the bookkeeping (edges, adjacency) must stay consistent."""
+    rows, cols, _ = cosmo_b200.problems.banded_random_graph(nv, deg, band, seed=seed)
+    tree0 = chordal.chordal_cliques(nv, rows, cols)
+    g = chordal.CliqueGraph([set(c.tolist()) for c in tree0.cliques], [set(x.tolist()) for x in tree0.sep])
+    steps = 0
+    while g.num > 1:
+        cand = g.traverse()
+        assert cand == g.traverse_by_sorting()
+        assert sorted((-w, e[1], e[0]) for e, w in g.edges.items()) == list(g._ranked)
+        assert all(e[0] in g.adj[e[1]] and e[1] in g.adj[e[0]] for e in g.edges)
+        if cand is None or g.edges[cand] < 0:
+            break
+        g.merge(cand)
+        steps += 1
+        assert cand[1] not in g.adj and not any(cand[1] in st for st in g.adj.values())
+        assert not any(cand[1] in e for e in g.edges)
+    assert steps > 0 or deg <= 2.0        # a very sparse pattern may offer no merge that saves work
+    assert _valid_clique_tree(g.clique_tree(tree0.order))
