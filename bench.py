@@ -201,9 +201,10 @@ def run_reference(a, rank, world):
 
 def main():
     a = parse_args()
-    # NCCL prints its version banner on STDOUT when NCCL_DEBUG=VERSION: keep stdout for the one JSON line
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION and at WARN (the GPU boxes export VERSION): keep
+    # stdout for the one JSON line.  An explicit INFO / TRACE is the caller's choice and stays.
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+        os.environ.pop("NCCL_DEBUG", None)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
