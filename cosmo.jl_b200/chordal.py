@@ -576,7 +576,7 @@ def decompose(P, q, A, b, sets, merge: str = "parent_child", min_dim: int = 3):
     return P2, q2, A2, b2, sets_new, info
 
 
-def psd_complete(Y: np.ndarray, tree: CliqueTree) -> np.ndarray:
+def psd_complete(Y: np.ndarray, tree: CliqueTree, assume_symmetric: bool = False) -> np.ndarray:
     """psd_complete! (chordal_decomposition.jl:262-311): fill the entries of the symmetric matrix `Y` that lie
     outside the cliques of `tree` so that the result is positive semidefinite (given that every clique block
     is).  Cliques are visited parents first; for clique k with separator alpha = C_k & C_parent and residual
@@ -584,7 +584,8 @@ def psd_complete(Y: np.ndarray, tree: CliqueTree) -> np.ndarray:
         Y[eta, nu] = Y[eta, alpha] Y[alpha, alpha]^-1 Y[alpha, nu]
     (pseudo-inverse when the separator block is singular, as the reference's try/catch does)."""
     W = np.array(Y, dtype=np.float64)
-    W = np.triu(W) + np.triu(W, 1).T
+    if not assume_symmetric:                 # the reference reads the upper triangle
+        W = np.triu(W) + np.triu(W, 1).T
     ncl = len(tree.cliques)
     children: List[List[int]] = [[] for _ in range(ncl)]
     roots = []
@@ -620,25 +621,23 @@ def psd_complete(Y: np.ndarray, tree: CliqueTree) -> np.ndarray:
 
 
 def _svec_to_mat(v: np.ndarray, N: int) -> np.ndarray:
-    """populate_upper_triangle!(X, v, 1/sqrt 2) + symmetrise (convexset.jl:432-442)"""
-    X = np.zeros((N, N))
-    iu = np.triu_indices(N)
-    # column-major upper triangle: (0,0), (0,1), (1,1), (0,2) ...
-    order = np.lexsort((iu[0], iu[1]))
-    X[iu[0][order], iu[1][order]] = v
-    X = X + np.triu(X, 1).T
-    off = ~np.eye(N, dtype=bool)
-    X[off] /= np.sqrt(2.0)
+    """populate_upper_triangle!(X, v, 1/sqrt 2) + symmetrise (convexset.jl:432-442).  The column-major upper triangle
+    (0,0), (0,1), (1,1), (0,2) ... is the row-major lower triangle of the transpose: one masked assignment."""
+    L = np.zeros((N, N))
+    L[np.tri(N, dtype=bool)] = v
+    d = np.diagonal(L).copy()
+    X = L + L.T
+    X *= 1.0 / np.sqrt(2.0)
+    np.fill_diagonal(X, d)
     return X
 
 
 def _mat_to_svec(X: np.ndarray) -> np.ndarray:
+    """extract_upper_triangle!(X, v, sqrt 2) of a symmetric X: X[c, r] for r = 0.., c <= r, i.e. its row-major lower triangle"""
     N = X.shape[0]
-    iu = np.triu_indices(N)
-    order = np.lexsort((iu[0], iu[1]))
-    i, j = iu[0][order], iu[1][order]
-    v = X[i, j].copy()
-    v[i != j] *= np.sqrt(2.0)
+    v = X[np.tri(N, dtype=bool)] * np.sqrt(2.0)
+    j = np.arange(N, dtype=np.int64)
+    v[j * (j + 1) // 2 + j] = np.diagonal(X)
     return v
 
 
@@ -668,6 +667,6 @@ def reverse(info: DecompositionInfo, x2, s2, mu2, complete_dual: bool = False):
             S = info.sets_orig[k]
             N = S.sqrt_dim
             seg = slice(off, off + S.dim)
-            Y = psd_complete(_svec_to_mat(-mu[seg], N), info.trees[k])
+            Y = psd_complete(_svec_to_mat(-mu[seg], N), info.trees[k], assume_symmetric=True)
             mu[seg] = -_mat_to_svec(Y)
     return x, s, mu
