@@ -582,10 +582,77 @@ def psd_complete(Y: np.ndarray, tree: CliqueTree, assume_symmetric: bool = False
     is).  Cliques are visited parents first; for clique k with separator alpha = C_k & C_parent and residual
     nu = C_k minus alpha, the unknown entries between nu and eta = (vertices of the cliques visited so far) minus C_k are
         Y[eta, nu] = Y[eta, alpha] Y[alpha, alpha]^-1 Y[alpha, nu]
-    (pseudo-inverse when the separator block is singular, as the reference's try/catch does)."""
+    (pseudo-inverse when the separator block is singular, as the reference's try/catch does).
+
+    The vertices are renumbered in the order the traversal first meets them: the visited set is then a leading block,
+    the residual of the current clique the next few indices, and the update is one product of a contiguous row block
+    (rows of alpha are recomputed to themselves and restored, so known entries stay bit-identical)."""
     W = np.array(Y, dtype=np.float64)
     if not assume_symmetric:                 # the reference reads the upper triangle
         W = np.triu(W) + np.triu(W, 1).T
+    N = W.shape[0]
+    ncl = len(tree.cliques)
+    children: List[List[int]] = [[] for _ in range(ncl)]
+    roots = []
+    for k, p in enumerate(tree.parent):
+        (children[p] if p >= 0 else roots).append(k)
+    # traversal order (parents first) and the renumbering it induces
+    order_k: List[int] = []
+    stack = list(reversed(roots))
+    while stack:
+        k = stack.pop()
+        order_k.append(k)
+        stack.extend(reversed(children[k]))
+    new_of = np.full(N, -1, dtype=np.int64)
+    nxt = 0
+    residuals: Dict[int, np.ndarray] = {}
+    for k in order_k:
+        c = np.asarray(tree.cliques[k], dtype=np.int64)
+        fresh = c[new_of[c] < 0]
+        residuals[k] = fresh
+        new_of[fresh] = np.arange(nxt, nxt + len(fresh))
+        nxt += len(fresh)
+    rest = np.nonzero(new_of < 0)[0]                       # vertices in no clique (cannot happen for a clique tree)
+    new_of[rest] = np.arange(nxt, nxt + len(rest))
+    perm = np.argsort(new_of)                              # perm[new] = old
+    W = W[np.ix_(perm, perm)]
+    seen = 0
+    for k in order_k:
+        nu_old = residuals[k]
+        nn = len(nu_old)
+        alpha_old = tree.sep[k] if tree.parent[k] >= 0 else np.zeros(0, dtype=np.int64)
+        # the reference's nu = C_k minus alpha; vertices of alpha are always met before (they belong to the parent)
+        lo, hi = seen, seen + nn                           # new indices of nu
+        if seen and nn:
+            if len(alpha_old):
+                al = new_of[np.asarray(alpha_old, dtype=np.int64)]
+                Waa = W[np.ix_(al, al)]
+                Wan = W[al, lo:hi].copy()
+                try:
+                    Z = np.linalg.solve(Waa, Wan)
+                    if not np.all(np.isfinite(Z)):
+                        raise np.linalg.LinAlgError
+                except np.linalg.LinAlgError:
+                    Z = np.linalg.pinv(Waa) @ Wan
+                blk = W[:seen, al] @ Z
+                blk[al, :] = Wan                           # known entries (alpha x nu lies inside the clique) stay exact
+            else:   # a new connected component: no coupling with what was completed before
+                blk = np.zeros((seen, nn))
+            # entries between nu and the OTHER members of its own clique are known as well: keep them
+            c_new = new_of[np.asarray(tree.cliques[k], dtype=np.int64)]
+            c_seen = c_new[c_new < seen]
+            blk[c_seen, :] = W[c_seen, lo:hi]
+            W[:seen, lo:hi] = blk
+            W[lo:hi, :seen] = blk.T
+        seen = hi
+    inv = new_of                                           # old -> new
+    return W[np.ix_(inv, inv)]
+
+
+def _psd_complete_reference(Y: np.ndarray, tree: CliqueTree) -> np.ndarray:
+    """the literal restatement (index sets per clique); kept as the cross-check of the renumbered version"""
+    W = np.array(Y, dtype=np.float64)
+    W = np.triu(W) + np.triu(W, 1).T
     ncl = len(tree.cliques)
     children: List[List[int]] = [[] for _ in range(ncl)]
     roots = []
@@ -611,7 +678,7 @@ def psd_complete(Y: np.ndarray, tree: CliqueTree, assume_symmetric: bool = False
                 except np.linalg.LinAlgError:
                     Z = np.linalg.pinv(Waa) @ Wan
                 blk = W[np.ix_(eta, alpha)] @ Z
-            else:   # a new connected component: no coupling with what was completed before
+            else:
                 blk = np.zeros((len(eta), len(nu)))
             W[np.ix_(eta, nu)] = blk
             W[np.ix_(nu, eta)] = blk.T

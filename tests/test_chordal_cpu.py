@@ -317,3 +317,29 @@ def test_clique_graph_merge_incremental_order_equals_the_literal_restatement(nv,
         assert not any(cand[1] in e for e in g.edges)
     assert steps > 0 or deg <= 2.0        # a very sparse pattern may offer no merge that saves work
     assert _valid_clique_tree(g.clique_tree(tree0.order))
+
+
+@pytest.mark.parametrize("nv,deg,band,seed", [(40, 3.0, 5, 4), (200, 3.0, 20, 2), (150, 5.0, 12, 3)])
+@pytest.mark.parametrize("merge", ["none", "parent_child", "clique_graph"])
+def test_psd_complete_renumbered_equals_the_literal_restatement(nv, deg, band, seed, merge):
+    """psd_complete works on a renumbered matrix (visited vertices = a leading block); the literal restatement of
+    psd_complete! (chordal_decomposition.jl:262-311) gathers index sets per clique.  Same completion, known entries
+    bit-identical, result positive definite."""
+    rows, cols, _ = cosmo_b200.problems.banded_random_graph(nv, deg, band, seed=seed)
+    tree = chordal.chordal_cliques(nv, rows, cols)
+    if merge == "parent_child":
+        tree = chordal.parent_child_merge(tree)
+    elif merge == "clique_graph":
+        tree = chordal.clique_graph_merge(tree)
+    rng = np.random.default_rng(seed)
+    B = rng.standard_normal((nv, nv))
+    X = B @ B.T + nv * np.eye(nv)
+    mask = np.zeros((nv, nv), dtype=bool)
+    for c in tree.cliques:
+        mask[np.ix_(c, c)] = True
+    Y0 = np.where(mask, X, 0.0)
+    got = chordal.psd_complete(Y0, tree)
+    ref = chordal._psd_complete_reference(Y0, tree)
+    assert np.array_equal(got[mask], X[mask])
+    assert np.max(np.abs(got - ref)) <= 1e-12 * np.max(np.abs(ref))
+    assert np.array_equal(got, got.T) and np.linalg.eigvalsh(got).min() > 0
